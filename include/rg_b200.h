@@ -1,0 +1,107 @@
+/* librg_b200.so — C ABI of the B200-native robust two-view / pose estimation hot path.
+ *
+ * This header is the drop-in boundary: every entry point is plain C (pointers + sizes, no C++/torch types) and is
+ * what a reference-side FFI (Python ctypes) binds.  The reference project has no FFI of its own:
+ * its boundary is a set of Python functions in flat modules.  Each entry point below names the reference function
+ * (file:line in bioengstrom/tsbb15-3d-reconstruction-project) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on failure; rg_last_error() gives the text
+ *     (-1 CUDA error, -2 invalid argument, -3 no sm_100 device, -4 internal overflow);
+ *   - there is NO CPU fallback: without a Blackwell (sm_100) device rg_init fails with -3;
+ *   - "_host" entry points take HOST buffers, do the H2D / D2H copies on `stream` and synchronise it before returning;
+ *     "_dev" entry points take DEVICE buffers (offset tables stay on the host) and are asynchronous on `stream`;
+ *   - all matrices are row-major doubles; correspondences of a pair are an (N, 4) array (x0, x1, y0, y1) where
+ *     x = image-1 point and y = image-2 point of the reference's convention x^T F y = 0 (lab3.py:196);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); a context is bound to one device and may be
+ *     used from one host thread at a time.
+ */
+#ifndef RG_B200_H
+#define RG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enumerations (ABI values) -------------------------------------------------------------------------------- */
+#define RG_MODE_EPI_MAX 0   /* max(|d1|,|d2|) < thr : the reference criterion, fun.py:316-317 */
+#define RG_MODE_SAMPSON 1   /* Sampson distance < thr : extension named by the north star, not in the reference */
+#define RG_TIE_FIRST 0      /* ties on the inlier count: first hypothesis wins (strict >, fun.py:320) */
+#define RG_TIE_REFERENCE 1  /* replay of the reference's tie rule norm(std(d_best)) > norm(d_new), fun.py:324-328 */
+#define RG_SOLVER_QR 0      /* Householder null vector, one hypothesis per thread (default) */
+#define RG_SOLVER_JACOBI 1  /* register-resident one-sided Jacobi SVD, one hypothesis per 16-lane group */
+#define RG_SCORE_FP32_GUARDED 0 /* FP32 fma.rn.f32x2 scorer + rigorous guard band re-evaluated in FP64 (exact counts) */
+#define RG_SCORE_FP64 1         /* every evaluation in FP64 with the reference formula */
+
+/* ---- context -------------------------------------------------------------------------------------------------- */
+int rg_abi_version(void);
+const char* rg_last_error(void);
+int rg_init(int device, void** out_ctx);
+int rg_shutdown(void* ctx);
+int rg_device_sm_count(void* ctx);
+
+/* Pipe micro-benchmarks on the context's device (roofline denominators for bench.py):
+ * out6 = {FFMA GFMA/s, FFMA2 GFMA/s, scalar-mix Gevals/s, packed-mix Gevals/s, DFMA GFMA/s, SM count}. */
+int rg_microbench_run(double* out6, void* stream);
+
+/* out8 = {recheck groups pushed, band evaluations redone in FP64, decisions changed, work-list overflow flag,
+ *         0, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
+int rg_get_last_stats(void* ctx, void* stream, long long* out8);
+
+/* ---- F-matrix RANSAC: replaces the loop of fun.getFFromLabCode (fun.py:303-328), which calls
+ *      lab3.fmatrix_stls (lab3.py:269-329) and lab3.fmatrix_residuals (lab3.py:188-227) once per trial ------------- */
+/* Batched over P image pairs (CSR layout).  pair_off[P+1] / hyp_off[P+1] are HOST int32 prefix tables.
+ *   pts64   : (pair_off[P], 4) doubles        idx : (hyp_off[P], 8) int32 sample indices local to the pair (host-drawn)
+ * Outputs per pair: best_idx (index of the selected hypothesis inside the pair, -1 if no hypothesis has an inlier),
+ * best_count, best_F (3x3); mask (pair_off[P] bytes, optional) = inlier set of the selected hypothesis. */
+int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                    const int32_t* idx_dev, const int32_t* hyp_off_host, double thr, int mode, int tie_mode, int solver,
+                    int score_path, int32_t* best_idx_dev, int32_t* best_count_dev, double* best_F_dev,
+                    unsigned char* mask_dev /* may be NULL */);
+/* per-hypothesis results of the last call on this context (device pointers, valid until the next call):
+ * counts (hyp_off[P] int32), F_all (hyp_off[P] x 9 doubles), flags (bit0: rank-deficient sample, bit1: non-finite F) */
+int rg_f_last_hypotheses_dev(void* ctx, const int32_t** counts_dev, const double** F_all_dev,
+                             const unsigned char** flags_dev);
+/* Same with host buffers; counts / F_all / flags / mask are optional (NULL = not copied back). */
+int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const int32_t* idx,
+                     const int32_t* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path,
+                     int32_t* best_idx, int32_t* best_count, double* best_F, unsigned char* mask, int32_t* counts,
+                     double* F_all, unsigned char* flags);
+
+/* Stage entry points (same kernels, one pair):
+ * 8-point solve of H samples — lab3.fmatrix_stls on 8 points (lab3.py:269-329) */
+int rg_f8pt_solve_host(void* ctx, void* stream, int N, const double* pts64, int H, const int32_t* idx, int solver,
+                       double* F_all, unsigned char* flags /* may be NULL */);
+/* inlier counts of H caller-supplied F over N correspondences — fmatrix_residuals + threshold (fun.py:315-317) */
+int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64, int H, const double* F_all, double thr,
+                            int mode, int score_path, int32_t* counts);
+/* lab3.fmatrix_residuals (lab3.py:188-227): x, y are (2, N) row-major, out is (2, N) signed distances */
+int rg_fmatrix_residuals_host(void* ctx, void* stream, const double* F9, int N, const double* x, const double* y,
+                              double* out);
+/* lab3.fmatrix_stls for any N >= 8 (lab3.py:269-329): pl, pr are (2, N) row-major */
+int rg_fmatrix_stls_host(void* ctx, void* stream, int N, const double* pl, const double* pr, double* F9);
+
+/* ---- PnP-RANSAC: restates ransac.ransac_robust (ransac.py:37-113, does not run in the reference) with the DLT pose
+ *      solver specified in pnp.py:132-152 (pnp.pnp_minimize, body unfinished in the reference) --------------------- */
+/* One view.  X : (N, 3) world points, y : (N, 2) C-normalised image points, idx : (H, n) sample indices, n in [6, 8].
+ * Inlier: squared reprojection distance e <= thr2 (inclusive, ransac.py:104).  N_sel <= N: only the first N_sel
+ * correspondences vote in the selection (the reference selects on D_med, ransac.py:108); mask covers all N.
+ * Outputs: best_idx, best_count, R (3x3), t (3), mask (N bytes, optional), counts (H, optional), poses (H x 12, opt). */
+int rg_pnp_ransac_host(void* ctx, void* stream, int N, int N_sel, const double* X, const double* y, int H, int n,
+                       const int32_t* idx, double thr2, int score_path, int32_t* best_idx, int32_t* best_count, double* R,
+                       double* t, unsigned char* mask, int32_t* counts, double* poses, unsigned char* flags);
+int rg_pnp_ransac_dev(void* ctx, void* stream, int N, int N_sel, const double* X_dev, const double* y_dev, int H, int n,
+                      const int32_t* idx_dev, double thr2, int score_path, int32_t* best_idx_dev, int32_t* best_count_dev,
+                      double* Rt_dev /* 12 doubles: R row-major then t */, unsigned char* mask_dev);
+/* pnp.pnp_minimize(_3d_pts, img_pts, m) (pnp.py:132-152) for any m >= 6: X (m, 3), y (m, 2) -> R (3x3), t (3) */
+int rg_pnp_minimize_host(void* ctx, void* stream, int m, const double* X, const double* y, double* R, double* t);
+/* reprojection scoring of H caller-supplied poses (H x 12: R row-major then t) — ransac.py:96-105 */
+int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, const double* y, int H, const double* poses,
+                            double thr2, int score_path, int32_t* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RG_B200_H */

@@ -1,0 +1,126 @@
+"""ctypes binding of librg_b200.so (the C ABI declared in include/rg_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or the machine has no sm_100 GPU, every
+product entry point raises.  Build the library with ``python __graft_entry__.py`` (or ``build.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librg_b200.so")
+
+MODE_EPI_MAX, MODE_SAMPSON = 0, 1
+TIE_FIRST, TIE_REFERENCE = 0, 1
+SOLVER_QR, SOLVER_JACOBI = 0, 1
+SCORE_FP32_GUARDED, SCORE_FP64 = 0, 1
+
+_vp = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+_pu8 = C.POINTER(C.c_ubyte)
+_pll = C.POINTER(C.c_longlong)
+
+# name -> (restype, argtypes); mirrors include/rg_b200.h one to one (tests check every symbol is exported)
+SIGNATURES = {
+    "rg_abi_version": (_i, []),
+    "rg_last_error": (C.c_char_p, []),
+    "rg_init": (_i, [_i, C.POINTER(_vp)]),
+    "rg_shutdown": (_i, [_vp]),
+    "rg_device_sm_count": (_i, [_vp]),
+    "rg_microbench_run": (_i, [_pd, _vp]),
+    "rg_get_last_stats": (_i, [_vp, _vp, _pll]),
+    "rg_f_ransac_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "rg_f_last_hypotheses_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "rg_f_ransac_host": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_f8pt_solve_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "rg_epi_score_count_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _i, _i, _vp]),
+    "rg_fmatrix_residuals_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rg_fmatrix_stls_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "rg_pnp_ransac_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_pnp_ransac_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp]),
+    "rg_pnp_minimize_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rg_pnp_score_count_host": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _d, _i, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_contexts: dict[int, int] = {}
+
+
+class RGError(RuntimeError):
+    """A librg_b200 call failed (message from rg_last_error)."""
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RGError(
+                    f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                    "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().rg_last_error()
+        text = msg.decode("utf-8", "replace") if msg else ""
+        if rc == -2:
+            raise ValueError(f"librg_b200: {text}")
+        raise RGError(f"librg_b200 call failed (code {rc}): {text}")
+
+
+def context(device: int | None = None) -> int:
+    """Lazily created per-device context handle (an opaque pointer as int)."""
+    lib = load_library()
+    if device is None:
+        device = int(os.environ.get("RG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _lock:
+        if device not in _contexts:
+            h = _vp()
+            check(lib.rg_init(int(device), C.byref(h)))
+            _contexts[device] = h.value
+        return _contexts[device]
+
+
+def shutdown_all() -> None:
+    lib = load_library()
+    with _lock:
+        for dev, h in list(_contexts.items()):
+            lib.rg_shutdown(_vp(h))
+            del _contexts[dev]
+
+
+def ptr(a) -> int | None:
+    """Raw address of a numpy array / torch tensor / int; None stays NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    raise TypeError(f"cannot take the address of {type(a)!r}")
+
+
+def as_i32(a) -> "C.Array":
+    arr = np.ascontiguousarray(a, dtype=np.int32)
+    return arr, arr.ctypes.data_as(_pi)

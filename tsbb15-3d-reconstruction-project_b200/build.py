@@ -1,0 +1,43 @@
+"""Builds librg_b200.so (sm_100a) in-tree with nvcc.  No torch involved: the boundary is a plain C ABI."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librg_b200.so")
+SOURCES = ["ctx.cu", "f_api.cu", "pnp_api.cu", "microbench.cu"]
+HEADERS = ["common.cuh", "f_kernels.cuh", "jacobi.cuh", "pnp_kernels.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and os.path.getmtime(p) > t:
+            return True
+    return os.path.getmtime(os.path.abspath(__file__)) > t
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.isfile(os.path.join(CSRC, f))]
+    cmd = [nvcc] + NVCC_FLAGS + srcs + ["-o", LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building librg_b200.so")
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+        f.write(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

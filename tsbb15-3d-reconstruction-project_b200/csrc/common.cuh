@@ -1,0 +1,170 @@
+// Shared declarations for librg_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+namespace rg {
+
+// ---------------------------------------------------------------------------------------------
+// status codes returned through the C ABI (0 = ok, negative = failure; text via rg_last_error())
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    RG_OK = 0,
+    RG_ERR_CUDA = -1,        // a CUDA runtime call failed
+    RG_ERR_ARG = -2,         // invalid argument (null pointer, negative size, sample size unsupported ...)
+    RG_ERR_NO_DEVICE = -3,   // no sm_100 device / wrong architecture
+    RG_ERR_OVERFLOW = -4,    // internal work-list overflow (never silently ignored)
+};
+
+void set_error(const char* fmt, ...);
+
+#define RG_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::rg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return ::rg::RG_ERR_CUDA;                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define RG_CHECK_ARG(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::rg::set_error("invalid argument: %s", msg);         \
+            return ::rg::RG_ERR_ARG;                              \
+        }                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// scoring criteria / selection modes (values are part of the ABI, see include/rg_b200.h)
+// ---------------------------------------------------------------------------------------------
+enum : int { MODE_EPI_MAX = 0, MODE_SAMPSON = 1 };
+enum : int { TIE_FIRST = 0, TIE_REFERENCE = 1 };
+enum : int { SOLVER_QR = 0, SOLVER_JACOBI = 1 };
+enum : int { SCORE_FP32_GUARDED = 0, SCORE_FP64 = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// device-side records
+// ---------------------------------------------------------------------------------------------
+// Per hypothesis, FP32 scorer input: F~ = M1^T F M2 scaled to unit weighted abs-sum, plus the
+// rigorous rounding-error band G (see DESIGN.md "guard band").  48 bytes, 16-byte aligned.
+struct __align__(16) Hyp32 {
+    float f[9];
+    float G;
+    float pad0, pad1;
+};
+static_assert(sizeof(Hyp32) == 48, "Hyp32 layout");
+
+// PnP hypothesis for the FP32 scorer: rows P0,P1,P2 (3x4 each, in the normalised frame), band G.
+struct __align__(16) Pose32 {
+    float p[12];
+    float G;
+    float pad0, pad1, pad2;
+};
+static_assert(sizeof(Pose32) == 64, "Pose32 layout");
+
+constexpr int kSub = 32;            // points per guard-band bookkeeping group (FP32 scorer)
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+// largest p with off[p] <= i  (off is non-decreasing, off[0] = 0, off[P] = total)
+__device__ __forceinline__ int find_segment(const int* __restrict__ off, int P, int i) {
+    int lo = 0, hi = P;           // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP) ----------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy, completion signalled on the mbarrier (bytes % 16 == 0, 16-B aligned)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// context: one per device, owns grow-only workspaces so steady-state calls never cudaMalloc
+// ---------------------------------------------------------------------------------------------
+struct Buffer {
+    void*  ptr = nullptr;
+    size_t cap = 0;
+};
+
+// Per image pair: integer geometry of the batch (filled on the host, uploaded once per call) and the
+// FP32 scoring frame (filled on the device by the prepare kernels).
+struct PairInfo {
+    int pt_off, n;             // offset / count in the caller's pts64 array (points)
+    int pt_off32, n_pad;       // offset / count in the normalised FP32 copy (points, multiples of kSub)
+    int hyp_off, H;            // offset / count in the hypothesis arrays
+    int item_off, nsplit;      // scorer work items of this pair: [item_off, item_off + ceil(H/kHypPerBlock)*nsplit)
+    int groups_per_split;      // kSub-point groups handled by one item
+    int pad0;
+    // frame of the FP32 scorer: x~ = (x - c1)/thr, y~ = (y - c2)/thr  => threshold is exactly 1, |x~|,|y~| <= B
+    double c1x, c1y, c2x, c2y;
+    double thr, B;
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 0;
+    // device workspaces (grow-only)
+    Buffer pair_info, bbox, pts32, F64, hyp32, flags, counts, worklist, stats, best, tie_stats;
+    Buffer d_in_a, d_in_b, d_in_c;                 // device copies of host inputs (host-buffer entry points)
+    Buffer d_out_a, d_out_b, d_out_c, d_out_d;     // device outputs of host-buffer entry points
+    Buffer pose64, pose32, X32;                    // PnP path
+    // pinned host staging for the small per-call tables and the statistics read-back
+    Buffer h_stage, h_stats;
+    cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage
+    long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+int ensure_pinned(Buffer& b, size_t bytes);
+void release_pinned(Buffer& b);
+int ensure(Buffer& b, size_t bytes);      // grow-only cudaMalloc
+void release(Buffer& b);
+
+}  // namespace rg

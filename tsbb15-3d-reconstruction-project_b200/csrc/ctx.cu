@@ -1,0 +1,108 @@
+// Context / error plumbing of librg_b200.so.
+#include "common.cuh"
+#include <cstdarg>
+#include <mutex>
+
+namespace rg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ensure(Buffer& b, size_t bytes) {
+    if (bytes <= b.cap) return RG_OK;
+    size_t want = bytes + bytes / 4 + 256;       // head-room: ragged batches do not realloc every call
+    if (b.ptr) {
+        RG_CUDA(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.cap = 0;
+    }
+    RG_CUDA(cudaMalloc(&b.ptr, want));
+    b.cap = want;
+    return RG_OK;
+}
+
+int ensure_pinned(Buffer& b, size_t bytes) {
+    if (bytes <= b.cap) return RG_OK;
+    size_t want = bytes + bytes / 4 + 256;
+    if (b.ptr) {
+        RG_CUDA(cudaFreeHost(b.ptr));
+        b.ptr = nullptr;
+        b.cap = 0;
+    }
+    RG_CUDA(cudaMallocHost(&b.ptr, want));
+    b.cap = want;
+    return RG_OK;
+}
+
+void release(Buffer& b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+}
+
+void release_pinned(Buffer& b) {
+    if (b.ptr) cudaFreeHost(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" {
+
+const char* rg_last_error(void) { return g_err; }
+
+int rg_abi_version(void) { return 1; }
+
+int rg_init(int device, void** out_ctx) {
+    RG_CHECK_ARG(out_ctx != nullptr, "out_ctx is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no CUDA device visible (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return RG_ERR_NO_DEVICE;
+    }
+    RG_CHECK_ARG(device >= 0 && device < n, "device index out of range");
+    cudaDeviceProp prop;
+    RG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; librg_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return RG_ERR_NO_DEVICE;
+    }
+    RG_CUDA(cudaSetDevice(device));
+    Ctx* c = new Ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    RG_CUDA(cudaEventCreateWithFlags(&c->staging_free, cudaEventDisableTiming));
+    *out_ctx = c;
+    return RG_OK;
+}
+
+int rg_shutdown(void* ctx) {
+    if (!ctx) return RG_OK;
+    Ctx* c = (Ctx*)ctx;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->worklist,
+                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_out_a, &c->d_out_b,
+                      &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
+        release(*b);
+    release_pinned(c->h_stage);
+    release_pinned(c->h_stats);
+    if (c->staging_free) cudaEventDestroy(c->staging_free);
+    delete c;
+    return RG_OK;
+}
+
+int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,866 @@
+// Device code of the F-matrix RANSAC path (sm_100a).
+//
+// Reference behaviour being reproduced (paths relative to the reference root):
+//   fun.py:303-328   RANSAC loop: sample 8 -> fmatrix_stls -> fmatrix_residuals on all N -> max|d| < thr -> best
+//   lab3.py:269-329  fmatrix_stls (Hartley scaling, A = [Xx Xy X Yx Yy Y x y 1], null vector, rank 2, denormalise)
+//   lab3.py:188-227  fmatrix_residuals (signed point-to-epipolar-line distances in both images)
+//
+// Kernels (launch order of one batched call):
+//   f_bbox_init / f_bbox / f_frame / f_normalise   per-pair FP32 scoring frame + NaN-padded packed FP32 points
+//   f8_solve_qr (or f8_solve_jacobi)               one hypothesis per thread (or 16-lane group), FP64
+//   f_score_packed                                 FP32 fma.rn.f32x2 scorer, 2 hypotheses x 2 points per thread-step
+//   f_fixup                                        FP64 re-evaluation of guard-band groups -> exact counts
+//   f_argmax / f_tie_stats / f_tie_resolve / f_mask   selection + winner's inlier mask (FP64)
+#pragma once
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kScoreThreads = 256;
+constexpr int kHypPerThread = 2;
+constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
+constexpr int kChunkPts     = 1024;                            // points per shared-memory stage (16 KB)
+constexpr int kStages       = 2;
+
+// ------------------------------------------------------------------------------------------------
+// exact (FP64) criterion, same formula as lab3.py:213-227 + fun.py:316-317
+// ------------------------------------------------------------------------------------------------
+// returns d = max(|res1|, |res2|) (EPI_MAX) or the Sampson distance; NaN propagates like numpy.
+__device__ __forceinline__ double epi_dist64(const double* __restrict__ F, double x0, double x1, double y0, double y1,
+                                             int mode) {
+    const double l1x = F[0] * y0 + F[1] * y1 + F[2];
+    const double l1y = F[3] * y0 + F[4] * y1 + F[5];
+    const double l1z = F[6] * y0 + F[7] * y1 + F[8];
+    const double l2x = F[0] * x0 + F[3] * x1 + F[6];
+    const double l2y = F[1] * x0 + F[4] * x1 + F[7];
+    const double l2z = F[2] * x0 + F[5] * x1 + F[8];
+    const double s1 = l1x * l1x + l1y * l1y;
+    const double s2 = l2x * l2x + l2y * l2y;
+    const double r1 = l1x * x0 + l1y * x1 + l1z;
+    if (mode == MODE_SAMPSON) return sqrt(r1 * r1 / (s1 + s2));
+    const double r2 = l2x * y0 + l2y * y1 + l2z;
+    const double d1 = fabs(r1 / sqrt(s1));
+    const double d2 = fabs(r2 / sqrt(s2));
+    // np.max propagates NaN (fmax would drop it)
+    if (d1 != d1) return d1;
+    if (d2 != d2) return d2;
+    return d1 > d2 ? d1 : d2;
+}
+
+__device__ __forceinline__ int epi_inlier64(const double* __restrict__ F, double x0, double x1, double y0, double y1,
+                                            double thr, int mode) {
+    return epi_dist64(F, x0, x1, y0, y1, mode) < thr ? 1 : 0;   // strict <, NaN -> outlier (fun.py:317)
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 criterion in the pair's normalised frame (threshold == 1):  q = r^2 - min(s1, s2)  (< 0 <=> inlier)
+// Scalar form; op-for-op the same IEEE sequence as the packed form used by the hot kernel.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ float epi_q32(const float* __restrict__ f, float x0, float x1, float y0, float y1) {
+    const float l1x = __fmaf_rn(f[0], y0, __fmaf_rn(f[1], y1, f[2]));
+    const float l1y = __fmaf_rn(f[3], y0, __fmaf_rn(f[4], y1, f[5]));
+    const float l1z = __fmaf_rn(f[6], y0, __fmaf_rn(f[7], y1, f[8]));
+    const float r   = __fmaf_rn(l1x, x0, __fmaf_rn(l1y, x1, l1z));
+    const float l2x = __fmaf_rn(f[0], x0, __fmaf_rn(f[3], x1, f[6]));
+    const float l2y = __fmaf_rn(f[1], x0, __fmaf_rn(f[4], x1, f[7]));
+    const float s1  = __fmaf_rn(l1x, l1x, __fmul_rn(l1y, l1y));
+    const float s2  = __fmaf_rn(l2x, l2x, __fmul_rn(l2y, l2y));
+    const float m   = (MODE == MODE_SAMPSON) ? __fadd_rn(s1, s2) : fminf(s1, s2);
+    return __fmaf_rn(r, r, -m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bounding boxes (FP32, rounded outwards) via ordered-int atomics
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2key(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+__global__ void f_bbox_init(int* __restrict__ bbox, int P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P * 8) bbox[i] = ((i & 7) < 4) ? 0x7FFFFFFF : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(256) f_bbox(const double4* __restrict__ pts, const PairInfo* __restrict__ pi,
+                                               int* __restrict__ bbox) {
+    const int p = blockIdx.y;
+    const PairInfo info = pi[p];
+    float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < info.n; i += gridDim.x * blockDim.x) {
+        const double4 v = pts[info.pt_off + i];
+        const double c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (isfinite(c[k])) {      // non-finite input can never be an inlier; keep it out of the frame
+                mn[k] = fminf(mn[k], __double2float_rd(c[k]));
+                mx[k] = fmaxf(mx[k], __double2float_ru(c[k]));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicMin(&bbox[p * 8 + k], f2key(mn[k]));
+            atomicMax(&bbox[p * 8 + 4 + k], f2key(mx[k]));
+        }
+    }
+}
+
+__global__ void f_frame(PairInfo* __restrict__ pi, const int* __restrict__ bbox, int P, double thr) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double c[4], half = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        float lo = key2f(bbox[p * 8 + k]), hi = key2f(bbox[p * 8 + 4 + k]);
+        if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }          // empty pair or all points non-finite
+        c[k] = 0.5 * ((double)lo + (double)hi);
+        half = fmax(half, fmax((double)hi - c[k], c[k] - (double)lo));
+    }
+    PairInfo& o = pi[p];
+    o.c1x = c[0]; o.c1y = c[1]; o.c2x = c[2]; o.c2y = c[3];
+    o.thr = thr;
+    // bound on |normalised coordinate| with head-room for the FP64 division and FP32 rounding
+    o.B = (half / thr) * (1.0 + 1e-6) + 1e-30;
+}
+
+// FP32 copy in the scoring frame, laid out for the packed scorer: point pair (a, b) occupies 32 bytes
+//   [x0a x0b x1a x1b] [y0a y0b y1a y1b]
+// Points beyond n (padding up to a multiple of kSub) are NaN: they can never count and never flag.
+__global__ void __launch_bounds__(256) f_normalise(const double4* __restrict__ pts, const PairInfo* __restrict__ pi,
+                                                    float4* __restrict__ pts32) {
+    const int p = blockIdx.y;
+    const PairInfo info = pi[p];
+    const float qnan = __int_as_float(0x7FFFFFFF);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < info.n_pad / 2; j += gridDim.x * blockDim.x) {
+        float a[4], b[4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = 2 * j + s;
+            float* dst = s ? b : a;
+            if (i < info.n) {
+                const double4 v = pts[info.pt_off + i];
+                dst[0] = (float)((v.x - info.c1x) / info.thr);
+                dst[1] = (float)((v.y - info.c1y) / info.thr);
+                dst[2] = (float)((v.z - info.c2x) / info.thr);
+                dst[3] = (float)((v.w - info.c2y) / info.thr);
+            } else {
+                dst[0] = dst[1] = dst[2] = dst[3] = qnan;
+            }
+        }
+        float4* out = pts32 + (size_t)(info.pt_off32 / 2 + j) * 2;
+        out[0] = make_float4(a[0], b[0], a[1], b[1]);
+        out[1] = make_float4(a[2], b[2], a[3], b[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// F (pixel frame, FP64) -> Hyp32 (normalised frame, FP32) + rigorous rounding band G
+// ------------------------------------------------------------------------------------------------
+// Derivation in DESIGN.md ("guard band").  eps = 2^-24.  With F~ scaled so that
+//   sum_ij |f_ij| w_i w_j = 1,  w = (B, B, 1)
+// every partial sum of r = x~^T F~ y~ is bounded by 1, |l1x|<=rho0, |l1y|<=rho1, |l2x|<=kap0, |l2y|<=kap1 and
+//   |q^ - q| <= 2 sqrt(Mb) 8eps + 64 eps^2 + 10 eps Smax + 2 eps Mb      whenever the decision could flip,
+// where S1 = rho0^2+rho1^2, S2 = kap0^2+kap1^2, Mb = min(S1,S2) (EPI) or S1+S2 (Sampson), Smax likewise.
+template <int MODE>
+__device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const PairInfo& fr, Hyp32* __restrict__ out) {
+    const double t = fr.thr, B = fr.B;
+    double g[9], ft[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g[3 * i + 0] = F[3 * i + 0] * t;
+        g[3 * i + 1] = F[3 * i + 1] * t;
+        g[3 * i + 2] = F[3 * i + 0] * fr.c2x + F[3 * i + 1] * fr.c2y + F[3 * i + 2];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ft[0 + j] = t * g[0 + j];
+        ft[3 + j] = t * g[3 + j];
+        ft[6 + j] = fr.c1x * g[0 + j] + fr.c1y * g[3 + j] + g[6 + j];
+    }
+    const double w[3] = {B, B, 1.0};
+    double phi = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) phi += fabs(ft[3 * i + j]) * w[i] * w[j];
+    Hyp32 h;
+    if (!(phi > 0.0) || !isfinite(phi)) {          // zero / NaN / inf hypothesis: never an inlier anywhere
+        const float qnan = __int_as_float(0x7FFFFFFF);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) h.f[k] = qnan;
+        h.G = 0.f; h.pad0 = 0.f; h.pad1 = 0.f;
+        *out = h;
+        return;
+    }
+    const double inv = 1.0 / phi;
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { a[k] = fabs(ft[k] * inv); h.f[k] = (float)(ft[k] * inv); }
+    const double rho0 = a[0] * B + a[1] * B + a[2];
+    const double rho1 = a[3] * B + a[4] * B + a[5];
+    const double kap0 = a[0] * B + a[3] * B + a[6];
+    const double kap1 = a[1] * B + a[4] * B + a[7];
+    const double S1 = rho0 * rho0 + rho1 * rho1;
+    const double S2 = kap0 * kap0 + kap1 * kap1;
+    const double eps = 5.9604644775390625e-08;   // 2^-24
+    double Mb, Smax;
+    if (MODE == MODE_SAMPSON) { Mb = S1 + S2; Smax = 1.1 * (S1 + S2); }
+    else                      { Mb = fmin(S1, S2); Smax = fmax(S1, S2); }
+    const double G = 1.25 * 16.0 * eps * sqrt(Mb) + 2.0 * (100.0 * eps * eps + 10.0 * eps * Smax + 2.0 * eps * Mb);
+    h.G = __double2float_ru(G);
+    h.pad0 = 0.f; h.pad1 = 0.f;
+    *out = h;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) f_make_hyp32(const double* __restrict__ F64, const PairInfo* __restrict__ pi, int P,
+                                                     int Htot, Hyp32* __restrict__ hyp32) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= Htot) return;
+    int lo = 0, hi = P;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = F64[(size_t)h * 9 + k];
+    make_hyp32<MODE>(F, pi[lo], hyp32 + h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3: right singular vector of the smallest singular value by one-sided Jacobi, then rank-2 projection
+//      Fs <- Fs - (Fs v3) v3^T      (== U diag(s1,s2,0) V^T, lab3.py:321-324)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_rot(double a, double b, double g, double& c, double& s) {
+    // rotation that orthogonalises two columns with squared norms a, b and inner product g
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    c = rsqrt(1.0 + t * t);
+    s = c * t;
+}
+
+__device__ __forceinline__ void rank2_project(double* __restrict__ Fs /* row-major 3x3, in/out */) {
+    // columns of W = Fs*V and of V
+    double w[3][3], v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { w[j][i] = Fs[3 * i + j]; v[j][i] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            const double a = w[p][0] * w[p][0] + w[p][1] * w[p][1] + w[p][2] * w[p][2];
+            const double b = w[q][0] * w[q][0] + w[q][1] * w[q][1] + w[q][2] * w[q][2];
+            const double g = w[p][0] * w[q][0] + w[p][1] * w[q][1] + w[p][2] * w[q][2];
+            if (g != 0.0 && fabs(g) > 1e-16 * sqrt(a * b)) {
+                double c, s;
+                jacobi_rot(a, b, g, c, s);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double wp = w[p][i], wq = w[q][i];
+                    w[p][i] = c * wp - s * wq;
+                    w[q][i] = s * wp + c * wq;
+                    const double vp = v[p][i], vq = v[q][i];
+                    v[p][i] = c * vp - s * vq;
+                    v[q][i] = s * vp + c * vq;
+                }
+                rotated = true;
+            }
+        }
+        if (!rotated) break;
+    }
+    double n0 = w[0][0] * w[0][0] + w[0][1] * w[0][1] + w[0][2] * w[0][2];
+    double n1 = w[1][0] * w[1][0] + w[1][1] * w[1][1] + w[1][2] * w[1][2];
+    double n2 = w[2][0] * w[2][0] + w[2][1] * w[2][1] + w[2][2] * w[2][2];
+    int jm = 0;
+    if (n1 < n0) { jm = 1; n0 = n1; }
+    if (n2 < n0) { jm = 2; }
+    double v3[3], fv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v3[i] = (jm == 0) ? v[0][i] : (jm == 1 ? v[1][i] : v[2][i]);
+    // re-normalise v3 (rotations keep it unit up to rounding)
+    const double nv = rsqrt(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v3[i] *= nv;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fv[i] = Fs[3 * i] * v3[0] + Fs[3 * i + 1] * v3[1] + Fs[3 * i + 2] * v3[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Fs[3 * i + j] -= fv[i] * v3[j];
+}
+
+// Hartley scaling of 8 points (lab3.py:288-295): returns a = 1/L, b = -mx/L, c = -my/L
+__device__ __forceinline__ void hartley8(const double* __restrict__ px, const double* __restrict__ py, double& a, double& b,
+                                         double& c) {
+    double mx = 0.0, my = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mx += px[k]; my += py[k]; }
+    mx *= 0.125; my *= 0.125;
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const double dx = px[k] - mx, dy = py[k] - my; ss += dx * dx + dy * dy; }
+    const double L = sqrt(ss / 16.0);      // sqrt(1/2/N * sum), N = 8
+    a = 1.0 / L;
+    b = -mx / L;
+    c = -my / L;
+}
+
+// F = S^T Fs T with S = [[a1,0,b1],[0,a1,c1],[0,0,1]], T = [[a2,0,b2],[0,a2,c2],[0,0,1]]   (lab3.py:327)
+__device__ __forceinline__ void denormalise(const double* __restrict__ Fs, double a1, double b1, double c1, double a2,
+                                            double b2, double c2, double* __restrict__ F) {
+    double g[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g[3 * i + 0] = Fs[3 * i + 0] * a2;
+        g[3 * i + 1] = Fs[3 * i + 1] * a2;
+        g[3 * i + 2] = Fs[3 * i + 0] * b2 + Fs[3 * i + 1] * c2 + Fs[3 * i + 2];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        F[0 + j] = a1 * g[0 + j];
+        F[3 + j] = a1 * g[3 + j];
+        F[6 + j] = b1 * g[0 + j] + c1 * g[3 + j] + g[6 + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8-point solve, QR form: one hypothesis per thread.
+// The null vector of the 8x9 design matrix A is the last column of Q in A^T = Q R (Householder, backward
+// stable: it is the exact null vector of A + E, |E| <= c u |A| — the same guarantee LAPACK's SVD gives).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ pts, const int* __restrict__ idx,
+                                                    const PairInfo* __restrict__ pi, int P, int Htot,
+                                                    double* __restrict__ F64, Hyp32* __restrict__ hyp32,
+                                                    unsigned char* __restrict__ flags) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= Htot) return;
+    int lo = 0, hi = P;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+    const PairInfo& info = pi[lo];
+
+    double X[8], Y[8], x[8], y[8];
+    {
+        const int4 i0 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2];
+        const int4 i1 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2 + 1];
+        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int j = id[k];
+            j = j < 0 ? 0 : (j >= info.n ? info.n - 1 : j);     // never read out of the pair
+            const double4 v = pts[info.pt_off + j];
+            X[k] = v.x; Y[k] = v.y; x[k] = v.z; y[k] = v.w;
+        }
+    }
+    double a1, b1, c1, a2, b2, c2;
+    hartley8(X, Y, a1, b1, c1);
+    hartley8(x, y, a2, b2, c2);
+
+    // rows of A (== columns of A^T)
+    double A[8][9];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double Xh = X[k] * a1 + b1, Yh = Y[k] * a1 + c1;
+        const double xh = x[k] * a2 + b2, yh = y[k] * a2 + c2;
+        A[k][0] = Xh * xh; A[k][1] = Xh * yh; A[k][2] = Xh;
+        A[k][3] = Yh * xh; A[k][4] = Yh * yh; A[k][5] = Yh;
+        A[k][6] = xh;      A[k][7] = yh;      A[k][8] = 1.0;
+    }
+    double beta[8];
+    double rmin = INFINITY, rmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double ss = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) ss += A[k][i] * A[k][i];
+        const double sigma = sqrt(ss);
+        const double x0 = A[k][k];
+        rmin = fmin(rmin, sigma);
+        rmax = fmax(rmax, sigma);
+        if (sigma > 0.0) {
+            A[k][k] = x0 + copysign(sigma, x0);                 // v0 = x0 - alpha, alpha = -sign(x0) sigma
+            beta[k] = 1.0 / (sigma * (sigma + fabs(x0)));       // 2 / |v|^2
+        } else {
+            beta[k] = 0.0;
+        }
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) {
+            double d = 0.0;
+#pragma unroll
+            for (int i = k; i < 9; ++i) d += A[k][i] * A[j][i];
+            d *= beta[k];
+#pragma unroll
+            for (int i = k; i < 9; ++i) A[j][i] -= d * A[k][i];
+        }
+    }
+    double nv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) nv[i] = (i == 8) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        double d = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) d += A[k][i] * nv[i];
+        d *= beta[k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) nv[i] -= d * A[k][i];
+    }
+    // unit norm (Q is orthogonal up to rounding; LAPACK's V[-1] is unit norm too)
+    {
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ss += nv[i] * nv[i];
+        const double inv = rsqrt(ss);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nv[i] *= inv;
+    }
+    rank2_project(nv);
+    double F[9];
+    denormalise(nv, a1, b1, c1, a2, b2, c2, F);
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { F64[(size_t)h * 9 + k] = F[k]; finite = finite && isfinite(F[k]); }
+    unsigned char fl = 0;
+    if (!(rmin > 1e-9 * rmax)) fl |= 1;       // (nearly) rank-deficient sample: null direction not unique
+    if (!finite) fl |= 2;
+    flags[h] = fl;
+    make_hyp32<MODE>(F, info, hyp32 + h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 packed scorer
+// ------------------------------------------------------------------------------------------------
+struct ScoreItem {
+    int pair, h_base, H_end;        // hypotheses [h_base, min(h_base + kHypPerBlock, H_end)) (global indices)
+    int g0, g1;                     // kSub-point groups [g0, g1) of the pair
+    const float4* src;              // packed points of the pair
+};
+
+__device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi, int P, int item) {
+    int lo = 0, hi = P;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].item_off <= item) lo = mid; else hi = mid; }
+    const PairInfo& info = pi[lo];
+    const int local = item - info.item_off;
+    const int hb = local / info.nsplit;
+    const int sp = local - hb * info.nsplit;
+    ScoreItem it;
+    it.pair = lo;
+    it.h_base = info.hyp_off + hb * kHypPerBlock;
+    it.H_end = info.hyp_off + info.H;
+    const int ngroups = info.n_pad / kSub;
+    it.g0 = min(sp * info.groups_per_split, ngroups);
+    it.g1 = min(it.g0 + info.groups_per_split, ngroups);
+    it.src = nullptr;
+    return it;
+}
+
+struct Hyp2 {            // one hypothesis, every coefficient duplicated into both halves of a 64-bit register pair
+    float2 f[9];
+};
+
+// hypothesis record from the item's shared-memory stage (or an all-NaN hypothesis past the end of the pair)
+__device__ __forceinline__ void load_hyp2(const Hyp32* __restrict__ sh, int slot, bool valid, Hyp2& out, float& G) {
+    if (valid) {
+        const float4* p = reinterpret_cast<const float4*>(sh + slot);
+        const float4 a = p[0], b = p[1], c = p[2];
+        const float f[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out.f[k] = make_float2(f[k], f[k]);
+        G = c.y;
+    } else {
+        const float qnan = __int_as_float(0x7FFFFFFF);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out.f[k] = make_float2(qnan, qnan);
+        G = 0.f;
+    }
+}
+
+// two correspondences (a,b) against one hypothesis; identical IEEE op sequence per lane as epi_q32
+template <int MODE>
+__device__ __forceinline__ void eval2(const Hyp2& H, const float4 X, const float4 Y, unsigned& cnt, float& minabs) {
+    const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
+    const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
+    const float2 l1x = __ffma2_rn(H.f[0], y0, __ffma2_rn(H.f[1], y1, H.f[2]));
+    const float2 l1y = __ffma2_rn(H.f[3], y0, __ffma2_rn(H.f[4], y1, H.f[5]));
+    const float2 l1z = __ffma2_rn(H.f[6], y0, __ffma2_rn(H.f[7], y1, H.f[8]));
+    const float2 r   = __ffma2_rn(l1x, x0, __ffma2_rn(l1y, x1, l1z));
+    const float2 l2x = __ffma2_rn(H.f[0], x0, __ffma2_rn(H.f[3], x1, H.f[6]));
+    const float2 l2y = __ffma2_rn(H.f[1], x0, __ffma2_rn(H.f[4], x1, H.f[7]));
+    const float2 s1  = __ffma2_rn(l1x, l1x, __fmul2_rn(l1y, l1y));
+    const float2 s2  = __ffma2_rn(l2x, l2x, __fmul2_rn(l2y, l2y));
+    float2 nm;
+    if (MODE == MODE_SAMPSON) {
+        const float2 m = __fadd2_rn(s1, s2);
+        nm = make_float2(-m.x, -m.y);
+    } else {
+        nm = make_float2(-fminf(s1.x, s2.x), -fminf(s1.y, s2.y));
+    }
+    const float2 q = __ffma2_rn(r, r, nm);
+    cnt += __float_as_uint(q.x) >> 31;
+    cnt += __float_as_uint(q.y) >> 31;
+    minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
+}
+
+// work-list record: one kSub-point group of one hypothesis whose FP32 result is inside the rounding band
+__device__ __forceinline__ void push_recheck(int2* __restrict__ wl, unsigned long long* __restrict__ stats, int cap, int h,
+                                             int group) {
+    const unsigned long long pos = atomicAdd(&stats[0], 1ull);
+    if (pos < (unsigned long long)cap) wl[pos] = make_int2(h, group);
+}
+
+// Shared-memory stage of the scorer: one chunk of packed points and (for the first chunk of a work item) the
+// item's hypothesis records.  Both arrive by 1-D bulk TMA on the same mbarrier.
+struct __align__(128) ScoreStage {
+    float4 pts[kChunkPts];           // 16 KB
+    Hyp32  hyp[kHypPerBlock];        // 24 KB
+};
+constexpr size_t kScoreSmemBytes = kStages * sizeof(ScoreStage) + 64;
+
+// persistent block: items blockIdx.x, blockIdx.x + gridDim.x, ...; every item = 512 hypotheses x a contiguous
+// range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1 hypothesis.
+template <int MODE>
+__global__ void __launch_bounds__(kScoreThreads, 2)
+f_score_packed(const float4* __restrict__ pts32, const Hyp32* __restrict__ hyp32, const PairInfo* __restrict__ pi, int P,
+               int n_items, int* __restrict__ counts, int2* __restrict__ wl, unsigned long long* __restrict__ stats,
+               int wl_cap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScoreStage* st = reinterpret_cast<ScoreStage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(ScoreStage));
+
+    const int tid = threadIdx.x;
+    int item = blockIdx.x;
+    if (item >= n_items) return;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t phases = 0u;
+    int stage = 0;
+
+    ScoreItem cur = decode_item(pi, P, item);
+    const float4* cur_src = pts32 + (size_t)pi[cur.pair].pt_off32;   // 1 float4 per point (pairs interleaved)
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)min((cur.g1 - cur.g0) * kSub, kChunkPts) * 16u;
+        const uint32_t hb = (uint32_t)min(kHypPerBlock, cur.H_end - cur.h_base) * (uint32_t)sizeof(Hyp32);
+        mbar_expect_tx(&full[0], nb + hb);
+        tma_load_1d(st[0].pts, cur_src + (size_t)cur.g0 * kSub, nb, &full[0]);
+        tma_load_1d(st[0].hyp, hyp32 + cur.h_base, hb, &full[0]);
+    }
+
+    while (true) {
+        const int next_item = item + gridDim.x;
+        const bool has_next = next_item < n_items;
+        ScoreItem nxt = cur;
+        const float4* nxt_src = cur_src;
+        if (has_next) {
+            nxt = decode_item(pi, P, next_item);
+            nxt_src = pts32 + (size_t)pi[nxt.pair].pt_off32;
+        }
+        Hyp2 H0, H1;
+        float G0 = 0.f, G1 = 0.f;
+        const int h0 = cur.h_base + tid, h1 = cur.h_base + kScoreThreads + tid;
+        unsigned cnt0 = 0, cnt1 = 0;
+
+        const int total_pts = (cur.g1 - cur.g0) * kSub;
+        for (int done = 0; done < total_pts; done += kChunkPts) {
+            const int npts = min(total_pts - done, kChunkPts);
+            // prefetch the following chunk (of this item, or the first chunk + hypotheses of the next item)
+            if (tid == 0) {
+                const int s2 = stage ^ 1;
+                if (done + kChunkPts < total_pts) {
+                    const uint32_t nb = (uint32_t)min(total_pts - done - kChunkPts, kChunkPts) * 16u;
+                    mbar_expect_tx(&full[s2], nb);
+                    tma_load_1d(st[s2].pts, cur_src + (size_t)cur.g0 * kSub + done + kChunkPts, nb, &full[s2]);
+                } else if (has_next) {
+                    const uint32_t nb = (uint32_t)min((nxt.g1 - nxt.g0) * kSub, kChunkPts) * 16u;
+                    const uint32_t hb = (uint32_t)min(kHypPerBlock, nxt.H_end - nxt.h_base) * (uint32_t)sizeof(Hyp32);
+                    mbar_expect_tx(&full[s2], nb + hb);
+                    tma_load_1d(st[s2].pts, nxt_src + (size_t)nxt.g0 * kSub, nb, &full[s2]);
+                    tma_load_1d(st[s2].hyp, hyp32 + nxt.h_base, hb, &full[s2]);
+                }
+            }
+            mbar_wait(&full[stage], (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+
+            if (done == 0) {
+                load_hyp2(st[stage].hyp, tid, h0 < cur.H_end, H0, G0);
+                load_hyp2(st[stage].hyp, kScoreThreads + tid, h1 < cur.H_end, H1, G1);
+            }
+            const float4* sp = st[stage].pts;
+            const int ngr = npts / kSub;
+            const int gbase = cur.g0 + done / kSub;
+            for (int g = 0; g < ngr; ++g) {
+                float ma0 = INFINITY, ma1 = INFINITY;
+                const float4* gp = sp + g * kSub;
+#pragma unroll 4
+                for (int j = 0; j < kSub / 2; ++j) {
+                    const float4 X = gp[2 * j];
+                    const float4 Y = gp[2 * j + 1];
+                    eval2<MODE>(H0, X, Y, cnt0, ma0);
+                    eval2<MODE>(H1, X, Y, cnt1, ma1);
+                }
+                if (ma0 <= G0) push_recheck(wl, stats, wl_cap, h0, gbase + g);
+                if (ma1 <= G1) push_recheck(wl, stats, wl_cap, h1, gbase + g);
+            }
+            __syncthreads();          // everyone is done with this stage before it is refilled
+            stage ^= 1;
+        }
+        if (h0 < cur.H_end && cnt0) atomicAdd(&counts[h0], (int)cnt0);
+        if (h1 < cur.H_end && cnt1) atomicAdd(&counts[h1], (int)cnt1);
+        if (!has_next) break;
+        item = next_item;
+        cur = nxt;
+        cur_src = nxt_src;
+    }
+}
+
+// FP64 re-evaluation of the flagged groups: counts[h] += (#exact inliers - #FP32 inliers) over band evals
+template <int MODE>
+__global__ void __launch_bounds__(256) f_fixup(const float4* __restrict__ pts32, const double4* __restrict__ pts64,
+                                                const Hyp32* __restrict__ hyp32, const double* __restrict__ F64,
+                                                const PairInfo* __restrict__ pi, int P, int* __restrict__ counts,
+                                                const int2* __restrict__ wl, unsigned long long* __restrict__ stats,
+                                                int wl_cap) {
+    const unsigned long long pushed = stats[0];
+    const int nrec = (int)(pushed < (unsigned long long)wl_cap ? pushed : (unsigned long long)wl_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && pushed > (unsigned long long)wl_cap) stats[3] = 1ull;   // overflow
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < nrec; r += nwarps) {
+        const int2 rec = wl[r];
+        const int h = rec.x;
+        int lo = 0, hi = P;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        const PairInfo& info = pi[lo];
+        const int i = rec.y * kSub + lane;                     // point index inside the pair
+        int delta = 0, amb = 0;
+        if (i < info.n) {
+            const Hyp32 hy = hyp32[h];
+            const float4* gp = pts32 + (size_t)info.pt_off32 + (size_t)(i >> 1) * 2;
+            const float4 X = gp[0], Y = gp[1];
+            const bool second = i & 1;
+            const float q = epi_q32<MODE>(hy.f, second ? X.y : X.x, second ? X.w : X.z, second ? Y.y : Y.x,
+                                          second ? Y.w : Y.z);
+            if (fabsf(q) <= hy.G) {
+                const double4 v = pts64[info.pt_off + i];
+                const int in64 = epi_inlier64(F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
+                delta = in64 - (int)(__float_as_uint(q) >> 31);
+                amb = 1;
+            }
+        }
+        const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+        if (lane == 0) {
+            if (delta) atomicAdd(&counts[h], delta);
+            atomicAdd(&stats[1], (unsigned long long)__popc(ambmask));
+            if (delta) atomicAdd(&stats[2], (unsigned long long)(delta < 0 ? -delta : delta));
+        }
+    }
+}
+
+// Plain FP64 scorer (reference formula for every evaluation).  One hypothesis per thread, points broadcast from
+// shared memory.  Two uses:
+//   * gate == nullptr : the SCORE_FP64 path and the on-device exact answer in tests; N may be split over gridDim.z
+//                       (counts must be zeroed beforehand, partial sums are added atomically);
+//   * gate != nullptr : repair pass after the packed scorer — does nothing unless *gate != 0 (recheck work-list
+//                       overflow), in which case every count is recomputed exactly and OVERWRITTEN (gridDim.z == 1).
+__global__ void __launch_bounds__(128) f_score_fp64(const double4* __restrict__ pts64, const double* __restrict__ F64,
+                                                     const PairInfo* __restrict__ pi, int mode, int* __restrict__ counts,
+                                                     const unsigned long long* __restrict__ gate) {
+    __shared__ double4 sp[256];
+    if (gate != nullptr && *gate == 0ull) return;
+    const int p = blockIdx.y;
+    const PairInfo info = pi[p];
+    const int hl = blockIdx.x * blockDim.x + threadIdx.x;           // hypothesis inside the pair
+    if (blockIdx.x * blockDim.x >= info.H) return;
+    const bool active = hl < info.H;
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = active ? F64[(size_t)(info.hyp_off + hl) * 9 + k] : 0.0;
+    const int per = (info.n + gridDim.z - 1) / gridDim.z;
+    const int n0 = min((int)blockIdx.z * per, info.n), n1 = min(n0 + per, info.n);
+    int cnt = 0;
+    for (int base = n0; base < n1; base += 256) {
+        const int m = min(256, n1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) sp[i] = pts64[info.pt_off + base + i];
+        __syncthreads();
+        if (active) {
+            for (int i = 0; i < m; ++i) {
+                const double4 v = sp[i];
+                cnt += epi_inlier64(F, v.x, v.y, v.z, v.w, info.thr, mode);
+            }
+        }
+    }
+    if (active) {
+        if (gate != nullptr) counts[info.hyp_off + hl] = cnt;
+        else if (cnt) atomicAdd(&counts[info.hyp_off + hl], cnt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// selection
+// ------------------------------------------------------------------------------------------------
+// best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
+__global__ void __launch_bounds__(256) f_argmax(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
+                                                 int2* __restrict__ best) {
+    __shared__ unsigned long long sk[8];
+    const int p = blockIdx.x;
+    const PairInfo info = pi[p];
+    unsigned long long key = 0ull;
+    for (int h = threadIdx.x; h < info.H; h += blockDim.x) {
+        const unsigned long long k =
+            ((unsigned long long)(unsigned)counts[info.hyp_off + h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+        key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) key = sk[w] > key ? sk[w] : key;
+        const int cnt = (int)(key >> 32);
+        const int idx = cnt > 0 ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : -1;
+        best[p] = make_int2(idx, cnt);
+    }
+}
+
+// tie_stats[h] = {std(d), ||d||_2} over all N points (FP64), only for hypotheses whose count equals the pair maximum
+// (the only ones the reference's tie rule fun.py:324-328 can ever look at once the maximum has appeared).
+__global__ void __launch_bounds__(256) f_tie_stats(const double4* __restrict__ pts64, const double* __restrict__ F64,
+                                                    const int* __restrict__ counts, const PairInfo* __restrict__ pi, int P,
+                                                    int Htot, const int2* __restrict__ best, int mode,
+                                                    double2* __restrict__ tie_stats) {
+    __shared__ double red[3][8];
+    for (int h = blockIdx.x; h < Htot; h += gridDim.x) {
+        int lo = 0, hi = P;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        const PairInfo& info = pi[lo];
+        if (counts[h] != best[lo].y || best[lo].x < 0) continue;          // uniform per block
+        const double* F = F64 + (size_t)h * 9;
+        // two-pass like np.std: mean first, then mean of squared deviations
+        double s = 0.0, s2 = 0.0;
+        for (int i = threadIdx.x; i < info.n; i += blockDim.x) {
+            const double4 v = pts64[info.pt_off + i];
+            const double d = epi_dist64(F, v.x, v.y, v.z, v.w, mode);
+            s += d; s2 += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = s2; }
+        __syncthreads();
+        double S = 0.0, S2 = 0.0;
+        for (int w = 0; w < 8; ++w) { S += red[0][w]; S2 += red[1][w]; }
+        const double mean = S / (double)info.n;
+        double dv = 0.0;
+        for (int i = threadIdx.x; i < info.n; i += blockDim.x) {
+            const double4 v = pts64[info.pt_off + i];
+            const double d = epi_dist64(F, v.x, v.y, v.z, v.w, mode) - mean;
+            dv += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
+        if ((threadIdx.x & 31) == 0) red[2][threadIdx.x >> 5] = dv;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double DV = 0.0;
+            for (int w = 0; w < 8; ++w) DV += red[2][w];
+            tie_stats[h] = make_double2(sqrt(DV / (double)info.n), sqrt(S2));
+        }
+        __syncthreads();
+    }
+}
+
+// sequential replay of fun.py:320-328 over the maximal-count hypotheses, in hypothesis order (one warp per pair)
+__global__ void __launch_bounds__(32) f_tie_resolve(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
+                                                     const double2* __restrict__ tie_stats, int2* __restrict__ best) {
+    const int p = blockIdx.x;
+    const PairInfo info = pi[p];
+    const int2 b = best[p];
+    if (b.x < 0) return;
+    const int lane = threadIdx.x;
+    int cur = -1;
+    double cur_std = 0.0;
+    for (int base = 0; base < info.H; base += 32) {
+        const int h = base + lane;
+        const bool cand = h < info.H && counts[info.hyp_off + h] == b.y;
+        double2 st = make_double2(0.0, 0.0);
+        if (cand) st = tie_stats[info.hyp_off + h];
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double sd = __shfl_sync(0xffffffffu, st.x, src);
+            const double nr = __shfl_sync(0xffffffffu, st.y, src);
+            if (cur < 0) { cur = base + src; cur_std = sd; }                 // first arrival at the max: strict >
+            else if (fabs(cur_std) > nr) { cur = base + src; cur_std = sd; } // norm(std_best) > norm(d_new)
+        }
+    }
+    if (lane == 0) best[p] = make_int2(cur, b.y);
+}
+
+// inlier mask of the winner (FP64 reference formula) + copy of its F
+__global__ void __launch_bounds__(256) f_mask(const double4* __restrict__ pts64, const double* __restrict__ F64,
+                                               const PairInfo* __restrict__ pi, const int2* __restrict__ best, int mode,
+                                               unsigned char* __restrict__ mask, double* __restrict__ best_F,
+                                               int* __restrict__ best_idx, int* __restrict__ best_count) {
+    const int p = blockIdx.y;
+    const PairInfo info = pi[p];
+    const int2 b = best[p];
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        best_F[p * 9 + threadIdx.x] = b.x >= 0 ? F64[(size_t)(info.hyp_off + b.x) * 9 + threadIdx.x] : nan("");
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { best_idx[p] = b.x; best_count[p] = b.y; }
+    if (mask == nullptr) return;
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = b.x >= 0 ? F64[(size_t)(info.hyp_off + b.x) * 9 + k] : nan("");
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < info.n; i += gridDim.x * blockDim.x) {
+        const double4 v = pts64[info.pt_off + i];
+        mask[info.pt_off + i] = (unsigned char)epi_inlier64(F, v.x, v.y, v.z, v.w, info.thr, mode);
+    }
+}
+
+// signed residuals of one F over N points (lab3.fmatrix_residuals drop-in): out[0..N) = res1, out[N..2N) = res2
+__global__ void __launch_bounds__(256) f_residuals(const double* __restrict__ F9, const double* __restrict__ x,
+                                                    const double* __restrict__ y, int N, double* __restrict__ out) {
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = F9[k];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double x0 = x[i], x1 = x[N + i], y0 = y[i], y1 = y[N + i];
+        const double l1x = F[0] * y0 + F[1] * y1 + F[2];
+        const double l1y = F[3] * y0 + F[4] * y1 + F[5];
+        const double l1z = F[6] * y0 + F[7] * y1 + F[8];
+        const double l2x = F[0] * x0 + F[3] * x1 + F[6];
+        const double l2y = F[1] * x0 + F[4] * x1 + F[7];
+        const double l2z = F[2] * x0 + F[5] * x1 + F[8];
+        out[i]     = (l1x * x0 + l1y * x1 + l1z) / sqrt(l1x * l1x + l1y * l1y);
+        out[N + i] = (l2x * y0 + l2y * y1 + l2z) / sqrt(l2x * l2x + l2y * l2y);
+    }
+}
+
+}  // namespace rg

@@ -1,0 +1,225 @@
+"""numpy-level wrappers over the C ABI (host-buffer entry points).
+
+These are the only functions of the package that touch ctypes; ``lab3.py`` / ``fun.py`` / ``ransac.py`` / ``pnp.py``
+(the mirrors of the reference's modules) and ``batched.py`` are written on top of them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as cabi
+from ._cabi import (MODE_EPI_MAX, MODE_SAMPSON, SCORE_FP32_GUARDED, SCORE_FP64, SOLVER_JACOBI, SOLVER_QR, TIE_FIRST,
+                    TIE_REFERENCE)
+
+_vp = C.c_void_p
+
+
+def _f64(a, shape_tail=None):
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_tail is not None and arr.shape[1:] != tuple(shape_tail):
+        raise ValueError(f"expected trailing shape {shape_tail}, got {arr.shape}")
+    return arr
+
+
+def pack_pairs(p1, p2) -> np.ndarray:
+    """(2, N) + (2, N) reference layout  ->  (N, 4) rows (x0, x1, y0, y1)."""
+    p1 = np.asarray(p1, dtype=np.float64)
+    p2 = np.asarray(p2, dtype=np.float64)
+    if p1.shape != p2.shape or p1.ndim != 2 or p1.shape[0] != 2:
+        raise ValueError("expected two (2, N) arrays of the same shape")
+    return np.ascontiguousarray(np.concatenate([p1.T, p2.T], axis=1))
+
+
+def last_stats(device=None, stream=0) -> dict:
+    lib = cabi.load_library()
+    out = (C.c_longlong * 8)()
+    cabi.check(lib.rg_get_last_stats(_vp(cabi.context(device)), _vp(stream), out))
+    return {"recheck_groups": out[0], "band_evals": out[1], "flips": out[2], "overflow": out[3], "launches": out[7]}
+
+
+def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TIE_FIRST, solver=SOLVER_QR,
+                     score_path=SCORE_FP32_GUARDED, want_counts=False, want_F_all=False, want_mask=True,
+                     want_flags=False, device=None, stream=0) -> dict:
+    """F-matrix RANSAC over a batch of image pairs in ONE library call.
+
+    pts_list[p] : (N_p, 4) float64 rows (x0, x1, y0, y1);  idx_list[p] : (H_p, 8) int sample indices (host-drawn).
+    Returns per-pair arrays ``best_idx`` (-1 = no hypothesis has any inlier), ``best_count``, ``F`` (P, 3, 3) and
+    lists ``mask`` / ``counts`` / ``F_all`` / ``flags`` split per pair when requested.
+    """
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    P = len(pts_list)
+    if len(idx_list) != P:
+        raise ValueError("pts_list and idx_list must have the same length")
+    pts = [_f64(p).reshape(-1, 4) for p in pts_list]
+    idx = [np.ascontiguousarray(i, dtype=np.int32).reshape(-1, 8) for i in idx_list]
+    pair_off = np.zeros(P + 1, dtype=np.int32)
+    hyp_off = np.zeros(P + 1, dtype=np.int32)
+    for p in range(P):
+        pair_off[p + 1] = pair_off[p] + pts[p].shape[0]
+        hyp_off[p + 1] = hyp_off[p] + idx[p].shape[0]
+        if idx[p].size and (idx[p].min() < 0 or idx[p].max() >= pts[p].shape[0]):
+            raise ValueError(f"pair {p}: sample index out of range")
+    Ntot, Htot = int(pair_off[-1]), int(hyp_off[-1])
+    pts_all = np.concatenate(pts, axis=0) if P else np.zeros((0, 4))
+    idx_all = np.concatenate(idx, axis=0) if P else np.zeros((0, 8), dtype=np.int32)
+    pts_all = np.ascontiguousarray(pts_all)
+    idx_all = np.ascontiguousarray(idx_all)
+    best_idx = np.full(P, -1, dtype=np.int32)
+    best_count = np.zeros(P, dtype=np.int32)
+    best_F = np.full((P, 3, 3), np.nan)
+    mask = np.zeros(Ntot, dtype=np.uint8) if want_mask else None
+    counts = np.zeros(Htot, dtype=np.int32) if want_counts else None
+    F_all = np.zeros((Htot, 3, 3)) if want_F_all else None
+    flags = np.zeros(Htot, dtype=np.uint8) if want_flags else None
+    cabi.check(lib.rg_f_ransac_host(
+        _vp(ctx), _vp(stream), P, _vp(cabi.ptr(pts_all)), pair_off.ctypes.data_as(C.POINTER(C.c_int32)),
+        _vp(cabi.ptr(idx_all)), hyp_off.ctypes.data_as(C.POINTER(C.c_int32)), float(thr), int(mode), int(tie_mode),
+        int(solver), int(score_path), _vp(cabi.ptr(best_idx)), _vp(cabi.ptr(best_count)), _vp(cabi.ptr(best_F)),
+        _vp(cabi.ptr(mask)), _vp(cabi.ptr(counts)), _vp(cabi.ptr(F_all)), _vp(cabi.ptr(flags))))
+    out = {"best_idx": best_idx, "best_count": best_count, "F": best_F, "pair_off": pair_off, "hyp_off": hyp_off}
+    split_n = lambda a: [a[pair_off[p]:pair_off[p + 1]] for p in range(P)]
+    split_h = lambda a: [a[hyp_off[p]:hyp_off[p + 1]] for p in range(P)]
+    if want_mask:
+        out["mask"] = split_n(mask)
+    if want_counts:
+        out["counts"] = split_h(counts)
+    if want_F_all:
+        out["F_all"] = split_h(F_all)
+    if want_flags:
+        out["flags"] = split_h(flags)
+    return out
+
+
+def f8pt_solve(pts, idx, solver=SOLVER_QR, device=None, stream=0):
+    """8-point F for every (H, 8) sample of one pair.  Returns (F_all (H,3,3), flags (H,))."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    pts = _f64(pts).reshape(-1, 4)
+    idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 8)
+    if idx.size and (idx.min() < 0 or idx.max() >= pts.shape[0]):
+        raise ValueError("sample index out of range")
+    H = idx.shape[0]
+    F_all = np.zeros((H, 3, 3))
+    flags = np.zeros(H, dtype=np.uint8)
+    cabi.check(lib.rg_f8pt_solve_host(_vp(ctx), _vp(stream), pts.shape[0], _vp(cabi.ptr(pts)), H, _vp(cabi.ptr(idx)),
+                                      int(solver), _vp(cabi.ptr(F_all)), _vp(cabi.ptr(flags))))
+    return F_all, flags
+
+
+def epi_score_count(pts, F_all, thr, mode=MODE_EPI_MAX, score_path=SCORE_FP32_GUARDED, device=None, stream=0):
+    """Inlier count of each caller-supplied F (H, 3, 3) over the (N, 4) correspondences."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    pts = _f64(pts).reshape(-1, 4)
+    F_all = _f64(F_all).reshape(-1, 9)
+    H = F_all.shape[0]
+    counts = np.zeros(H, dtype=np.int32)
+    cabi.check(lib.rg_epi_score_count_host(_vp(ctx), _vp(stream), pts.shape[0], _vp(cabi.ptr(pts)), H,
+                                           _vp(cabi.ptr(F_all)), float(thr), int(mode), int(score_path),
+                                           _vp(cabi.ptr(counts))))
+    return counts
+
+
+def fmatrix_residuals(F, x, y, device=None, stream=0):
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    F = _f64(F).reshape(9)
+    x = _f64(x)
+    y = _f64(y)
+    N = x.shape[1]
+    out = np.empty((2, N))
+    cabi.check(lib.rg_fmatrix_residuals_host(_vp(ctx), _vp(stream), _vp(cabi.ptr(F)), N, _vp(cabi.ptr(x)),
+                                             _vp(cabi.ptr(y)), _vp(cabi.ptr(out))))
+    return out
+
+
+def fmatrix_stls(pl, pr, device=None, stream=0):
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    pl = _f64(pl)
+    pr = _f64(pr)
+    F = np.empty((3, 3))
+    cabi.check(lib.rg_fmatrix_stls_host(_vp(ctx), _vp(stream), pl.shape[1], _vp(cabi.ptr(pl)), _vp(cabi.ptr(pr)),
+                                        _vp(cabi.ptr(F))))
+    return F
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PnP
+# ---------------------------------------------------------------------------------------------------------------
+def pnp_ransac(X, y, idx, thr2, n_sel=None, score_path=SCORE_FP32_GUARDED, want_counts=False, want_poses=False,
+               want_mask=True, want_flags=False, device=None, stream=0) -> dict:
+    """DLT-PnP RANSAC on one view.  X (N,3), y (N,2) C-normalised, idx (H,n) with 6 <= n <= 8."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    X = _f64(X).reshape(-1, 3)
+    y = _f64(y).reshape(-1, 2)
+    if X.shape[0] != y.shape[0]:
+        raise ValueError("X and y must have the same number of rows")
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    if idx.ndim != 2:
+        raise ValueError("idx must be (H, n)")
+    H, n = idx.shape
+    N = X.shape[0]
+    if idx.size and (idx.min() < 0 or idx.max() >= N):
+        raise ValueError("sample index out of range")
+    n_sel = N if n_sel is None else int(n_sel)
+    best_idx = np.full(1, -1, dtype=np.int32)
+    best_count = np.zeros(1, dtype=np.int32)
+    R = np.full((3, 3), np.nan)
+    t = np.full(3, np.nan)
+    mask = np.zeros(N, dtype=np.uint8) if want_mask else None
+    counts = np.zeros(H, dtype=np.int32) if want_counts else None
+    poses = np.zeros((H, 12)) if want_poses else None
+    flags = np.zeros(H, dtype=np.uint8) if want_flags else None
+    cabi.check(lib.rg_pnp_ransac_host(_vp(ctx), _vp(stream), N, n_sel, _vp(cabi.ptr(X)), _vp(cabi.ptr(y)), H, n,
+                                      _vp(cabi.ptr(idx)), float(thr2), int(score_path), _vp(cabi.ptr(best_idx)),
+                                      _vp(cabi.ptr(best_count)), _vp(cabi.ptr(R)), _vp(cabi.ptr(t)), _vp(cabi.ptr(mask)),
+                                      _vp(cabi.ptr(counts)), _vp(cabi.ptr(poses)), _vp(cabi.ptr(flags))))
+    out = {"best_idx": int(best_idx[0]), "best_count": int(best_count[0]), "R": R, "t": t}
+    if want_mask:
+        out["mask"] = mask
+    if want_counts:
+        out["counts"] = counts
+    if want_poses:
+        out["poses"] = poses
+    if want_flags:
+        out["flags"] = flags
+    return out
+
+
+def pnp_minimize(X, y, device=None, stream=0):
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    X = _f64(X).reshape(-1, 3)
+    y = _f64(y).reshape(-1, 2)
+    R = np.empty((3, 3))
+    t = np.empty(3)
+    cabi.check(lib.rg_pnp_minimize_host(_vp(ctx), _vp(stream), X.shape[0], _vp(cabi.ptr(X)), _vp(cabi.ptr(y)),
+                                        _vp(cabi.ptr(R)), _vp(cabi.ptr(t))))
+    return R, t
+
+
+def pnp_score_count(X, y, poses, thr2, score_path=SCORE_FP32_GUARDED, device=None, stream=0):
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    X = _f64(X).reshape(-1, 3)
+    y = _f64(y).reshape(-1, 2)
+    poses = _f64(poses).reshape(-1, 12)
+    counts = np.zeros(poses.shape[0], dtype=np.int32)
+    cabi.check(lib.rg_pnp_score_count_host(_vp(ctx), _vp(stream), X.shape[0], _vp(cabi.ptr(X)), _vp(cabi.ptr(y)),
+                                           poses.shape[0], _vp(cabi.ptr(poses)), float(thr2), int(score_path),
+                                           _vp(cabi.ptr(counts))))
+    return counts
+
+
+def microbench(device=None, stream=0) -> dict:
+    lib = cabi.load_library()
+    cabi.context(device)
+    out = (C.c_double * 6)()
+    cabi.check(lib.rg_microbench_run(out, _vp(stream)))
+    return {"ffma_gfma_s": out[0], "ffma2_gfma_s": out[1], "mix_scalar_gevals_s": out[2],
+            "mix_packed_gevals_s": out[3], "dfma_gfma_s": out[4], "sms": int(out[5])}
