@@ -7,7 +7,7 @@
  *
  * Conventions
  *   - every function returns 0 on success and a negative code on failure; rg_last_error() gives the text
- *     (-1 CUDA error, -2 invalid argument, -3 no sm_100 device, -4 internal overflow);
+ *     (-1 CUDA error, -2 invalid argument, -3 no sm_100 device);
  *   - there is NO CPU fallback: without a Blackwell (sm_100) device rg_init fails with -3;
  *   - "_host" entry points take HOST buffers, do the H2D / D2H copies on `stream` and synchronise it before returning;
  *     "_dev" entry points take DEVICE buffers (offset tables stay on the host) and are asynchronous on `stream`;
@@ -41,13 +41,18 @@ const char* rg_last_error(void);
 int rg_init(int device, void** out_ctx);
 int rg_shutdown(void* ctx);
 int rg_device_sm_count(void* ctx);
+/* option 1 = phase profiling on/off: CUDA events on the launching stream around the phases of every RANSAC call */
+int rg_set_option(void* ctx, int option, long long value);
+/* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the calls since the last read
+ * (at most 256 calls are remembered); synchronises `stream` */
+int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 
 /* Pipe micro-benchmarks on the context's device (roofline denominators for bench.py):
  * out6 = {FFMA GFMA/s, FFMA2 GFMA/s, scalar-mix Gevals/s, packed-mix Gevals/s, DFMA GFMA/s, SM count}. */
 int rg_microbench_run(double* out6, void* stream);
 
-/* out8 = {recheck groups pushed, band evaluations redone in FP64, decisions changed, work-list overflow flag,
- *         0, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
+/* out8 = {guard-band groups flagged by the FP32 scorer, band evaluations redone in FP64, decisions changed by that,
+ *         0, 0, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
 int rg_get_last_stats(void* ctx, void* stream, long long* out8);
 
 /* ---- F-matrix RANSAC: replaces the loop of fun.getFFromLabCode (fun.py:303-328), which calls

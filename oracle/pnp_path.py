@@ -120,6 +120,6 @@ def pnp_ransac(X: np.ndarray, y_h: np.ndarray, idx: np.ndarray, thresh: float, n
 
 
 def rotation_angle(Ra: np.ndarray, Rb: np.ndarray) -> float:
-    """geodesic distance between two rotations (radians)."""
-    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
-    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+    """geodesic distance between two rotations (radians); chordal form, accurate for tiny angles."""
+    chord = np.linalg.norm(np.asarray(Ra) - np.asarray(Rb)) / (2.0 * np.sqrt(2.0))
+    return float(2.0 * np.arcsin(min(1.0, chord)))

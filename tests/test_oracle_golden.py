@@ -1,0 +1,104 @@
+"""The numpy oracle (oracle/) against the golden vectors produced by the UNMODIFIED reference (oracle/gen_golden.py).
+CPU only.  This is what pins the oracle; the GPU tests then compare the CUDA path with the oracle."""
+import numpy as np
+import pytest
+
+from oracle import f_path as orc
+from oracle import pnp_path as opnp
+
+
+def _nerr(Fa, Fb):
+    Fb = orc.normalise_F(Fb)
+    return np.linalg.norm(orc.normalise_F(Fa, Fb) - Fb)
+
+
+def test_fmatrix_stls_matches_reference_8pt(f_golden, noisy01):
+    p1, p2 = noisy01
+    for sel, Fref in zip(f_golden["stls_idx"], f_golden["stls_F"]):
+        F = orc.fmatrix_stls(p1[:, sel], p2[:, sel])
+        assert np.allclose(F, Fref, rtol=0, atol=1e-12 * np.abs(Fref).max()) or _nerr(F, Fref) < 1e-11
+
+
+def test_fmatrix_stls_matches_reference_all_points(f_golden, noisy01):
+    p1, p2 = noisy01
+    assert _nerr(orc.fmatrix_stls(p1, p2), f_golden["stlsN_F_noisy01"]) < 1e-12
+
+
+def test_fmatrix_stls_shape_error():
+    with pytest.raises(ValueError):
+        orc.fmatrix_stls(np.zeros((2, 8)), np.zeros((2, 9)))
+
+
+def test_fmatrix_residuals_matches_reference(f_golden, noisy01):
+    p1, p2 = noisy01
+    for F, ref in zip(f_golden["resid_F"], f_golden["resid_out"]):
+        out = orc.fmatrix_residuals(F, p1, p2)
+        assert out.shape == ref.shape == (2, p1.shape[1])
+        assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        orc.fmatrix_residuals(np.eye(3), p1, p2[:, :-1])
+
+
+def test_ransac_loop_matches_reference(f_golden, noisy01):
+    """fun.py:303-328 replayed by the reference itself with seeded draws: counts, both selection rules, inlier set."""
+    p1, p2 = noisy01
+    idx = f_golden["ransac_idx"]
+    res = orc.f_ransac(p1, p2, idx, thr=1.5, tie="reference")
+    assert np.array_equal(res["counts"], f_golden["ransac_counts"])
+    assert res["best"] == int(f_golden["ransac_best_reference_rule"])
+    assert np.array_equal(res["mask"], f_golden["ransac_mask"])
+    assert _nerr(res["F"], f_golden["ransac_F"]) < 1e-12
+    assert orc.select_first_max(res["counts"]) == int(f_golden["ransac_best_first_max"])
+
+
+def test_clean_pairs_reproduce_camera_F(dino, f_golden):
+    """BAdino2.mat is exact synthetic data: any 8 visible correspondences give the F of the two cameras."""
+    x2d = dino["x2d"]
+    rng = np.random.default_rng(0)
+    for i in (0, 7, 20, 34):
+        y1, y2 = x2d[i].T, x2d[i + 1].T
+        ok = np.logical_and(np.any(y1 != -1, axis=1), np.any(y2 != -1, axis=1))
+        p1, p2 = y1[ok].T, y2[ok].T
+        F = orc.fmatrix_stls(p1, p2)
+        assert _nerr(F, f_golden["F_from_cameras"][i]) < 1e-7
+        assert orc.inliers(F, p1, p2, 1.5).size == p1.shape[1]
+        sel = rng.choice(p1.shape[1], 8, replace=False)
+        F8 = orc.fmatrix_stls(p1[:, sel], p2[:, sel])
+        assert orc.inliers(F8, p1, p2, 1.5).size >= 8
+
+
+def test_shipped_Fmatrix_is_the_clean_pair_F(dino, f_golden):
+    """The reference's own artefact Fmatrix.npy (output of getFFromLabCode on clean pair (0,1))."""
+    assert _nerr(dino["Fmatrix"], f_golden["F_from_cameras"][0]) < 1e-9
+    assert _nerr(f_golden["getF_clean01_seed0"], dino["Fmatrix"]) < 1e-9
+
+
+def test_pnp_oracle_recovers_ground_truth_cameras(dino, pnp_golden):
+    """pnp.py:132-152 restated: on the exact Dino data the DLT pose equals fun.camera_resectioning's (R, t)."""
+    for i in (0, 5, 17, 35):
+        vis = np.any(dino["x2d"][i] != -1, axis=0)
+        X = dino["X3d"][vis]
+        px = dino["x2d"][i][:, vis]
+        K = pnp_golden["K"][i]
+        yh = np.linalg.solve(K, np.vstack([px, np.ones(px.shape[1])])).T
+        Xh = np.hstack([X, np.ones((X.shape[0], 1))])
+        R, t = opnp.pnp_minimize(Xh, yh)
+        assert opnp.rotation_angle(R, pnp_golden["R"][i]) < 1e-9
+        assert np.linalg.norm(t - pnp_golden["t"][i]) < 1e-9 * max(1.0, np.linalg.norm(t))
+        # 6-point minimal sample of exact data gives the same pose
+        R6, t6 = opnp.pnp_minimize(Xh[:6], yh[:6])
+        assert opnp.rotation_angle(R6, pnp_golden["R"][i]) < 1e-6
+        e = opnp.reprojection_error_sq(R, t, X, yh)
+        assert e.max() < 1e-20
+
+
+def test_pnp_oracle_consensus_is_inclusive():
+    R, t = np.eye(3), np.zeros(3)
+    X = np.array([[0.0, 0.0, 1.0], [0.5, 0.0, 1.0]])
+    y = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 1.0]])
+    e = opnp.reprojection_error_sq(R, t, X, y)
+    assert np.allclose(e, [0.0, 0.25])
+    assert opnp.consensus(R, t, X, y, 0.25).tolist() == [True, True]          # thresh >= e (ransac.py:104)
+    assert opnp.consensus(R, t, X, y, 0.2499).tolist() == [True, False]
+    with pytest.raises(ValueError):
+        opnp.pnp_minimize(np.ones((5, 4)), np.ones((5, 3)))

@@ -34,6 +34,8 @@ SIGNATURES = {
     "rg_init": (_i, [_i, C.POINTER(_vp)]),
     "rg_shutdown": (_i, [_vp]),
     "rg_device_sm_count": (_i, [_vp]),
+    "rg_set_option": (_i, [_vp, _i, C.c_longlong]),
+    "rg_get_profile": (_i, [_vp, _vp, _pd, C.POINTER(C.c_int)]),
     "rg_microbench_run": (_i, [_pd, _vp]),
     "rg_get_last_stats": (_i, [_vp, _vp, _pll]),
     "rg_f_ransac_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -1,0 +1,31 @@
+"""Batched entry points (one library call for many image pairs / one view): what ``main.py``-style drivers and the
+benchmark use instead of calling ``fun.getFFromLabCode`` pair by pair."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import runtime as _rt
+from . import sampling as _sampling
+from ._cabi import MODE_EPI_MAX, SCORE_FP32_GUARDED, SOLVER_QR, TIE_FIRST
+
+
+def f_ransac_pairs(pairs, n_hyp=10000, thr=1.5, seed=0, idx_list=None, **kw) -> dict:
+    """pairs: list of (p1, p2) with (2, N_p) arrays (reference layout) or of (N_p, 4) arrays.  Sample indices are
+    drawn on the host from ``seed`` (pair p uses seed + p) unless ``idx_list`` is given."""
+    pts = []
+    for pr in pairs:
+        if isinstance(pr, (tuple, list)):
+            pts.append(_rt.pack_pairs(pr[0], pr[1]))
+        else:
+            pts.append(np.ascontiguousarray(pr, dtype=np.float64).reshape(-1, 4))
+    if idx_list is None:
+        idx_list = [_sampling.fast(p.shape[0], n_hyp, 8, seed + k) for k, p in enumerate(pts)]
+    return _rt.f_ransac_batched(pts, idx_list, thr=thr, **kw)
+
+
+def pnp_ransac_view(X, y, n_hyp=1024, thr2=(1.5 / 3217.0) ** 2, n=6, seed=0, idx=None, **kw) -> dict:
+    """DLT-PnP RANSAC of one view: X (N, 3), y (N, 2) C-normalised."""
+    X = np.asarray(X, dtype=np.float64)
+    if idx is None:
+        idx = _sampling.fast(X.shape[0], n_hyp, n, seed)
+    return _rt.pnp_ransac(X, y, idx, thr2, **kw)

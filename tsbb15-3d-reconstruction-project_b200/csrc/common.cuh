@@ -17,7 +17,6 @@ enum : int {
     RG_ERR_CUDA = -1,        // a CUDA runtime call failed
     RG_ERR_ARG = -2,         // invalid argument (null pointer, negative size, sample size unsupported ...)
     RG_ERR_NO_DEVICE = -3,   // no sm_100 device / wrong architecture
-    RG_ERR_OVERFLOW = -4,    // internal work-list overflow (never silently ignored)
 };
 
 void set_error(const char* fmt, ...);
@@ -141,8 +140,10 @@ struct PairInfo {
     int pt_off32, n_pad;       // offset / count in the normalised FP32 copy (points, multiples of kSub)
     int hyp_off, H;            // offset / count in the hypothesis arrays
     int item_off, nsplit;      // scorer work items of this pair: [item_off, item_off + ceil(H/kHypPerBlock)*nsplit)
-    int groups_per_split;      // kSub-point groups handled by one item
-    int pad0;
+    int groups_per_split;      // kSub-point groups handled by one item (multiple of 32 when nsplit > 1)
+    int words_per_hyp;         // guard-band bitmap: one bit per (hypothesis, group) -> ceil(n_pad / kSub / 32) words
+    long long word_off;        // offset of this pair's words in the bitmap: word(h, w) = word_off + h * words_per_hyp + w
+
     // frame of the FP32 scorer: x~ = (x - c1)/thr, y~ = (y - c2)/thr  => threshold is exactly 1, |x~|,|y~| <= B
     double c1x, c1y, c2x, c2y;
     double thr, B;
@@ -152,7 +153,7 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     // device workspaces (grow-only)
-    Buffer pair_info, bbox, pts32, F64, hyp32, flags, counts, worklist, stats, best, tie_stats;
+    Buffer pair_info, bbox, pts32, F64, hyp32, flags, counts, bitmap, stats, best, tie_stats;
     Buffer d_in_a, d_in_b, d_in_c;                 // device copies of host inputs (host-buffer entry points)
     Buffer d_out_a, d_out_b, d_out_c, d_out_d;     // device outputs of host-buffer entry points
     Buffer pose64, pose32, X32;                    // PnP path
@@ -160,9 +161,16 @@ struct Ctx {
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage
     long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // optional phase profiling (option 1): CUDA events on the launching stream around the phases of every call
+    int opt_profile = 0;
+    static constexpr int kProfPhases = 5;          // prepare, solve, score kernel, fixup+repair, select
+    static constexpr int kProfRing = 256;          // calls remembered between two reads
+    cudaEvent_t* prof_ev = nullptr;                // kProfRing * (kProfPhases + 1) events
+    int prof_calls = 0;                            // test hook: cap of the recheck work-list (0 = automatic)
 };
 
 int ensure_pinned(Buffer& b, size_t bytes);
+void prof_mark(Ctx* c, cudaStream_t st, int boundary);   // boundary 0 opens a call, 1..kProfPhases close the phases
 void release_pinned(Buffer& b);
 int ensure(Buffer& b, size_t bytes);      // grow-only cudaMalloc
 void release(Buffer& b);

@@ -46,6 +46,17 @@ void release(Buffer& b) {
     b.cap = 0;
 }
 
+void prof_mark(Ctx* c, cudaStream_t st, int boundary) {
+    if (!c->opt_profile || !c->prof_ev) return;
+    if (boundary == 0) {
+        if (c->prof_calls >= Ctx::kProfRing) return;          // ring full: later calls are not profiled
+    }
+    const int call = boundary == 0 ? c->prof_calls : c->prof_calls - 1;
+    if (call < 0 || call >= Ctx::kProfRing) return;
+    cudaEventRecord(c->prof_ev[call * (Ctx::kProfPhases + 1) + boundary], st);
+    if (boundary == 0) c->prof_calls++;
+}
+
 void release_pinned(Buffer& b) {
     if (b.ptr) cudaFreeHost(b.ptr);
     b.ptr = nullptr;
@@ -92,17 +103,61 @@ int rg_shutdown(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->worklist,
+    for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->bitmap,
                       &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_out_a, &c->d_out_b,
                       &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
         release(*b);
     release_pinned(c->h_stage);
     release_pinned(c->h_stats);
+    if (c->prof_ev) {
+        for (int i = 0; i < Ctx::kProfRing * (Ctx::kProfPhases + 1); ++i) cudaEventDestroy(c->prof_ev[i]);
+        delete[] c->prof_ev;
+    }
     if (c->staging_free) cudaEventDestroy(c->staging_free);
     delete c;
     return RG_OK;
 }
 
 int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
+
+// option 1: phase profiling (CUDA events on the launching stream around the phases of every RANSAC call)
+int rg_set_option(void* ctx, int option, long long value) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    Ctx* c = (Ctx*)ctx;
+    if (option == 1) {
+        c->opt_profile = value != 0;
+        c->prof_calls = 0;
+        if (c->opt_profile && !c->prof_ev) {
+            const int n = Ctx::kProfRing * (Ctx::kProfPhases + 1);
+            c->prof_ev = new cudaEvent_t[n];
+            for (int i = 0; i < n; ++i) RG_CUDA(cudaEventCreate(&c->prof_ev[i]));
+        }
+        return RG_OK;
+    }
+    set_error("invalid argument: unknown option %d", option);
+    return RG_ERR_ARG;
+}
+
+// Phase times of the calls made since profiling was switched on / last read (option 1): out_ms[0..4] = summed
+// milliseconds of {prepare, solve, score kernel, fixup + repair, select}, *out_calls = number of calls covered.
+// Synchronises the stream; resets the ring.
+int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls) {
+    RG_CHECK_ARG(ctx != nullptr && out_ms5 != nullptr && out_calls != nullptr, "null argument");
+    Ctx* c = (Ctx*)ctx;
+    RG_CUDA(cudaSetDevice(c->device));
+    RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < Ctx::kProfPhases; ++k) out_ms5[k] = 0.0;
+    *out_calls = c->prof_calls;
+    for (int call = 0; call < c->prof_calls; ++call) {
+        cudaEvent_t* e = c->prof_ev + call * (Ctx::kProfPhases + 1);
+        for (int k = 0; k < Ctx::kProfPhases; ++k) {
+            float ms = 0.f;
+            RG_CUDA(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+            out_ms5[k] += ms;
+        }
+    }
+    c->prof_calls = 0;
+    return RG_OK;
+}
 
 }  // extern "C"

@@ -1,104 +1,11 @@
 // Host orchestration + C ABI of the F-matrix RANSAC path.  See include/rg_b200.h for the contract of each entry point.
 #include "f_kernels.cuh"
 #include "jacobi.cuh"
+#include "plan.cuh"
 #include <algorithm>
 #include <vector>
 
 namespace rg {
-
-struct FPlan {
-    int P = 0;
-    long long Ntot = 0, Htot = 0, N32tot = 0;
-    int n_items = 0;
-    int maxN = 0, maxH = 0;
-    long long total_groups_hyps = 0;     // sum_p H_p * ngroups_p  (upper bound on recheck records)
-};
-
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
-
-// Fill the PairInfo table (integer part) on the host and upload it.  Work items of the packed scorer:
-// item = (pair, 512-hypothesis block, contiguous range of 32-point groups).  The ranges are sized so that the total
-// item count is a multiple of the persistent grid when the batch allows it (static round-robin has no tail then).
-static int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan) {
-    RG_CHECK_ARG(P >= 0 && P <= 65535, "number of pairs must be in [0, 65535]");
-    RG_CHECK_ARG(pair_off != nullptr && hyp_off != nullptr, "offset arrays are null");
-    RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
-    plan = FPlan();
-    plan.P = P;
-    if (P == 0) return RG_OK;
-    for (int p = 0; p < P; ++p) {
-        RG_CHECK_ARG(pair_off[p + 1] >= pair_off[p] && hyp_off[p + 1] >= hyp_off[p], "offset arrays must be non-decreasing");
-    }
-    int rc = ensure_pinned(c->h_stage, sizeof(PairInfo) * (size_t)P);
-    if (rc) return rc;
-    RG_CUDA(cudaEventSynchronize(c->staging_free));
-    PairInfo* pi = (PairInfo*)c->h_stage.ptr;
-
-    long long unit_total = 0;      // work in units of (hypothesis block x point group)
-    long long off32 = 0;
-    for (int p = 0; p < P; ++p) {
-        PairInfo& o = pi[p];
-        memset(&o, 0, sizeof(o));
-        o.pt_off = pair_off[p];
-        o.n = pair_off[p + 1] - pair_off[p];
-        o.hyp_off = hyp_off[p];
-        o.H = hyp_off[p + 1] - hyp_off[p];
-        o.n_pad = ((o.n + kSub - 1) / kSub) * kSub;
-        o.pt_off32 = (int)off32;
-        off32 += o.n_pad;
-        plan.maxN = std::max(plan.maxN, o.n);
-        plan.maxH = std::max(plan.maxH, o.H);
-        const long long nhb = ceil_div(o.H, kHypPerBlock), ng = o.n_pad / kSub;
-        unit_total += nhb * ng;
-        plan.total_groups_hyps += (long long)o.H * ng;
-    }
-    RG_CHECK_ARG(off32 < (1ll << 31) && (long long)hyp_off[P] * 9 < (1ll << 40), "batch too large for 32-bit offsets");
-    plan.Ntot = pair_off[P];
-    plan.Htot = hyp_off[P];
-    plan.N32tot = off32;
-
-    const long long grid = (long long)c->sm_count * 2;
-    // aim for ~8 items per resident block, never below 8 groups (256 points) per item
-    long long gps_target = std::max<long long>(8, unit_total / std::max<long long>(1, grid * 8));
-    long long hb_total = 0;
-    for (int p = 0; p < P; ++p) hb_total += ceil_div(pi[p].H, kHypPerBlock) * (pi[p].n_pad > 0 ? 1 : 0);
-    // uniform batches: nudge the split so that (#items) % grid == 0
-    bool uniform = true;
-    for (int p = 1; p < P; ++p) uniform = uniform && pi[p].n_pad == pi[0].n_pad && pi[p].H == pi[0].H;
-    if (uniform && hb_total > 0 && pi[0].n_pad > 0) {
-        const long long ng = pi[0].n_pad / kSub;
-        long long ns0 = std::max<long long>(1, ceil_div(ng, gps_target));
-        long long best_ns = ns0;
-        for (long long ns = ns0; ns <= std::min<long long>(ng, ns0 * 2 + 4); ++ns) {
-            if ((hb_total * ns) % grid == 0) { best_ns = ns; break; }
-        }
-        gps_target = std::max<long long>(1, ceil_div(ng, best_ns));
-    }
-    long long item_off = 0;
-    for (int p = 0; p < P; ++p) {
-        PairInfo& o = pi[p];
-        const int ng = o.n_pad / kSub;
-        const int nhb = ceil_div(o.H, kHypPerBlock);
-        o.item_off = (int)item_off;
-        if (ng == 0 || nhb == 0) { o.nsplit = 1; o.groups_per_split = 0; continue; }     // contributes no items
-        int gps = (int)std::min<long long>(ng, gps_target);
-        int ns = ceil_div(ng, gps);
-        gps = ceil_div(ng, ns);
-        ns = ceil_div(ng, gps);
-        o.nsplit = ns;
-        o.groups_per_split = gps;
-        item_off += (long long)nhb * ns;
-    }
-    RG_CHECK_ARG(item_off < (1ll << 31), "too many scorer work items");
-    plan.n_items = (int)item_off;
-    // (pairs without items share their item_off with the next pair; decode_item takes the LAST pair whose
-    //  item_off <= item, which is never an empty one)
-    rc = ensure(c->pair_info, sizeof(PairInfo) * (size_t)P);
-    if (rc) return rc;
-    RG_CUDA(cudaMemcpyAsync(c->pair_info.ptr, pi, sizeof(PairInfo) * (size_t)P, cudaMemcpyHostToDevice, st));
-    RG_CUDA(cudaEventRecord(c->staging_free, st));
-    return RG_OK;
-}
 
 static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, double thr) {
     const int P = plan.P;
@@ -117,7 +24,7 @@ static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const double* p
     return RG_OK;
 }
 
-static int f_workspace(Ctx* c, const FPlan& plan, int* wl_cap) {
+static int f_workspace(Ctx* c, const FPlan& plan) {
     int rc;
     const size_t H = (size_t)std::max<long long>(plan.Htot, 1);
     if ((rc = ensure(c->F64, sizeof(double) * 9 * H))) return rc;
@@ -128,11 +35,7 @@ static int f_workspace(Ctx* c, const FPlan& plan, int* wl_cap) {
     if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure(c->tie_stats, sizeof(double2) * H))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
-    long long cap = std::min<long long>(plan.total_groups_hyps, std::max<long long>(1ll << 22, plan.total_groups_hyps / 8));
-    cap = std::max<long long>(cap, 1024);
-    cap = std::min<long long>(cap, (1ll << 31) - 1);
-    if ((rc = ensure(c->worklist, sizeof(int2) * (size_t)cap))) return rc;
-    *wl_cap = (int)cap;
+    if ((rc = ensure(c->bitmap, sizeof(unsigned) * (size_t)std::max<long long>(plan.total_words, 1)))) return rc;
     return RG_OK;
 }
 
@@ -156,7 +59,7 @@ static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
 }
 
 template <int MODE>
-static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, int score_path, int wl_cap) {
+static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, int score_path) {
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     int* counts = (int*)c->counts.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
@@ -165,30 +68,30 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     if (plan.Htot == 0 || plan.Ntot == 0) return RG_OK;
     if (score_path == SCORE_FP32_GUARDED) {
         if (plan.n_items > 0) {
+            constexpr size_t smem = score_smem_bytes<EpiPolicy<MODE>>();
             static bool attr_set = false;
             if (!attr_set) {
-                RG_CUDA(cudaFuncSetAttribute(f_score_packed<MODE_EPI_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kScoreSmemBytes));
-                RG_CUDA(cudaFuncSetAttribute(f_score_packed<MODE_SAMPSON>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kScoreSmemBytes));
+                RG_CUDA(cudaFuncSetAttribute(score_packed<EpiPolicy<MODE>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
                 attr_set = true;
             }
             const int grid = std::min(plan.n_items, c->sm_count * 2);
-            f_score_packed<MODE><<<grid, kScoreThreads, kScoreSmemBytes, st>>>(
+            score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>(
                 (const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr, pi, plan.P, plan.n_items, counts,
-                (int2*)c->worklist.ptr, stats, wl_cap);
-            f_fixup<MODE><<<c->sm_count * 4, 256, 0, st>>>((const float4*)c->pts32.ptr, (const double4*)pts64,
-                                                           (const Hyp32*)c->hyp32.ptr, (const double*)c->F64.ptr, pi, plan.P,
-                                                           counts, (const int2*)c->worklist.ptr, stats, wl_cap);
-            // exact FP64 rescoring of everything, executed only if the recheck work-list overflowed (stats[3] != 0)
-            f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, 1), 128, 0, st>>>(
-                (const double4*)pts64, (const double*)c->F64.ptr, pi, MODE, counts, stats + 3);
-            c->last_stats[7] += 3;
+                (unsigned*)c->bitmap.ptr);
+            prof_mark(c, st, 3);
+            const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
+                                                                              (plan.total_words + 255) / 256));
+            f_fixup<MODE><<<fgrid, 256, 0, st>>>((const float4*)c->pts32.ptr, (const double4*)pts64,
+                                                 (const Hyp32*)c->hyp32.ptr, (const double*)c->F64.ptr, pi, plan.P,
+                                                 plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
+            c->last_stats[7] += 2;
         }
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
         f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, zs), 128, 0, st>>>(
-            (const double4*)pts64, (const double*)c->F64.ptr, pi, MODE, counts, nullptr);
+            (const double4*)pts64, (const double*)c->F64.ptr, pi, MODE, counts);
+        prof_mark(c, st, 3);
         c->last_stats[7] += 1;
     }
     RG_CUDA(cudaGetLastError());
@@ -201,7 +104,7 @@ static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const dou
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     int* counts = (int*)c->counts.ptr;
     int2* best = (int2*)c->best.ptr;
-    f_argmax<<<plan.P, 256, 0, st>>>(counts, pi, best);
+    argmax_counts<<<plan.P, 256, 0, st>>>(counts, pi, best);
     c->last_stats[7] += 1;
     if (tie_mode == TIE_REFERENCE && plan.Htot > 0) {
         const int nb = (int)std::min<long long>(plan.Htot, (long long)c->sm_count * 8);
@@ -240,18 +143,22 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, int P, const double* pts64, con
         const int n = pair_off[p + 1] - pair_off[p], H = hyp_off[p + 1] - hyp_off[p];
         RG_CHECK_ARG(H == 0 || n >= 8, "a pair with hypotheses needs at least 8 correspondences");
     }
-    int wl_cap = 0;
-    if ((rc = f_workspace(c, plan, &wl_cap))) return rc;
+    if ((rc = f_workspace(c, plan))) return rc;
     c->last_stats[7] = 0;
     if (P == 0) return RG_OK;
+    prof_mark(c, st, 0);
     if ((rc = f_prepare(c, st, plan, pts64, thr))) return rc;
+    prof_mark(c, st, 1);
     rc = (mode == MODE_SAMPSON) ? f_solve_launch<MODE_SAMPSON>(c, st, plan, pts64, idx, solver)
                                 : f_solve_launch<MODE_EPI_MAX>(c, st, plan, pts64, idx, solver);
     if (rc) return rc;
-    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, pts64, score_path, wl_cap)
-                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, pts64, score_path, wl_cap);
+    prof_mark(c, st, 2);
+    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, pts64, score_path)
+                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, pts64, score_path);
     if (rc) return rc;
+    prof_mark(c, st, 4);
     if ((rc = f_select_launch(c, st, plan, pts64, mode, tie_mode, mask, best_F, best_idx, best_count))) return rc;
+    prof_mark(c, st, 5);
     return f_stats_readback(c, st);
 }
 
@@ -280,8 +187,8 @@ int rg_f_last_hypotheses_dev(void* ctx, const int** counts_dev, const double** F
     return RG_OK;
 }
 
-// out[0] recheck groups pushed, [1] band evaluations re-done in FP64, [2] decisions changed by the recheck,
-// [3] work-list overflow (FP64 rescoring was executed), [7] kernel launches of the last call.  Synchronises the stream.
+// out[0] guard-band groups flagged, [1] band evaluations re-done in FP64, [2] decisions changed by the recheck,
+// [7] kernel launches of the last call.  Synchronises the stream.
 int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
     RG_CHECK_ARG(ctx != nullptr && out8 != nullptr, "null argument");
     Ctx* c = (Ctx*)ctx;
@@ -348,8 +255,7 @@ int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64,
     FPlan plan;
     int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
     if (rc) return rc;
-    int wl_cap = 0;
-    if ((rc = f_workspace(c, plan, &wl_cap))) return rc;
+    if ((rc = f_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * std::max<size_t>((size_t)N, 1)))) return rc;
     if (N) RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, st));
     RG_CUDA(cudaMemcpyAsync(c->F64.ptr, F_all, sizeof(double) * 9 * (size_t)H, cudaMemcpyHostToDevice, st));
@@ -361,8 +267,8 @@ int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64,
     else
         f_make_hyp32<MODE_EPI_MAX><<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->F64.ptr, pi, 1, H, (Hyp32*)c->hyp32.ptr);
     c->last_stats[7] += 1;
-    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, (const double*)c->d_in_a.ptr, score_path, wl_cap)
-                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, (const double*)c->d_in_a.ptr, score_path, wl_cap);
+    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, (const double*)c->d_in_a.ptr, score_path)
+                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, (const double*)c->d_in_a.ptr, score_path);
     if (rc) return rc;
     if ((rc = f_stats_readback(c, st))) return rc;
     RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
@@ -385,8 +291,7 @@ int rg_f8pt_solve_host(void* ctx, void* stream, int N, const double* pts64, int 
     FPlan plan;
     int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
     if (rc) return rc;
-    int wl_cap = 0;
-    if ((rc = f_workspace(c, plan, &wl_cap))) return rc;
+    if ((rc = f_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * (size_t)N))) return rc;
     if ((rc = ensure(c->d_in_b, sizeof(int) * 8 * (size_t)H))) return rc;
     RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, st));

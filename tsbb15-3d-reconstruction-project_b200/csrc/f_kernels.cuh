@@ -13,14 +13,10 @@
 //   f_argmax / f_tie_stats / f_tie_resolve / f_mask   selection + winner's inlier mask (FP64)
 #pragma once
 #include "common.cuh"
+#include "score_core.cuh"
 
 namespace rg {
 
-constexpr int kScoreThreads = 256;
-constexpr int kHypPerThread = 2;
-constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
-constexpr int kChunkPts     = 1024;                            // points per shared-memory stage (16 KB)
-constexpr int kStages       = 2;
 
 // ------------------------------------------------------------------------------------------------
 // exact (FP64) criterion, same formula as lab3.py:213-227 + fun.py:316-317
@@ -442,252 +438,148 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP32 packed scorer
+// FP32 packed scorer policy for the epipolar criterion
 // ------------------------------------------------------------------------------------------------
-struct ScoreItem {
-    int pair, h_base, H_end;        // hypotheses [h_base, min(h_base + kHypPerBlock, H_end)) (global indices)
-    int g0, g1;                     // kSub-point groups [g0, g1) of the pair
-    const float4* src;              // packed points of the pair
-};
-
-__device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi, int P, int item) {
-    int lo = 0, hi = P;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].item_off <= item) lo = mid; else hi = mid; }
-    const PairInfo& info = pi[lo];
-    const int local = item - info.item_off;
-    const int hb = local / info.nsplit;
-    const int sp = local - hb * info.nsplit;
-    ScoreItem it;
-    it.pair = lo;
-    it.h_base = info.hyp_off + hb * kHypPerBlock;
-    it.H_end = info.hyp_off + info.H;
-    const int ngroups = info.n_pad / kSub;
-    it.g0 = min(sp * info.groups_per_split, ngroups);
-    it.g1 = min(it.g0 + info.groups_per_split, ngroups);
-    it.src = nullptr;
-    return it;
-}
-
-struct Hyp2 {            // one hypothesis, every coefficient duplicated into both halves of a 64-bit register pair
+struct Hyp2 {            // one hypothesis; ptxas keeps the coefficients scalar and broadcasts them inside FFMA2
     float2 f[9];
 };
 
-// hypothesis record from the item's shared-memory stage (or an all-NaN hypothesis past the end of the pair)
-__device__ __forceinline__ void load_hyp2(const Hyp32* __restrict__ sh, int slot, bool valid, Hyp2& out, float& G) {
-    if (valid) {
-        const float4* p = reinterpret_cast<const float4*>(sh + slot);
-        const float4 a = p[0], b = p[1], c = p[2];
-        const float f[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
-#pragma unroll
-        for (int k = 0; k < 9; ++k) out.f[k] = make_float2(f[k], f[k]);
-        G = c.y;
-    } else {
-        const float qnan = __int_as_float(0x7FFFFFFF);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) out.f[k] = make_float2(qnan, qnan);
-        G = 0.f;
-    }
-}
-
-// two correspondences (a,b) against one hypothesis; identical IEEE op sequence per lane as epi_q32
 template <int MODE>
-__device__ __forceinline__ void eval2(const Hyp2& H, const float4 X, const float4 Y, unsigned& cnt, float& minabs) {
-    const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
-    const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
-    const float2 l1x = __ffma2_rn(H.f[0], y0, __ffma2_rn(H.f[1], y1, H.f[2]));
-    const float2 l1y = __ffma2_rn(H.f[3], y0, __ffma2_rn(H.f[4], y1, H.f[5]));
-    const float2 l1z = __ffma2_rn(H.f[6], y0, __ffma2_rn(H.f[7], y1, H.f[8]));
-    const float2 r   = __ffma2_rn(l1x, x0, __ffma2_rn(l1y, x1, l1z));
-    const float2 l2x = __ffma2_rn(H.f[0], x0, __ffma2_rn(H.f[3], x1, H.f[6]));
-    const float2 l2y = __ffma2_rn(H.f[1], x0, __ffma2_rn(H.f[4], x1, H.f[7]));
-    const float2 s1  = __ffma2_rn(l1x, l1x, __fmul2_rn(l1y, l1y));
-    const float2 s2  = __ffma2_rn(l2x, l2x, __fmul2_rn(l2y, l2y));
-    float2 nm;
-    if (MODE == MODE_SAMPSON) {
-        const float2 m = __fadd2_rn(s1, s2);
-        nm = make_float2(-m.x, -m.y);
-    } else {
-        nm = make_float2(-fminf(s1.x, s2.x), -fminf(s1.y, s2.y));
+struct EpiPolicy {
+    typedef Hyp32 Rec;
+    typedef Hyp2 Regs;
+    static constexpr int kVec4PerPair = 2;      // [x0a x0b x1a x1b] [y0a y0b y1a y1b]
+    static constexpr int kChunkPts = 1024;      // 16 KB of points per stage
+
+    // hypothesis record from the item's shared-memory stage (or an all-NaN hypothesis past the end of the pair)
+    __device__ static __forceinline__ void load(const Hyp32* __restrict__ sh, int slot, bool valid, Hyp2& out, float& G) {
+        if (valid) {
+            const float4* p = reinterpret_cast<const float4*>(sh + slot);
+            const float4 a = p[0], b = p[1], c = p[2];
+            const float f[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out.f[k] = make_float2(f[k], f[k]);
+            G = c.y;
+        } else {
+            const float qnan = __int_as_float(0x7FFFFFFF);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out.f[k] = make_float2(qnan, qnan);
+            G = 0.f;
+        }
     }
-    const float2 q = __ffma2_rn(r, r, nm);
-    cnt += __float_as_uint(q.x) >> 31;
-    cnt += __float_as_uint(q.y) >> 31;
-    minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
-}
 
-// work-list record: one kSub-point group of one hypothesis whose FP32 result is inside the rounding band
-__device__ __forceinline__ void push_recheck(int2* __restrict__ wl, unsigned long long* __restrict__ stats, int cap, int h,
-                                             int group) {
-    const unsigned long long pos = atomicAdd(&stats[0], 1ull);
-    if (pos < (unsigned long long)cap) wl[pos] = make_int2(h, group);
-}
-
-// Shared-memory stage of the scorer: one chunk of packed points and (for the first chunk of a work item) the
-// item's hypothesis records.  Both arrive by 1-D bulk TMA on the same mbarrier.
-struct __align__(128) ScoreStage {
-    float4 pts[kChunkPts];           // 16 KB
-    Hyp32  hyp[kHypPerBlock];        // 24 KB
+    // two correspondences (a,b) against one hypothesis; identical IEEE op sequence per lane as epi_q32
+    __device__ static __forceinline__ void eval2(const Hyp2& H, const float4* __restrict__ pr, unsigned& cnt, float& minabs) {
+        const float4 X = pr[0], Y = pr[1];
+        const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
+        const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
+        const float2 l1x = __ffma2_rn(H.f[0], y0, __ffma2_rn(H.f[1], y1, H.f[2]));
+        const float2 l1y = __ffma2_rn(H.f[3], y0, __ffma2_rn(H.f[4], y1, H.f[5]));
+        const float2 l1z = __ffma2_rn(H.f[6], y0, __ffma2_rn(H.f[7], y1, H.f[8]));
+        const float2 r   = __ffma2_rn(l1x, x0, __ffma2_rn(l1y, x1, l1z));
+        const float2 l2x = __ffma2_rn(H.f[0], x0, __ffma2_rn(H.f[3], x1, H.f[6]));
+        const float2 l2y = __ffma2_rn(H.f[1], x0, __ffma2_rn(H.f[4], x1, H.f[7]));
+        const float2 s1  = __ffma2_rn(l1x, l1x, __fmul2_rn(l1y, l1y));
+        const float2 s2  = __ffma2_rn(l2x, l2x, __fmul2_rn(l2y, l2y));
+        float2 nm;
+        if (MODE == MODE_SAMPSON) {
+            const float2 m = __fadd2_rn(s1, s2);
+            nm = make_float2(-m.x, -m.y);
+        } else {
+            nm = make_float2(-fminf(s1.x, s2.x), -fminf(s1.y, s2.y));
+        }
+        const float2 q = __ffma2_rn(r, r, nm);
+        cnt += __float_as_uint(q.x) >> 31;
+        cnt += __float_as_uint(q.y) >> 31;
+        minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
+    }
 };
-constexpr size_t kScoreSmemBytes = kStages * sizeof(ScoreStage) + 64;
 
-// persistent block: items blockIdx.x, blockIdx.x + gridDim.x, ...; every item = 512 hypotheses x a contiguous
-// range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1 hypothesis.
-template <int MODE>
-__global__ void __launch_bounds__(kScoreThreads, 2)
-f_score_packed(const float4* __restrict__ pts32, const Hyp32* __restrict__ hyp32, const PairInfo* __restrict__ pi, int P,
-               int n_items, int* __restrict__ counts, int2* __restrict__ wl, unsigned long long* __restrict__ stats,
-               int wl_cap) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ScoreStage* st = reinterpret_cast<ScoreStage*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(ScoreStage));
-
-    const int tid = threadIdx.x;
-    int item = blockIdx.x;
-    if (item >= n_items) return;
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    uint32_t phases = 0u;
-    int stage = 0;
-
-    ScoreItem cur = decode_item(pi, P, item);
-    const float4* cur_src = pts32 + (size_t)pi[cur.pair].pt_off32;   // 1 float4 per point (pairs interleaved)
-    if (tid == 0) {
-        const uint32_t nb = (uint32_t)min((cur.g1 - cur.g0) * kSub, kChunkPts) * 16u;
-        const uint32_t hb = (uint32_t)min(kHypPerBlock, cur.H_end - cur.h_base) * (uint32_t)sizeof(Hyp32);
-        mbar_expect_tx(&full[0], nb + hb);
-        tma_load_1d(st[0].pts, cur_src + (size_t)cur.g0 * kSub, nb, &full[0]);
-        tma_load_1d(st[0].hyp, hyp32 + cur.h_base, hb, &full[0]);
-    }
-
-    while (true) {
-        const int next_item = item + gridDim.x;
-        const bool has_next = next_item < n_items;
-        ScoreItem nxt = cur;
-        const float4* nxt_src = cur_src;
-        if (has_next) {
-            nxt = decode_item(pi, P, next_item);
-            nxt_src = pts32 + (size_t)pi[nxt.pair].pt_off32;
-        }
-        Hyp2 H0, H1;
-        float G0 = 0.f, G1 = 0.f;
-        const int h0 = cur.h_base + tid, h1 = cur.h_base + kScoreThreads + tid;
-        unsigned cnt0 = 0, cnt1 = 0;
-
-        const int total_pts = (cur.g1 - cur.g0) * kSub;
-        for (int done = 0; done < total_pts; done += kChunkPts) {
-            const int npts = min(total_pts - done, kChunkPts);
-            // prefetch the following chunk (of this item, or the first chunk + hypotheses of the next item)
-            if (tid == 0) {
-                const int s2 = stage ^ 1;
-                if (done + kChunkPts < total_pts) {
-                    const uint32_t nb = (uint32_t)min(total_pts - done - kChunkPts, kChunkPts) * 16u;
-                    mbar_expect_tx(&full[s2], nb);
-                    tma_load_1d(st[s2].pts, cur_src + (size_t)cur.g0 * kSub + done + kChunkPts, nb, &full[s2]);
-                } else if (has_next) {
-                    const uint32_t nb = (uint32_t)min((nxt.g1 - nxt.g0) * kSub, kChunkPts) * 16u;
-                    const uint32_t hb = (uint32_t)min(kHypPerBlock, nxt.H_end - nxt.h_base) * (uint32_t)sizeof(Hyp32);
-                    mbar_expect_tx(&full[s2], nb + hb);
-                    tma_load_1d(st[s2].pts, nxt_src + (size_t)nxt.g0 * kSub, nb, &full[s2]);
-                    tma_load_1d(st[s2].hyp, hyp32 + nxt.h_base, hb, &full[s2]);
-                }
-            }
-            mbar_wait(&full[stage], (phases >> stage) & 1u);
-            phases ^= 1u << stage;
-
-            if (done == 0) {
-                load_hyp2(st[stage].hyp, tid, h0 < cur.H_end, H0, G0);
-                load_hyp2(st[stage].hyp, kScoreThreads + tid, h1 < cur.H_end, H1, G1);
-            }
-            const float4* sp = st[stage].pts;
-            const int ngr = npts / kSub;
-            const int gbase = cur.g0 + done / kSub;
-            for (int g = 0; g < ngr; ++g) {
-                float ma0 = INFINITY, ma1 = INFINITY;
-                const float4* gp = sp + g * kSub;
-#pragma unroll 4
-                for (int j = 0; j < kSub / 2; ++j) {
-                    const float4 X = gp[2 * j];
-                    const float4 Y = gp[2 * j + 1];
-                    eval2<MODE>(H0, X, Y, cnt0, ma0);
-                    eval2<MODE>(H1, X, Y, cnt1, ma1);
-                }
-                if (ma0 <= G0) push_recheck(wl, stats, wl_cap, h0, gbase + g);
-                if (ma1 <= G1) push_recheck(wl, stats, wl_cap, h1, gbase + g);
-            }
-            __syncthreads();          // everyone is done with this stage before it is refilled
-            stage ^= 1;
-        }
-        if (h0 < cur.H_end && cnt0) atomicAdd(&counts[h0], (int)cnt0);
-        if (h1 < cur.H_end && cnt1) atomicAdd(&counts[h1], (int)cnt1);
-        if (!has_next) break;
-        item = next_item;
-        cur = nxt;
-        cur_src = nxt_src;
-    }
-}
-
-// FP64 re-evaluation of the flagged groups: counts[h] += (#exact inliers - #FP32 inliers) over band evals
+// FP64 re-evaluation of the flagged groups: counts[h] += (#exact inliers - #FP32 inliers) over the band evaluations.
+// Threads scan the guard-band bitmap (one word per thread, coalesced); every set bit is then handled by the whole warp,
+// one lane per correspondence of the group.  stats: [0] flagged groups, [1] band evaluations, [2] changed decisions.
 template <int MODE>
 __global__ void __launch_bounds__(256) f_fixup(const float4* __restrict__ pts32, const double4* __restrict__ pts64,
                                                 const Hyp32* __restrict__ hyp32, const double* __restrict__ F64,
-                                                const PairInfo* __restrict__ pi, int P, int* __restrict__ counts,
-                                                const int2* __restrict__ wl, unsigned long long* __restrict__ stats,
-                                                int wl_cap) {
-    const unsigned long long pushed = stats[0];
-    const int nrec = (int)(pushed < (unsigned long long)wl_cap ? pushed : (unsigned long long)wl_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && pushed > (unsigned long long)wl_cap) stats[3] = 1ull;   // overflow
+                                                const PairInfo* __restrict__ pi, int P, long long total_words,
+                                                const unsigned* __restrict__ bitmap, int* __restrict__ counts,
+                                                unsigned long long* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < nrec; r += nwarps) {
-        const int2 rec = wl[r];
-        const int h = rec.x;
-        int lo = 0, hi = P;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
-        const PairInfo& info = pi[lo];
-        const int i = rec.y * kSub + lane;                     // point index inside the pair
-        int delta = 0, amb = 0;
-        if (i < info.n) {
-            const Hyp32 hy = hyp32[h];
-            const float4* gp = pts32 + (size_t)info.pt_off32 + (size_t)(i >> 1) * 2;
-            const float4 X = gp[0], Y = gp[1];
-            const bool second = i & 1;
-            const float q = epi_q32<MODE>(hy.f, second ? X.y : X.x, second ? X.w : X.z, second ? Y.y : Y.x,
-                                          second ? Y.w : Y.z);
-            if (fabsf(q) <= hy.G) {
-                const double4 v = pts64[info.pt_off + i];
-                const int in64 = epi_inlier64(F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
-                delta = in64 - (int)(__float_as_uint(q) >> 31);
-                amb = 1;
+    unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += stride) {
+        const long long wi = wbase + lane;
+        unsigned word = 0u;
+        int pair = 0, h = 0, gword = 0;
+        if (wi < total_words) {
+            word = bitmap[wi];
+            if (word) {
+                int lo = 0, hi = P;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].word_off <= wi) lo = mid; else hi = mid; }
+                pair = lo;
+                const long long local = wi - pi[lo].word_off;
+                const int hl = (int)(local / pi[lo].words_per_hyp);
+                gword = (int)(local - (long long)hl * pi[lo].words_per_hyp);
+                h = pi[lo].hyp_off + hl;
             }
         }
-        const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+        unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            unsigned bits = __shfl_sync(0xffffffffu, word, src);
+            const int rp = __shfl_sync(0xffffffffu, pair, src);
+            const int rh = __shfl_sync(0xffffffffu, h, src);
+            const int rg0 = __shfl_sync(0xffffffffu, gword, src) * 32;
+            const PairInfo& info = pi[rp];
+            const Hyp32 hy = hyp32[rh];
+            n_groups += (lane == 0) ? __popc(bits) : 0;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int i = (rg0 + b) * kSub + lane;                 // correspondence index inside the pair
+                int delta = 0, amb = 0;
+                if (i < info.n) {
+                    const float4* gp = pts32 + (size_t)info.pt_off32 + (size_t)(i >> 1) * 2;
+                    const float4 X = gp[0], Y = gp[1];
+                    const bool second = i & 1;
+                    const float q = epi_q32<MODE>(hy.f, second ? X.y : X.x, second ? X.w : X.z, second ? Y.y : Y.x,
+                                                  second ? Y.w : Y.z);
+                    if (fabsf(q) <= hy.G) {
+                        const double4 v = pts64[info.pt_off + i];
+                        const int in64 = epi_inlier64(F64 + (size_t)rh * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
+                        delta = in64 - (int)(__float_as_uint(q) >> 31);
+                        amb = 1;
+                    }
+                }
+                const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+                if (ambmask) {
+                    const unsigned chg = __ballot_sync(0xffffffffu, delta != 0);
+                    if (chg) {
+                        int d = delta;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
-        if (lane == 0) {
-            if (delta) atomicAdd(&counts[h], delta);
-            atomicAdd(&stats[1], (unsigned long long)__popc(ambmask));
-            if (delta) atomicAdd(&stats[2], (unsigned long long)(delta < 0 ? -delta : delta));
+                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                        if (lane == 0 && d) atomicAdd(&counts[rh], d);
+                        n_flip += (lane == 0) ? __popc(chg) : 0;
+                    }
+                    n_band += (lane == 0) ? __popc(ambmask) : 0;
+                }
+            }
         }
+    }
+    if (lane == 0) {
+        if (n_groups) atomicAdd(&stats[0], n_groups);
+        if (n_band) atomicAdd(&stats[1], n_band);
+        if (n_flip) atomicAdd(&stats[2], n_flip);
     }
 }
 
-// Plain FP64 scorer (reference formula for every evaluation).  One hypothesis per thread, points broadcast from
-// shared memory.  Two uses:
-//   * gate == nullptr : the SCORE_FP64 path and the on-device exact answer in tests; N may be split over gridDim.z
-//                       (counts must be zeroed beforehand, partial sums are added atomically);
-//   * gate != nullptr : repair pass after the packed scorer — does nothing unless *gate != 0 (recheck work-list
-//                       overflow), in which case every count is recomputed exactly and OVERWRITTEN (gridDim.z == 1).
+// Plain FP64 scorer (reference formula for every evaluation): the SCORE_FP64 path and the on-device exact answer in
+// tests.  One hypothesis per thread, points broadcast from shared memory; N may be split over gridDim.z (counts must be
+// zeroed beforehand, partial sums are added atomically).
 __global__ void __launch_bounds__(128) f_score_fp64(const double4* __restrict__ pts64, const double* __restrict__ F64,
-                                                     const PairInfo* __restrict__ pi, int mode, int* __restrict__ counts,
-                                                     const unsigned long long* __restrict__ gate) {
+                                                     const PairInfo* __restrict__ pi, int mode, int* __restrict__ counts) {
     __shared__ double4 sp[256];
-    if (gate != nullptr && *gate == 0ull) return;
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
     const int hl = blockIdx.x * blockDim.x + threadIdx.x;           // hypothesis inside the pair
@@ -711,42 +603,12 @@ __global__ void __launch_bounds__(128) f_score_fp64(const double4* __restrict__ 
             }
         }
     }
-    if (active) {
-        if (gate != nullptr) counts[info.hyp_off + hl] = cnt;
-        else if (cnt) atomicAdd(&counts[info.hyp_off + hl], cnt);
-    }
+    if (active && cnt) atomicAdd(&counts[info.hyp_off + hl], cnt);
 }
 
 // ------------------------------------------------------------------------------------------------
 // selection
 // ------------------------------------------------------------------------------------------------
-// best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
-__global__ void __launch_bounds__(256) f_argmax(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
-                                                 int2* __restrict__ best) {
-    __shared__ unsigned long long sk[8];
-    const int p = blockIdx.x;
-    const PairInfo info = pi[p];
-    unsigned long long key = 0ull;
-    for (int h = threadIdx.x; h < info.H; h += blockDim.x) {
-        const unsigned long long k =
-            ((unsigned long long)(unsigned)counts[info.hyp_off + h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
-        key = k > key ? k : key;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-        key = other > key ? other : key;
-    }
-    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) key = sk[w] > key ? sk[w] : key;
-        const int cnt = (int)(key >> 32);
-        const int idx = cnt > 0 ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : -1;
-        best[p] = make_int2(idx, cnt);
-    }
-}
-
 // tie_stats[h] = {std(d), ||d||_2} over all N points (FP64), only for hypotheses whose count equals the pair maximum
 // (the only ones the reference's tie rule fun.py:324-328 can ever look at once the maximum has appeared).
 __global__ void __launch_bounds__(256) f_tie_stats(const double4* __restrict__ pts64, const double* __restrict__ F64,

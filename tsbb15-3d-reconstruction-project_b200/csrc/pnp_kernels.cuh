@@ -1,0 +1,505 @@
+// Device code of the PnP-RANSAC path (sm_100a).
+//
+// Reference behaviour being restated (the reference code for this path does not run):
+//   pnp.py:132-152    DLT pose: rows vec(r_l x_k^T), r_l rows of [y_k]_x -> A (3m x 12); c0 = smallest right singular
+//                     vector -> C0 = (A|b); tau = sign det A; tau A = U S V^T; R = U V^T; t = (3 tau / tr S) b
+//   ransac.py:96-111  y' = R x + t for every correspondence; e = |pnorm(y) - pnorm(y')|^2; member iff thresh >= e;
+//                     keep the pose with the largest consensus
+//
+// Kernels: pnp_bbox_init / pnp_bbox / pnp_frame / pnp_normalise, pnp_solve_jacobi<n>, score_packed<PnpPolicy>,
+//          pnp_fixup, pnp_score_fp64, argmax_counts, pnp_finish.
+#pragma once
+#include "f_kernels.cuh"
+#include "jacobi.cuh"
+
+namespace rg {
+
+// FP32 scoring frame of one view:  X' = (X - cX)/sX (|X'| <= 1),  y^ = (y - cy)/sqrt(thr2)  (|y^| <= By)
+struct PnpFrame {
+    double cX[3], sX;
+    double cy[2], sthr;
+    double By, thr2;
+};
+
+// ------------------------------------------------------------------------------------------------
+// exact (FP64) membership test, ransac.py:31-35 + 96-105
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pnp_err64(const double* __restrict__ Rt /* R row-major (9) then t (3) */, double X0,
+                                            double X1, double X2, double y0, double y1) {
+    const double p0 = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+    const double p1 = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+    const double p2 = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+    const double a = y0 - p0 / p2;
+    const double b = y1 - p1 / p2;
+    return a * a + b * b;
+}
+__device__ __forceinline__ int pnp_inlier64(const double* __restrict__ Rt, double X0, double X1, double X2, double y0,
+                                            double y1, double thr2) {
+    return thr2 >= pnp_err64(Rt, X0, X1, X2, y0, y1) ? 1 : 0;      // inclusive, NaN -> not a member
+}
+
+// FP32 criterion in the view's frame:  q = a^2 + b^2 - w^2  (<= 0  <=>  member); scalar twin of PnpPolicy::eval2
+__device__ __forceinline__ float pnp_q32(const float* __restrict__ p, float X0, float X1, float X2, float y0, float y1) {
+    const float w  = __fmaf_rn(p[8], X0, __fmaf_rn(p[9], X1, __fmaf_rn(p[10], X2, p[11])));
+    const float p0 = __fmaf_rn(p[0], X0, __fmaf_rn(p[1], X1, __fmaf_rn(p[2], X2, p[3])));
+    const float p1 = __fmaf_rn(p[4], X0, __fmaf_rn(p[5], X1, __fmaf_rn(p[6], X2, p[7])));
+    const float a = __fmaf_rn(y0, w, p0);
+    const float b = __fmaf_rn(y1, w, p1);
+    const float t2 = __fmaf_rn(b, b, __fmul_rn(a, a));
+    return __fmaf_rn(-w, w, t2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame + packed FP32 points:  pair (a,b) = [X0a X0b X1a X1b] [X2a X2b y0a y0b] [y1a y1b 0 0]
+// ------------------------------------------------------------------------------------------------
+__global__ void pnp_bbox_init(int* __restrict__ bbox) {
+    const int i = threadIdx.x;
+    if (i < 10) bbox[i] = (i < 5) ? 0x7FFFFFFF : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(256) pnp_bbox(const double* __restrict__ X, const double* __restrict__ y, int N,
+                                                 int* __restrict__ bbox) {
+    float mn[5], mx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double c[5] = {X[3 * (size_t)i], X[3 * (size_t)i + 1], X[3 * (size_t)i + 2], y[2 * (size_t)i],
+                             y[2 * (size_t)i + 1]};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (isfinite(c[k])) {
+                mn[k] = fminf(mn[k], __double2float_rd(c[k]));
+                mx[k] = fmaxf(mx[k], __double2float_ru(c[k]));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            atomicMin(&bbox[k], f2key(mn[k]));
+            atomicMax(&bbox[5 + k], f2key(mx[k]));
+        }
+    }
+}
+
+__global__ void pnp_frame(PnpFrame* __restrict__ fr, const int* __restrict__ bbox, double thr2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double c[5], half[5];
+    for (int k = 0; k < 5; ++k) {
+        float lo = key2f(bbox[k]), hi = key2f(bbox[5 + k]);
+        if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }
+        c[k] = 0.5 * ((double)lo + (double)hi);
+        half[k] = fmax((double)hi - c[k], c[k] - (double)lo);
+    }
+    PnpFrame f;
+    f.cX[0] = c[0]; f.cX[1] = c[1]; f.cX[2] = c[2];
+    f.sX = fmax(fmax(half[0], half[1]), half[2]) * (1.0 + 1e-6) + 1e-300;
+    f.cy[0] = c[3]; f.cy[1] = c[4];
+    f.sthr = sqrt(thr2);
+    f.By = fmax(half[3], half[4]) / f.sthr * (1.0 + 1e-6) + 1e-30;
+    f.thr2 = thr2;
+    *fr = f;
+}
+
+__global__ void __launch_bounds__(256) pnp_normalise(const double* __restrict__ X, const double* __restrict__ y, int N,
+                                                      int n_pad, const PnpFrame* __restrict__ frp,
+                                                      float4* __restrict__ out) {
+    const PnpFrame fr = *frp;
+    const float qnan = __int_as_float(0x7FFFFFFF);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad / 2; j += gridDim.x * blockDim.x) {
+        float v[2][5];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = 2 * j + s;
+            if (i < N) {
+                v[s][0] = (float)((X[3 * (size_t)i] - fr.cX[0]) / fr.sX);
+                v[s][1] = (float)((X[3 * (size_t)i + 1] - fr.cX[1]) / fr.sX);
+                v[s][2] = (float)((X[3 * (size_t)i + 2] - fr.cX[2]) / fr.sX);
+                v[s][3] = (float)((y[2 * (size_t)i] - fr.cy[0]) / fr.sthr);
+                v[s][4] = (float)((y[2 * (size_t)i + 1] - fr.cy[1]) / fr.sthr);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) v[s][k] = qnan;
+            }
+        }
+        float4* o = out + (size_t)j * 3;
+        o[0] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+        o[1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+        o[2] = make_float4(v[0][4], v[1][4], 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose (FP64) -> Pose32 in the view's frame + rounding band G   (derivation: DESIGN.md "guard band", PnP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void make_pose32(const double* __restrict__ Rt, const PnpFrame& fr, Pose32* __restrict__ out) {
+    // y' = R X + t = (sX R) X' + (R cX + t)
+    double row[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        row[i][0] = Rt[3 * i + 0] * fr.sX;
+        row[i][1] = Rt[3 * i + 1] * fr.sX;
+        row[i][2] = Rt[3 * i + 2] * fr.sX;
+        row[i][3] = Rt[3 * i + 0] * fr.cX[0] + Rt[3 * i + 1] * fr.cX[1] + Rt[3 * i + 2] * fr.cX[2] + Rt[9 + i];
+    }
+    double q[12];
+    const double inv = 1.0 / fr.sthr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        q[j]     = (fr.cy[0] * row[2][j] - row[0][j]) * inv;      // p0' = (cy0 y'2 - y'0)/sqrt(thr2)
+        q[4 + j] = (fr.cy[1] * row[2][j] - row[1][j]) * inv;
+        q[8 + j] = row[2][j];
+    }
+    double rho0 = 0.0, rho1 = 0.0, rho2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { rho0 += fabs(q[j]); rho1 += fabs(q[4 + j]); rho2 += fabs(q[8 + j]); }
+    const double phi = fmax(fmax(fr.By * rho2 + rho0, fr.By * rho2 + rho1), rho2);
+    Pose32 h;
+    if (!(phi > 0.0) || !isfinite(phi)) {
+        const float qnan = __int_as_float(0x7FFFFFFF);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) h.p[k] = qnan;
+        h.G = 0.f; h.pad0 = h.pad1 = h.pad2 = 0.f;
+        *out = h;
+        return;
+    }
+    const double sc = 1.0 / phi;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) h.p[k] = (float)(q[k] * sc);
+    rho0 *= sc; rho1 *= sc; rho2 *= sc;
+    const double eps = 5.9604644775390625e-08;
+    const double A0 = fr.By * rho2 + rho0, A1 = fr.By * rho2 + rho1;
+    const double G = 1.25 * 14.0 * eps * rho2 * (A0 + A1) +
+                     2.0 * (49.0 * eps * eps * (A0 * A0 + A1 * A1) + 16.0 * eps * rho2 * rho2 + 25.0 * eps * eps * rho2 * rho2);
+    h.G = __double2float_ru(G);
+    h.pad0 = h.pad1 = h.pad2 = 0.f;
+    *out = h;
+}
+
+__global__ void __launch_bounds__(256) pnp_make_pose32(const double* __restrict__ pose64, int H,
+                                                        const PnpFrame* __restrict__ fr, Pose32* __restrict__ pose32) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    double Rt[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Rt[k] = pose64[(size_t)h * 12 + k];
+    make_pose32(Rt, *fr, pose32 + h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint enforcement C0 = (A|b) -> (R|t)    pnp.py:147-151
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi3(double (&w)[3][3], double (&v)[3][3]) {
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            const double a = w[p][0] * w[p][0] + w[p][1] * w[p][1] + w[p][2] * w[p][2];
+            const double b = w[q][0] * w[q][0] + w[q][1] * w[q][1] + w[q][2] * w[q][2];
+            const double g = w[p][0] * w[q][0] + w[p][1] * w[q][1] + w[p][2] * w[q][2];
+            if (g != 0.0 && fabs(g) > 1e-16 * sqrt(a * b)) {
+                double c, s;
+                jacobi_rot(a, b, g, c, s);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double wp = w[p][i], wq = w[q][i];
+                    w[p][i] = c * wp - s * wq;
+                    w[q][i] = s * wp + c * wq;
+                    const double vp = v[p][i], vq = v[q][i];
+                    v[p][i] = c * vp - s * vq;
+                    v[q][i] = s * vp + c * vq;
+                }
+                rotated = true;
+            }
+        }
+        if (!rotated) break;
+    }
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// c0: 12-vector (row-major 3x4).  Rt: R row-major then t.  Returns false if the result is not finite.
+__device__ __forceinline__ bool enforce_pose(const double* __restrict__ c0, double* __restrict__ Rt) {
+    const double A[9] = {c0[0], c0[1], c0[2], c0[4], c0[5], c0[6], c0[8], c0[9], c0[10]};
+    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+                       A[2] * (A[3] * A[7] - A[4] * A[6]);
+    const double tau = det > 0.0 ? 1.0 : (det < 0.0 ? -1.0 : 0.0);
+    double w[3][3], v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { w[j][i] = tau * A[3 * i + j]; v[j][i] = (i == j) ? 1.0 : 0.0; }
+    jacobi3(w, v);
+    double sg[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sg[j] = sqrt(w[j][0] * w[j][0] + w[j][1] * w[j][1] + w[j][2] * w[j][2]);
+    // the two dominant singular pairs; the third direction follows from orthogonality (det(tau A) > 0 => proper R)
+    int i3 = 0;
+    if (sg[1] < sg[i3]) i3 = 1;
+    if (sg[2] < sg[i3]) i3 = 2;
+    double u1[3], u2[3], v1[3], v2[3];
+    double s1 = 0.0, s2 = 0.0;
+    {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j == i3) continue;
+            double* u = cnt == 0 ? u1 : u2;
+            double* vv = cnt == 0 ? v1 : v2;
+            const double inv = 1.0 / sg[j];
+            u[0] = w[j][0] * inv; u[1] = w[j][1] * inv; u[2] = w[j][2] * inv;
+            vv[0] = v[j][0]; vv[1] = v[j][1]; vv[2] = v[j][2];
+            if (cnt == 0) s1 = sg[j]; else s2 = sg[j];
+            ++cnt;
+        }
+    }
+    double u3[3], v3[3];
+    cross3(u1, u2, u3);
+    cross3(v1, v2, v3);
+    const double lam = 3.0 * tau / (s1 + s2 + sg[i3]);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double r = u1[i] * v1[j] + u2[i] * v2[j] + u3[i] * v3[j];
+            Rt[3 * i + j] = r;
+            ok = ok && isfinite(r);
+        }
+    Rt[9] = lam * c0[3]; Rt[10] = lam * c0[7]; Rt[11] = lam * c0[11];
+    ok = ok && isfinite(Rt[9]) && isfinite(Rt[10]) && isfinite(Rt[11]);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// minimal-sample DLT-PnP: one hypothesis per 16-lane group, register-resident one-sided Jacobi on the 3n x 12 matrix
+// ------------------------------------------------------------------------------------------------
+template <int NPTS>
+__global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double* __restrict__ X, const double* __restrict__ y,
+                                                                    const int* __restrict__ idx, int N, int H,
+                                                                    const PnpFrame* __restrict__ fr,
+                                                                    double* __restrict__ pose64, Pose32* __restrict__ pose32,
+                                                                    unsigned char* __restrict__ flags) {
+    constexpr int ROWS = 3 * NPTS;
+    const int lane = threadIdx.x & 31;
+    const int j = lane & 15;
+    const int base = lane & 16;
+    const int hq = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = hq < H;
+    const int h = live ? hq : H - 1;
+    const int ca = (j < 12) ? j / 4 : 0;       // which row of C0 this column multiplies
+    const int cb = j & 3;                      // which component of the homogeneous world point
+
+    double w[ROWS], v[12];
+#pragma unroll
+    for (int k = 0; k < NPTS; ++k) {
+        int q = idx[(size_t)h * NPTS + k];
+        q = q < 0 ? 0 : (q >= N ? N - 1 : q);
+        const double Xh[4] = {X[3 * (size_t)q], X[3 * (size_t)q + 1], X[3 * (size_t)q + 2], 1.0};
+        const double y0 = y[2 * (size_t)q], y1 = y[2 * (size_t)q + 1];
+        const double xb = cb == 0 ? Xh[0] : (cb == 1 ? Xh[1] : (cb == 2 ? Xh[2] : 1.0));
+        // rows of [y]_x for y = (y0, y1, 1):  r0 = (0,-1,y1)  r1 = (1,0,-y0)  r2 = (-y1,y0,0)
+        const double r0 = ca == 0 ? 0.0 : (ca == 1 ? -1.0 : y1);
+        const double r1 = ca == 0 ? 1.0 : (ca == 1 ? 0.0 : -y0);
+        const double r2 = ca == 0 ? -y1 : (ca == 1 ? y0 : 0.0);
+        const bool col = j < 12;
+        w[3 * k + 0] = col ? r0 * xb : 0.0;
+        w[3 * k + 1] = col ? r1 * xb : 0.0;
+        w[3 * k + 2] = col ? r2 * xb : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = (i == j) ? 1.0 : 0.0;
+
+    GroupJacobi<ROWS, 12>::run(w, v, j, base);
+    double s0, s1, smax;
+    const int jm = GroupJacobi<ROWS, 12>::smallest(w, j, s0, s1, smax);
+    double c0[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c0[i] = __shfl_sync(0xffffffffu, v[i], base + jm);
+    double Rt[12];
+    const bool ok = enforce_pose(c0, Rt);
+    if (live && j == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pose64[(size_t)h * 12 + k] = Rt[k];
+        unsigned char fl = 0;
+        // minimiser not unique: sigma_11 ~ sigma_12 relative to sigma_1
+        if (!(sqrt(s1) - sqrt(s0) > 1e-9 * sqrt(smax))) fl |= 1;
+        if (!ok) fl |= 2;
+        flags[h] = fl;
+        make_pose32(Rt, *fr, pose32 + h);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed FP32 scorer policy for the reprojection criterion
+// ------------------------------------------------------------------------------------------------
+struct Pose2 { float2 p[12]; };
+
+struct PnpPolicy {
+    typedef Pose32 Rec;
+    typedef Pose2 Regs;
+    static constexpr int kVec4PerPair = 3;
+    static constexpr int kChunkPts = 512;       // 12 KB of points per stage (half a bitmap word)
+
+    __device__ static __forceinline__ void load(const Pose32* __restrict__ sh, int slot, bool valid, Pose2& out, float& G) {
+        if (valid) {
+            const float4* p = reinterpret_cast<const float4*>(sh + slot);
+            const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+            const float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out.p[k] = make_float2(f[k], f[k]);
+            G = d.x;
+        } else {
+            const float qnan = __int_as_float(0x7FFFFFFF);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out.p[k] = make_float2(qnan, qnan);
+            G = 0.f;
+        }
+    }
+
+    __device__ static __forceinline__ void eval2(const Pose2& H, const float4* __restrict__ pr, unsigned& cnt, float& minabs) {
+        const float4 A = pr[0], B = pr[1];
+        const float2 Cc = *reinterpret_cast<const float2*>(pr + 2);
+        const float2 X0 = make_float2(A.x, A.y), X1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y);
+        const float2 y0 = make_float2(B.z, B.w), y1 = Cc;
+        const float2 w  = __ffma2_rn(H.p[8], X0, __ffma2_rn(H.p[9], X1, __ffma2_rn(H.p[10], X2, H.p[11])));
+        const float2 p0 = __ffma2_rn(H.p[0], X0, __ffma2_rn(H.p[1], X1, __ffma2_rn(H.p[2], X2, H.p[3])));
+        const float2 p1 = __ffma2_rn(H.p[4], X0, __ffma2_rn(H.p[5], X1, __ffma2_rn(H.p[6], X2, H.p[7])));
+        const float2 a = __ffma2_rn(y0, w, p0);
+        const float2 b = __ffma2_rn(y1, w, p1);
+        const float2 t2 = __ffma2_rn(b, b, __fmul2_rn(a, a));
+        const float2 q = __ffma2_rn(make_float2(-w.x, -w.y), w, t2);
+        cnt += __float_as_uint(q.x) >> 31;
+        cnt += __float_as_uint(q.y) >> 31;
+        minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
+    }
+};
+
+// FP64 re-evaluation of the flagged groups (single view): same bitmap scan as f_fixup
+__global__ void __launch_bounds__(256) pnp_fixup(const float4* __restrict__ pts32, const double* __restrict__ X,
+                                                  const double* __restrict__ y, int n_sel, const Pose32* __restrict__ pose32,
+                                                  const double* __restrict__ pose64, double thr2, int words_per_hyp,
+                                                  long long total_words, const unsigned* __restrict__ bitmap,
+                                                  int* __restrict__ counts, unsigned long long* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += stride) {
+        const long long wi = wbase + lane;
+        unsigned word = 0u;
+        if (wi < total_words) word = bitmap[wi];
+        const int h = (int)(wi / words_per_hyp);
+        const int gword = (int)(wi - (long long)h * words_per_hyp);
+        unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            unsigned bits = __shfl_sync(0xffffffffu, word, src);
+            const int rh = __shfl_sync(0xffffffffu, h, src);
+            const int rg0 = __shfl_sync(0xffffffffu, gword, src) * 32;
+            const Pose32 ps = pose32[rh];
+            n_groups += (lane == 0) ? __popc(bits) : 0;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int i = (rg0 + b) * kSub + lane;
+                int delta = 0, amb = 0;
+                if (i < n_sel) {
+                    const float4* gp = pts32 + (size_t)(i >> 1) * 3;
+                    const float4 A = gp[0], B = gp[1], Cc = gp[2];
+                    const bool s = i & 1;
+                    const float q = pnp_q32(ps.p, s ? A.y : A.x, s ? A.w : A.z, s ? B.y : B.x, s ? B.w : B.z,
+                                            s ? Cc.y : Cc.x);
+                    if (fabsf(q) <= ps.G) {
+                        const int in64 = pnp_inlier64(pose64 + (size_t)rh * 12, X[3 * (size_t)i], X[3 * (size_t)i + 1],
+                                                      X[3 * (size_t)i + 2], y[2 * (size_t)i], y[2 * (size_t)i + 1], thr2);
+                        delta = in64 - (int)(__float_as_uint(q) >> 31);
+                        amb = 1;
+                    }
+                }
+                const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+                if (ambmask) {
+                    const unsigned chg = __ballot_sync(0xffffffffu, delta != 0);
+                    if (chg) {
+                        int d = delta;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                        if (lane == 0 && d) atomicAdd(&counts[rh], d);
+                        n_flip += (lane == 0) ? __popc(chg) : 0;
+                    }
+                    n_band += (lane == 0) ? __popc(ambmask) : 0;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (n_groups) atomicAdd(&stats[0], n_groups);
+        if (n_band) atomicAdd(&stats[1], n_band);
+        if (n_flip) atomicAdd(&stats[2], n_flip);
+    }
+}
+
+// Plain FP64 scorer (see f_score_fp64)
+__global__ void __launch_bounds__(128) pnp_score_fp64(const double* __restrict__ X, const double* __restrict__ y, int n_sel,
+                                                       const double* __restrict__ pose64, int H, double thr2,
+                                                       int* __restrict__ counts) {
+    __shared__ double sp[256 * 5];
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = h < H;
+    double Rt[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Rt[k] = active ? pose64[(size_t)h * 12 + k] : 0.0;
+    const int per = (n_sel + gridDim.z - 1) / gridDim.z;
+    const int n0 = min((int)blockIdx.z * per, n_sel), n1 = min(n0 + per, n_sel);
+    int cnt = 0;
+    for (int base = n0; base < n1; base += 256) {
+        const int m = min(256, n1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            sp[5 * i + 0] = X[3 * (size_t)(base + i)];
+            sp[5 * i + 1] = X[3 * (size_t)(base + i) + 1];
+            sp[5 * i + 2] = X[3 * (size_t)(base + i) + 2];
+            sp[5 * i + 3] = y[2 * (size_t)(base + i)];
+            sp[5 * i + 4] = y[2 * (size_t)(base + i) + 1];
+        }
+        __syncthreads();
+        if (active)
+            for (int i = 0; i < m; ++i)
+                cnt += pnp_inlier64(Rt, sp[5 * i], sp[5 * i + 1], sp[5 * i + 2], sp[5 * i + 3], sp[5 * i + 4], thr2);
+    }
+    if (active && cnt) atomicAdd(&counts[h], cnt);
+}
+
+// winner's pose + consensus mask over ALL N correspondences (FP64)
+__global__ void __launch_bounds__(256) pnp_finish(const double* __restrict__ X, const double* __restrict__ y, int N,
+                                                   const double* __restrict__ pose64, const int2* __restrict__ best,
+                                                   double thr2, unsigned char* __restrict__ mask, double* __restrict__ Rt_out,
+                                                   int* __restrict__ best_idx, int* __restrict__ best_count) {
+    const int2 b = best[0];
+    if (blockIdx.x == 0 && threadIdx.x < 12)
+        Rt_out[threadIdx.x] = b.x >= 0 ? pose64[(size_t)b.x * 12 + threadIdx.x] : nan("");
+    if (blockIdx.x == 0 && threadIdx.x == 0) { best_idx[0] = b.x; best_count[0] = b.y; }
+    if (mask == nullptr) return;
+    double Rt[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Rt[k] = b.x >= 0 ? pose64[(size_t)b.x * 12 + k] : nan("");
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        mask[i] = (unsigned char)pnp_inlier64(Rt, X[3 * (size_t)i], X[3 * (size_t)i + 1], X[3 * (size_t)i + 2],
+                                              y[2 * (size_t)i], y[2 * (size_t)i + 1], thr2);
+}
+
+}  // namespace rg

@@ -1,0 +1,201 @@
+// Generic persistent FP32 scorer skeleton shared by the F path (epipolar criterion) and the PnP path (reprojection
+// criterion).  A policy supplies the packed point layout, the hypothesis record and the two-point evaluation.
+#pragma once
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kScoreThreads = 256;
+constexpr int kHypPerThread = 2;
+constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
+constexpr int kStages       = 2;
+
+struct ScoreItem {
+    int pair, h_base, H_end;        // hypotheses [h_base, min(h_base + kHypPerBlock, H_end)) (global indices)
+    int g0, g1;                     // kSub-point groups [g0, g1) of the pair (g0 is a multiple of 32)
+    int W;                          // bitmap words per hypothesis of this pair
+    long long wbase;                // bitmap word of (first hypothesis of the item, group g0)
+};
+
+__device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi, int P, int item) {
+    int lo = 0, hi = P;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].item_off <= item) lo = mid; else hi = mid; }
+    const PairInfo& info = pi[lo];
+    const int local = item - info.item_off;
+    const int hb = local / info.nsplit;
+    const int sp = local - hb * info.nsplit;
+    ScoreItem it;
+    it.pair = lo;
+    it.h_base = info.hyp_off + hb * kHypPerBlock;
+    it.H_end = info.hyp_off + info.H;
+    const int ngroups = info.n_pad / kSub;
+    it.g0 = min(sp * info.groups_per_split, ngroups);
+    it.g1 = min(it.g0 + info.groups_per_split, ngroups);
+    it.W = info.words_per_hyp;
+    it.wbase = info.word_off + (long long)(hb * kHypPerBlock) * info.words_per_hyp + (it.g0 >> 5);
+    return it;
+}
+
+// Guard-band bookkeeping: one bit per (hypothesis, kSub-point group).  A set bit means "the FP32 result of at least
+// one evaluation of this group lies inside the rounding band of this hypothesis" and makes the fix-up kernel re-evaluate
+// that group in FP64.  Every 32-bit word (32 groups = 1024 points of one hypothesis) is written by exactly one thread of
+// exactly one work item, so the scorer needs no atomics and the bitmap needs no clearing.
+// Policy requirements:
+//   typedef Rec;                       hypothesis record in global/shared memory (sizeof % 16 == 0)
+//   typedef Regs;                      hypothesis in registers
+//   static constexpr int kVec4PerPair; float4 per packed point pair
+//   static constexpr int kChunkPts;    points per shared-memory stage
+//   static void load(const Rec* sh, int slot, bool valid, Regs&, float& G);
+//   static void eval2(const Regs&, const float4* pair, unsigned& cnt, float& minabs);
+template <class Pol>
+struct __align__(128) ScoreStage {
+    float4 pts[Pol::kChunkPts / 2 * Pol::kVec4PerPair];
+    typename Pol::Rec hyp[kHypPerBlock];
+};
+template <class Pol>
+constexpr size_t score_smem_bytes() { return kStages * sizeof(ScoreStage<Pol>) + 64; }
+
+// persistent block: items blockIdx.x, blockIdx.x + gridDim.x, ...; every item = 512 hypotheses x a contiguous
+// range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1 hypothesis.
+// Points and (at the first chunk of an item) hypothesis records arrive by 1-D bulk TMA on one mbarrier per stage;
+// the next chunk / next item is always in flight while the current one is being scored.
+template <class Pol>
+__global__ void __launch_bounds__(kScoreThreads, 2)
+score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restrict__ hyp32,
+             const PairInfo* __restrict__ pi, int P, int n_items, int* __restrict__ counts,
+             unsigned* __restrict__ bitmap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScoreStage<Pol>* st = reinterpret_cast<ScoreStage<Pol>*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(ScoreStage<Pol>));
+    constexpr int kChunkPts = Pol::kChunkPts;
+    constexpr uint32_t kPtBytes = Pol::kVec4PerPair * 8;        // bytes per point in the packed layout
+    constexpr int kV = Pol::kVec4PerPair;
+
+    const int tid = threadIdx.x;
+    int item = blockIdx.x;
+    if (item >= n_items) return;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t phases = 0u;
+    int stage = 0;
+
+    ScoreItem cur = decode_item(pi, P, item);
+    // packed points of the pair: kV float4 per point pair
+    const float4* cur_src = pts32 + (size_t)(pi[cur.pair].pt_off32 / 2) * kV;
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)min((cur.g1 - cur.g0) * kSub, kChunkPts) * kPtBytes;
+        const uint32_t hb = (uint32_t)min(kHypPerBlock, cur.H_end - cur.h_base) * (uint32_t)sizeof(typename Pol::Rec);
+        mbar_expect_tx(&full[0], nb + hb);
+        tma_load_1d(st[0].pts, cur_src + (size_t)cur.g0 * (kSub / 2) * kV, nb, &full[0]);
+        tma_load_1d(st[0].hyp, hyp32 + cur.h_base, hb, &full[0]);
+    }
+
+    while (true) {
+        const int next_item = item + gridDim.x;
+        const bool has_next = next_item < n_items;
+        ScoreItem nxt = cur;
+        const float4* nxt_src = cur_src;
+        if (has_next) {
+            nxt = decode_item(pi, P, next_item);
+            nxt_src = pts32 + (size_t)(pi[nxt.pair].pt_off32 / 2) * kV;
+        }
+        typename Pol::Regs H0, H1;
+        float G0 = 0.f, G1 = 0.f;
+        const int h0 = cur.h_base + tid, h1 = cur.h_base + kScoreThreads + tid;
+        unsigned cnt0 = 0, cnt1 = 0;
+        unsigned flag0 = 0u, flag1 = 0u;          // guard-band bits of the current 32-group word
+        unsigned* const w0 = bitmap + cur.wbase + (long long)tid * cur.W;
+        unsigned* const w1 = bitmap + cur.wbase + (long long)(kScoreThreads + tid) * cur.W;
+
+        const int total_pts = (cur.g1 - cur.g0) * kSub;
+        for (int done = 0; done < total_pts; done += kChunkPts) {
+            const int npts = min(total_pts - done, kChunkPts);
+            // prefetch the following chunk (of this item, or the first chunk + hypotheses of the next item)
+            if (tid == 0) {
+                const int s2 = stage ^ 1;
+                if (done + kChunkPts < total_pts) {
+                    const uint32_t nb = (uint32_t)min(total_pts - done - kChunkPts, kChunkPts) * kPtBytes;
+                    mbar_expect_tx(&full[s2], nb);
+                    tma_load_1d(st[s2].pts, cur_src + (size_t)(cur.g0 * kSub + done + kChunkPts) / 2 * kV, nb, &full[s2]);
+                } else if (has_next) {
+                    const uint32_t nb = (uint32_t)min((nxt.g1 - nxt.g0) * kSub, kChunkPts) * kPtBytes;
+                    const uint32_t hb =
+                        (uint32_t)min(kHypPerBlock, nxt.H_end - nxt.h_base) * (uint32_t)sizeof(typename Pol::Rec);
+                    mbar_expect_tx(&full[s2], nb + hb);
+                    tma_load_1d(st[s2].pts, nxt_src + (size_t)nxt.g0 * (kSub / 2) * kV, nb, &full[s2]);
+                    tma_load_1d(st[s2].hyp, hyp32 + nxt.h_base, hb, &full[s2]);
+                }
+            }
+            mbar_wait(&full[stage], (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+
+            if (done == 0) {
+                Pol::load(st[stage].hyp, tid, h0 < cur.H_end, H0, G0);
+                Pol::load(st[stage].hyp, kScoreThreads + tid, h1 < cur.H_end, H1, G1);
+            }
+            const float4* sp = st[stage].pts;
+            const int ngr = npts / kSub;
+            const int bit0 = (done / kSub) & 31;      // position of this chunk's first group inside its bitmap word
+            for (int g = 0; g < ngr; ++g) {
+                float ma0 = INFINITY, ma1 = INFINITY;
+                const float4* gp = sp + g * (kSub / 2) * kV;
+#pragma unroll 4
+                for (int j = 0; j < kSub / 2; ++j) {
+                    Pol::eval2(H0, gp + j * kV, cnt0, ma0);
+                    Pol::eval2(H1, gp + j * kV, cnt1, ma1);
+                }
+                flag0 |= (ma0 <= G0 ? 1u : 0u) << (bit0 + g);
+                flag1 |= (ma1 <= G1 ? 1u : 0u) << (bit0 + g);
+            }
+            // word complete (32 groups) or item finished: publish it
+            if (((done + npts) / kSub & 31) == 0 || done + npts >= total_pts) {
+                const int w = done / (kSub * 32);
+                if (h0 < cur.H_end) w0[w] = flag0;
+                if (h1 < cur.H_end) w1[w] = flag1;
+                flag0 = 0u; flag1 = 0u;
+            }
+            __syncthreads();          // everyone is done with this stage before it is refilled
+            stage ^= 1;
+        }
+        if (h0 < cur.H_end && cnt0) atomicAdd(&counts[h0], (int)cnt0);
+        if (h1 < cur.H_end && cnt1) atomicAdd(&counts[h1], (int)cnt1);
+        if (!has_next) break;
+        item = next_item;
+        cur = nxt;
+        cur_src = nxt_src;
+    }
+}
+
+// best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
+__global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
+                                                      int2* __restrict__ best) {
+    __shared__ unsigned long long sk[8];
+    const int p = blockIdx.x;
+    const PairInfo info = pi[p];
+    unsigned long long key = 0ull;
+    for (int h = threadIdx.x; h < info.H; h += blockDim.x) {
+        const unsigned long long k =
+            ((unsigned long long)(unsigned)counts[info.hyp_off + h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+        key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) key = sk[w] > key ? sk[w] : key;
+        const int cnt = (int)(key >> 32);
+        const int idx = cnt > 0 ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : -1;
+        best[p] = make_int2(idx, cnt);
+    }
+}
+
+}  // namespace rg

@@ -1,0 +1,132 @@
+"""Multi-GPU sharding of the RANSAC path: one process per GPU, ``torch.distributed`` (NCCL over NVLink) as plumbing.
+
+Two decompositions:
+
+* by image pair (``f_ransac_pairs_sharded``): pairs are independent, rank g takes a contiguous block of pairs, there is
+  NO collective on the data path; the tiny per-pair results (best index, count, F) are gathered afterwards.
+* by hypothesis block inside one pair (``f_ransac_split_hypotheses``): every rank holds all N correspondences, scores
+  its slice of the hypotheses, and ONE 8-byte max-all-reduce on the key ``(count << 32) | (0xFFFFFFFF - index)`` picks
+  the global winner with the lowest index among equal counts (= first-maximum rule of fun.py:320); the owner of the
+  winner broadcasts F and the inlier mask.
+
+``compute`` can be injected so the distributed logic is testable on CPU with the gloo backend (tests/ use the oracle
+there); by default it is the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import runtime as _rt
+
+
+def shard_range(n_units: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block partition: the first ``n_units % world`` ranks get one extra unit."""
+    base, extra = divmod(n_units, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def argmax_key(count: int, index: int) -> int:
+    """Monotone key: larger count wins, then the LOWER hypothesis index."""
+    return (int(count) << 32) | (0xFFFFFFFF - int(index))
+
+
+def key_decode(key: int) -> tuple[int, int]:
+    return int(key) >> 32, 0xFFFFFFFF - (int(key) & 0xFFFFFFFF)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _world(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _device_for_collectives(group=None):
+    import torch
+    dist = _dist()
+    if dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def f_ransac_pairs_sharded(pts_list, idx_list, thr=1.5, group=None, gather=True, compute=None, **kw) -> dict:
+    """Pair-sharded batched F-RANSAC.  Every rank passes the SAME full lists (or at least its own shard filled in);
+    returns, on every rank, arrays over all pairs when ``gather`` is True, else only the local shard's results."""
+    rank, world = _world(group)
+    P = len(pts_list)
+    lo, hi = shard_range(P, rank, world)
+    compute = compute or _rt.f_ransac_batched
+    local = compute(pts_list[lo:hi], idx_list[lo:hi], thr=thr, **kw)
+    out_local = {"range": (lo, hi), "best_idx": np.asarray(local["best_idx"]), "best_count": np.asarray(local["best_count"]),
+                 "F": np.asarray(local["F"])}
+    if not gather or world == 1:
+        return out_local
+    import torch
+    dist = _dist()
+    dev = _device_for_collectives(group)
+    # fixed-size payload per pair: [best_idx, best_count, F(9)] as float64 -> one all_gather of padded blocks
+    per = (P + world - 1) // world
+    buf = torch.full((per, 11), float("nan"), dtype=torch.float64)
+    n_loc = hi - lo
+    if n_loc:
+        buf[:n_loc, 0] = torch.from_numpy(out_local["best_idx"].astype(np.float64))
+        buf[:n_loc, 1] = torch.from_numpy(out_local["best_count"].astype(np.float64))
+        buf[:n_loc, 2:] = torch.from_numpy(out_local["F"].reshape(n_loc, 9))
+    buf = buf.to(dev)
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    best_idx = np.full(P, -1, dtype=np.int32)
+    best_count = np.zeros(P, dtype=np.int32)
+    F = np.full((P, 3, 3), np.nan)
+    for r in range(world):
+        a, b = shard_range(P, r, world)
+        if b > a:
+            blk = gathered[r][:b - a].cpu().numpy()
+            best_idx[a:b] = blk[:, 0].astype(np.int32)
+            best_count[a:b] = blk[:, 1].astype(np.int32)
+            F[a:b] = blk[:, 2:].reshape(-1, 3, 3)
+    return {"range": (lo, hi), "best_idx": best_idx, "best_count": best_count, "F": F}
+
+
+def f_ransac_split_hypotheses(pts, idx, thr=1.5, group=None, compute=None, **kw) -> dict:
+    """One pair, hypotheses split across ranks, one max-all-reduce of an int64 key (first-maximum selection)."""
+    import torch
+    rank, world = _world(group)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    H = idx.shape[0]
+    lo, hi = shard_range(H, rank, world)
+    compute = compute or _rt.f_ransac_batched
+    kw = dict(kw)
+    kw["want_mask"] = True
+    local = compute([pts], [idx[lo:hi]], thr=thr, **kw)
+    li = int(local["best_idx"][0])
+    key = argmax_key(int(local["best_count"][0]), lo + li) if li >= 0 else 0
+    if world == 1:
+        cnt, gi = key_decode(key) if key else (0, -1)
+        return {"best_idx": gi, "best_count": cnt, "F": local["F"][0], "mask": local["mask"][0], "owner": 0}
+    dist = _dist()
+    dev = _device_for_collectives(group)
+    k = torch.tensor([key], dtype=torch.int64, device=dev)
+    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+    gkey = int(k.item())
+    if gkey == 0:
+        n = np.asarray(pts).reshape(-1, 4).shape[0]
+        return {"best_idx": -1, "best_count": 0, "F": np.full((3, 3), np.nan), "mask": np.zeros(n, np.uint8), "owner": -1}
+    cnt, gi = key_decode(gkey)
+    owner = next(r for r in range(world) if shard_range(H, r, world)[0] <= gi < shard_range(H, r, world)[1])
+    n = np.asarray(pts).reshape(-1, 4).shape[0]
+    payload = torch.zeros(9 + n, dtype=torch.float64)
+    if rank == owner:
+        payload[:9] = torch.from_numpy(np.asarray(local["F"][0]).reshape(9))
+        payload[9:] = torch.from_numpy(np.asarray(local["mask"][0], dtype=np.float64))
+    payload = payload.to(dev)
+    dist.broadcast(payload, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    payload = payload.cpu().numpy()
+    return {"best_idx": gi, "best_count": cnt, "F": payload[:9].reshape(3, 3), "mask": payload[9:].astype(np.uint8),
+            "owner": owner}

@@ -32,6 +32,19 @@ def pack_pairs(p1, p2) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([p1.T, p2.T], axis=1))
 
 
+def set_option(option: int, value: int, device=None) -> None:
+    cabi.check(cabi.load_library().rg_set_option(_vp(cabi.context(device)), int(option), int(value)))
+
+
+def profile(device=None, stream=0) -> dict:
+    """Phase times (ms, summed) of the calls since profiling was enabled / last read: see rg_get_profile."""
+    out = (C.c_double * 5)()
+    n = C.c_int(0)
+    cabi.check(cabi.load_library().rg_get_profile(_vp(cabi.context(device)), _vp(stream), out, C.byref(n)))
+    return {"calls": n.value, "prepare_ms": out[0], "solve_ms": out[1], "score_ms": out[2], "fixup_ms": out[3],
+            "select_ms": out[4]}
+
+
 def last_stats(device=None, stream=0) -> dict:
     lib = cabi.load_library()
     out = (C.c_longlong * 8)()
