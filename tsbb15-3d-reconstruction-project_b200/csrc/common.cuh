@@ -66,7 +66,7 @@ struct __align__(16) Pose32 {
 };
 static_assert(sizeof(Pose32) == 64, "Pose32 layout");
 
-constexpr int kSub = 32;            // points per guard-band bookkeeping group (FP32 scorer)
+constexpr int kSub = 8;             // points per guard-band flag bit (FP32 scorer); 32 flags = one bitmap word = 256 points
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

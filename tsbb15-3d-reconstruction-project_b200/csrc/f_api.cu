@@ -82,9 +82,9 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
             prof_mark(c, st, 3);
             const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
                                                                               (plan.total_words + 255) / 256));
-            f_fixup<MODE><<<fgrid, 256, 0, st>>>((const float4*)c->pts32.ptr, (const double4*)pts64,
-                                                 (const Hyp32*)c->hyp32.ptr, (const double*)c->F64.ptr, pi, plan.P,
-                                                 plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
+            typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
+                                             (const double*)c->F64.ptr, pi, plan.P};
+            fixup_scan<EpiFix<MODE>><<<fgrid, 256, 0, st>>>(fp, plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
             c->last_stats[7] += 2;
         }
     } else {

@@ -495,84 +495,48 @@ struct EpiPolicy {
     }
 };
 
-// FP64 re-evaluation of the flagged groups: counts[h] += (#exact inliers - #FP32 inliers) over the band evaluations.
-// Threads scan the guard-band bitmap (one word per thread, coalesced); every set bit is then handled by the whole warp,
-// one lane per correspondence of the group.  stats: [0] flagged groups, [1] band evaluations, [2] changed decisions.
+// FP64 re-evaluation of the flagged groups (policy of fixup_scan, score_core.cuh)
 template <int MODE>
-__global__ void __launch_bounds__(256) f_fixup(const float4* __restrict__ pts32, const double4* __restrict__ pts64,
-                                                const Hyp32* __restrict__ hyp32, const double* __restrict__ F64,
-                                                const PairInfo* __restrict__ pi, int P, long long total_words,
-                                                const unsigned* __restrict__ bitmap, int* __restrict__ counts,
-                                                unsigned long long* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += stride) {
-        const long long wi = wbase + lane;
-        unsigned word = 0u;
-        int pair = 0, h = 0, gword = 0;
-        if (wi < total_words) {
-            word = bitmap[wi];
-            if (word) {
-                int lo = 0, hi = P;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].word_off <= wi) lo = mid; else hi = mid; }
-                pair = lo;
-                const long long local = wi - pi[lo].word_off;
-                const int hl = (int)(local / pi[lo].words_per_hyp);
-                gword = (int)(local - (long long)hl * pi[lo].words_per_hyp);
-                h = pi[lo].hyp_off + hl;
-            }
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            unsigned bits = __shfl_sync(0xffffffffu, word, src);
-            const int rp = __shfl_sync(0xffffffffu, pair, src);
-            const int rh = __shfl_sync(0xffffffffu, h, src);
-            const int rg0 = __shfl_sync(0xffffffffu, gword, src) * 32;
-            const PairInfo& info = pi[rp];
-            const Hyp32 hy = hyp32[rh];
-            n_groups += (lane == 0) ? __popc(bits) : 0;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int i = (rg0 + b) * kSub + lane;                 // correspondence index inside the pair
-                int delta = 0, amb = 0;
-                if (i < info.n) {
-                    const float4* gp = pts32 + (size_t)info.pt_off32 + (size_t)(i >> 1) * 2;
-                    const float4 X = gp[0], Y = gp[1];
-                    const bool second = i & 1;
-                    const float q = epi_q32<MODE>(hy.f, second ? X.y : X.x, second ? X.w : X.z, second ? Y.y : Y.x,
-                                                  second ? Y.w : Y.z);
-                    if (fabsf(q) <= hy.G) {
-                        const double4 v = pts64[info.pt_off + i];
-                        const int in64 = epi_inlier64(F64 + (size_t)rh * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
-                        delta = in64 - (int)(__float_as_uint(q) >> 31);
-                        amb = 1;
-                    }
-                }
-                const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
-                if (ambmask) {
-                    const unsigned chg = __ballot_sync(0xffffffffu, delta != 0);
-                    if (chg) {
-                        int d = delta;
+struct EpiFix {
+    struct Params {
+        const float4* pts32; const double4* pts64; const Hyp32* hyp32; const double* F64; const PairInfo* pi; int P;
+    };
+    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& pair) {
+        int lo = 0, hi = p.P;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].word_off <= wi) lo = mid; else hi = mid; }
+        const long long local = wi - p.pi[lo].word_off;
+        const int hl = (int)(local / p.pi[lo].words_per_hyp);
+        pair = lo;
+        h = p.pi[lo].hyp_off + hl;
+        fbase = (int)(local - (long long)hl * p.pi[lo].words_per_hyp) * 32;
+    }
+    // one flagged group = kSub consecutive correspondences of one hypothesis
+    __device__ static __forceinline__ int process(const Params& p, int h, int flag, int pair, int& n_band, int& n_flip) {
+        const PairInfo& info = p.pi[pair];
+        const Hyp32 hy = p.hyp32[h];
+        const float4* gp = p.pts32 + (size_t)info.pt_off32 + (size_t)flag * kSub;      // kSub/2 point pairs, 2 float4 each
+        int delta = 0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        if (lane == 0 && d) atomicAdd(&counts[rh], d);
-                        n_flip += (lane == 0) ? __popc(chg) : 0;
-                    }
-                    n_band += (lane == 0) ? __popc(ambmask) : 0;
+        for (int j = 0; j < kSub / 2; ++j) {
+            const float4 X = gp[2 * j], Y = gp[2 * j + 1];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = flag * kSub + 2 * j + s;
+                if (i >= info.n) continue;
+                const float q = epi_q32<MODE>(hy.f, s ? X.y : X.x, s ? X.w : X.z, s ? Y.y : Y.x, s ? Y.w : Y.z);
+                if (fabsf(q) <= hy.G) {
+                    const double4 v = p.pts64[info.pt_off + i];
+                    const int in64 = epi_inlier64(p.F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
+                    const int d = in64 - (int)(__float_as_uint(q) >> 31);
+                    delta += d;
+                    n_band += 1;
+                    n_flip += d != 0;
                 }
             }
         }
+        return delta;
     }
-    if (lane == 0) {
-        if (n_groups) atomicAdd(&stats[0], n_groups);
-        if (n_band) atomicAdd(&stats[1], n_band);
-        if (n_flip) atomicAdd(&stats[2], n_flip);
-    }
-}
+};
 
 // Plain FP64 scorer (reference formula for every evaluation): the SCORE_FP64 path and the on-device exact answer in
 // tests.  One hypothesis per thread, points broadcast from shared memory; N may be split over gridDim.z (counts must be

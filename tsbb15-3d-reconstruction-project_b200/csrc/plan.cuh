@@ -59,8 +59,8 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     plan.N32tot = off32;
 
     const long long grid = (long long)c->sm_count * 2;
-    // aim for ~8 items per resident block, never below 8 groups (256 points) per item
-    long long gps_target = std::max<long long>(8, unit_total / std::max<long long>(1, grid * 8));
+    // aim for ~8 items per resident block, never below 64 groups (512 points) per item
+    long long gps_target = std::max<long long>(64, unit_total / std::max<long long>(1, grid * 8));
     long long hb_total = 0;
     for (int p = 0; p < P; ++p) hb_total += ceil_div(pi[p].H, kHypPerBlock) * (pi[p].n_pad > 0 ? 1 : 0);
     // uniform batches: nudge the split so that (#items) % grid == 0

@@ -82,9 +82,9 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
             const int wph = (int)(plan.total_words / std::max(H, 1));
             const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
                                                                               (plan.total_words + 255) / 256));
-            pnp_fixup<<<fgrid, 256, 0, st>>>((const float4*)c->X32.ptr, X, y, n_sel, (const Pose32*)c->pose32.ptr,
-                                             (const double*)c->pose64.ptr, thr2, wph, plan.total_words,
-                                             (const unsigned*)c->bitmap.ptr, counts, stats);
+            PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, n_sel, (const Pose32*)c->pose32.ptr,
+                              (const double*)c->pose64.ptr, thr2, wph};
+            fixup_scan<PnpFix><<<fgrid, 256, 0, st>>>(fp, plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
             c->last_stats[7] += 2;
         }
     } else {

@@ -389,69 +389,42 @@ struct PnpPolicy {
     }
 };
 
-// FP64 re-evaluation of the flagged groups (single view): same bitmap scan as f_fixup
-__global__ void __launch_bounds__(256) pnp_fixup(const float4* __restrict__ pts32, const double* __restrict__ X,
-                                                  const double* __restrict__ y, int n_sel, const Pose32* __restrict__ pose32,
-                                                  const double* __restrict__ pose64, double thr2, int words_per_hyp,
-                                                  long long total_words, const unsigned* __restrict__ bitmap,
-                                                  int* __restrict__ counts, unsigned long long* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += stride) {
-        const long long wi = wbase + lane;
-        unsigned word = 0u;
-        if (wi < total_words) word = bitmap[wi];
-        const int h = (int)(wi / words_per_hyp);
-        const int gword = (int)(wi - (long long)h * words_per_hyp);
-        unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            unsigned bits = __shfl_sync(0xffffffffu, word, src);
-            const int rh = __shfl_sync(0xffffffffu, h, src);
-            const int rg0 = __shfl_sync(0xffffffffu, gword, src) * 32;
-            const Pose32 ps = pose32[rh];
-            n_groups += (lane == 0) ? __popc(bits) : 0;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int i = (rg0 + b) * kSub + lane;
-                int delta = 0, amb = 0;
-                if (i < n_sel) {
-                    const float4* gp = pts32 + (size_t)(i >> 1) * 3;
-                    const float4 A = gp[0], B = gp[1], Cc = gp[2];
-                    const bool s = i & 1;
-                    const float q = pnp_q32(ps.p, s ? A.y : A.x, s ? A.w : A.z, s ? B.y : B.x, s ? B.w : B.z,
-                                            s ? Cc.y : Cc.x);
-                    if (fabsf(q) <= ps.G) {
-                        const int in64 = pnp_inlier64(pose64 + (size_t)rh * 12, X[3 * (size_t)i], X[3 * (size_t)i + 1],
-                                                      X[3 * (size_t)i + 2], y[2 * (size_t)i], y[2 * (size_t)i + 1], thr2);
-                        delta = in64 - (int)(__float_as_uint(q) >> 31);
-                        amb = 1;
-                    }
-                }
-                const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
-                if (ambmask) {
-                    const unsigned chg = __ballot_sync(0xffffffffu, delta != 0);
-                    if (chg) {
-                        int d = delta;
+// FP64 re-evaluation of the flagged groups (single view; policy of fixup_scan, score_core.cuh)
+struct PnpFix {
+    struct Params {
+        const float4* pts32; const double* X; const double* y; int n_sel; const Pose32* pose32; const double* pose64;
+        double thr2; int words_per_hyp;
+    };
+    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& aux) {
+        h = (int)(wi / p.words_per_hyp);
+        fbase = (int)(wi - (long long)h * p.words_per_hyp) * 32;
+        aux = 0;
+    }
+    __device__ static __forceinline__ int process(const Params& p, int h, int flag, int, int& n_band, int& n_flip) {
+        const Pose32 ps = p.pose32[h];
+        const float4* gp = p.pts32 + (size_t)flag * (kSub / 2) * 3;
+        int delta = 0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        if (lane == 0 && d) atomicAdd(&counts[rh], d);
-                        n_flip += (lane == 0) ? __popc(chg) : 0;
-                    }
-                    n_band += (lane == 0) ? __popc(ambmask) : 0;
+        for (int j = 0; j < kSub / 2; ++j) {
+            const float4 A = gp[3 * j], B = gp[3 * j + 1], Cc = gp[3 * j + 2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = flag * kSub + 2 * j + s;
+                if (i >= p.n_sel) continue;
+                const float q = pnp_q32(ps.p, s ? A.y : A.x, s ? A.w : A.z, s ? B.y : B.x, s ? B.w : B.z, s ? Cc.y : Cc.x);
+                if (fabsf(q) <= ps.G) {
+                    const int in64 = pnp_inlier64(p.pose64 + (size_t)h * 12, p.X[3 * (size_t)i], p.X[3 * (size_t)i + 1],
+                                                  p.X[3 * (size_t)i + 2], p.y[2 * (size_t)i], p.y[2 * (size_t)i + 1], p.thr2);
+                    const int d = in64 - (int)(__float_as_uint(q) >> 31);
+                    delta += d;
+                    n_band += 1;
+                    n_flip += d != 0;
                 }
             }
         }
+        return delta;
     }
-    if (lane == 0) {
-        if (n_groups) atomicAdd(&stats[0], n_groups);
-        if (n_band) atomicAdd(&stats[1], n_band);
-        if (n_flip) atomicAdd(&stats[2], n_flip);
-    }
-}
+};
 
 // Plain FP64 scorer (see f_score_fp64)
 __global__ void __launch_bounds__(128) pnp_score_fp64(const double* __restrict__ X, const double* __restrict__ y, int n_sel,
