@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librg_b200.so")
+LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librg_b200.so"))   # RG_LIB: kernel-variant experiments
 
 MODE_EPI_MAX, MODE_SAMPSON = 0, 1
 TIE_FIRST, TIE_REFERENCE = 0, 1

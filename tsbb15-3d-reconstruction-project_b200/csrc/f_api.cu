@@ -69,13 +69,7 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     if (score_path == SCORE_FP32_GUARDED) {
         if (plan.n_items > 0) {
             constexpr size_t smem = score_smem_bytes<EpiPolicy<MODE>>();
-            static bool attr_set = false;
-            if (!attr_set) {
-                RG_CUDA(cudaFuncSetAttribute(score_packed<EpiPolicy<MODE>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-                attr_set = true;
-            }
-            const int grid = std::min(plan.n_items, c->sm_count * 2);
+            const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<EpiPolicy<MODE>>());
             score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>(
                 (const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr, pi, plan.P, plan.n_items, counts,
                 (unsigned*)c->bitmap.ptr);
@@ -137,7 +131,7 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, int P, const double* pts64, con
     RG_CHECK_ARG(score_path == SCORE_FP32_GUARDED || score_path == SCORE_FP64, "unknown scoring path");
     RG_CUDA(cudaSetDevice(c->device));
     FPlan plan;
-    int rc = f_plan(c, st, P, pair_off, hyp_off, plan);
+    int rc = f_plan(c, st, P, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
     if (rc) return rc;
     for (int p = 0; p < P; ++p) {
         const int n = pair_off[p + 1] - pair_off[p], H = hyp_off[p + 1] - hyp_off[p];
@@ -253,7 +247,7 @@ int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64,
     if (H == 0) return RG_OK;
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
+    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
     if (rc) return rc;
     if ((rc = f_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * std::max<size_t>((size_t)N, 1)))) return rc;
@@ -289,7 +283,7 @@ int rg_f8pt_solve_host(void* ctx, void* stream, int N, const double* pts64, int 
     RG_CHECK_ARG(idx != nullptr, "idx is null");
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
+    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
     if (rc) return rc;
     if ((rc = f_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * (size_t)N))) return rc;

@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // FP32 packed scorer policy for the epipolar criterion
 // ------------------------------------------------------------------------------------------------
-struct Hyp2 {            // one hypothesis; ptxas keeps the coefficients scalar and broadcasts them inside FFMA2
-    float2 f[9];
+struct Hyp2 {            // one hypothesis: nine scalar coefficients, broadcast inside FFMA2 (.F32 operand form)
+    float f[9];
 };
 
 template <int MODE>
@@ -449,7 +449,7 @@ struct EpiPolicy {
     typedef Hyp32 Rec;
     typedef Hyp2 Regs;
     static constexpr int kVec4PerPair = 2;      // [x0a x0b x1a x1b] [y0a y0b y1a y1b]
-    static constexpr int kChunkPts = 1024;      // 16 KB of points per stage
+    static constexpr int kChunkPts = RG_EPI_CHUNK;   // 16 KB of points per stage by default
 
     // hypothesis record from the item's shared-memory stage (or an all-NaN hypothesis past the end of the pair)
     __device__ static __forceinline__ void load(const Hyp32* __restrict__ sh, int slot, bool valid, Hyp2& out, float& G) {
@@ -458,40 +458,69 @@ struct EpiPolicy {
             const float4 a = p[0], b = p[1], c = p[2];
             const float f[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
 #pragma unroll
-            for (int k = 0; k < 9; ++k) out.f[k] = make_float2(f[k], f[k]);
+            for (int k = 0; k < 9; ++k) out.f[k] = f[k];
             G = c.y;
         } else {
             const float qnan = __int_as_float(0x7FFFFFFF);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) out.f[k] = make_float2(qnan, qnan);
+            for (int k = 0; k < 9; ++k) out.f[k] = qnan;
             G = 0.f;
         }
     }
 
-    // two correspondences (a,b) against one hypothesis; identical IEEE op sequence per lane as epi_q32
-    __device__ static __forceinline__ void eval2(const Hyp2& H, const float4* __restrict__ pr, unsigned& cnt, float& minabs) {
+    // two correspondences (a,b) against K hypotheses, written step-major across the hypotheses so that consecutive
+    // FFMA2 share their point operand (operand-reuse cache: the scorer is register-file-port bound);
+    // per lane the IEEE op sequence is identical to epi_q32
+    template <int K>
+    __device__ static __forceinline__ void evalN(const Hyp2 (&H)[K], const float4* __restrict__ pr, unsigned (&cnt)[K],
+                                                 float (&minabs)[K]) {
         const float4 X = pr[0], Y = pr[1];
         const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
         const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
-        const float2 l1x = __ffma2_rn(H.f[0], y0, __ffma2_rn(H.f[1], y1, H.f[2]));
-        const float2 l1y = __ffma2_rn(H.f[3], y0, __ffma2_rn(H.f[4], y1, H.f[5]));
-        const float2 l1z = __ffma2_rn(H.f[6], y0, __ffma2_rn(H.f[7], y1, H.f[8]));
-        const float2 r   = __ffma2_rn(l1x, x0, __ffma2_rn(l1y, x1, l1z));
-        const float2 l2x = __ffma2_rn(H.f[0], x0, __ffma2_rn(H.f[3], x1, H.f[6]));
-        const float2 l2y = __ffma2_rn(H.f[1], x0, __ffma2_rn(H.f[4], x1, H.f[7]));
-        const float2 s1  = __ffma2_rn(l1x, l1x, __fmul2_rn(l1y, l1y));
-        const float2 s2  = __ffma2_rn(l2x, l2x, __fmul2_rn(l2y, l2y));
-        float2 nm;
-        if (MODE == MODE_SAMPSON) {
-            const float2 m = __fadd2_rn(s1, s2);
-            nm = make_float2(-m.x, -m.y);
-        } else {
-            nm = make_float2(-fminf(s1.x, s2.x), -fminf(s1.y, s2.y));
+        float2 l1x[K], l1y[K], l1z[K], l2x[K], l2y[K], r[K], s1[K], s2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            l1x[k] = ffma2_sbs(H[k].f[1], y1, H[k].f[2]);
+            l1y[k] = ffma2_sbs(H[k].f[4], y1, H[k].f[5]);
+            l1z[k] = ffma2_sbs(H[k].f[7], y1, H[k].f[8]);
         }
-        const float2 q = __ffma2_rn(r, r, nm);
-        cnt += __float_as_uint(q.x) >> 31;
-        cnt += __float_as_uint(q.y) >> 31;
-        minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            l1x[k] = ffma2_sbc(H[k].f[0], y0, l1x[k]);
+            l1y[k] = ffma2_sbc(H[k].f[3], y0, l1y[k]);
+            l1z[k] = ffma2_sbc(H[k].f[6], y0, l1z[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            l2x[k] = ffma2_sbs(H[k].f[3], x1, H[k].f[6]);
+            l2y[k] = ffma2_sbs(H[k].f[4], x1, H[k].f[7]);
+            r[k]   = __ffma2_rn(l1y[k], x1, l1z[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            l2x[k] = ffma2_sbc(H[k].f[0], x0, l2x[k]);
+            l2y[k] = ffma2_sbc(H[k].f[1], x0, l2y[k]);
+            r[k]   = __ffma2_rn(l1x[k], x0, r[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            s1[k] = __ffma2_rn(l1x[k], l1x[k], __fmul2_rn(l1y[k], l1y[k]));
+            s2[k] = __ffma2_rn(l2x[k], l2x[k], __fmul2_rn(l2y[k], l2y[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float2 nm;
+            if (MODE == MODE_SAMPSON) {
+                const float2 m = __fadd2_rn(s1[k], s2[k]);
+                nm = make_float2(-m.x, -m.y);
+            } else {
+                nm = make_float2(-fminf(s1[k].x, s2[k].x), -fminf(s1[k].y, s2[k].y));
+            }
+            const float2 q = __ffma2_rn(r[k], r[k], nm);
+            cnt[k] += __float_as_uint(q.x) >> 31;
+            cnt[k] += __float_as_uint(q.y) >> 31;
+            minabs[k] = fminf(minabs[k], fminf(fabsf(q.x), fabsf(q.y)));
+        }
     }
 };
 

@@ -18,7 +18,22 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // Fill the PairInfo table (integer part) on the host and upload it.  Work items of the packed scorer:
 // item = (pair, 512-hypothesis block, contiguous range of 32-point groups).  The ranges are sized so that the total
 // item count is a multiple of the persistent grid when the batch allows it (static round-robin has no tail then).
-inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan) {
+// resident blocks per SM of a persistent scorer instantiation (queried once; also sets the dynamic smem attribute)
+template <class Pol>
+inline int score_blocks_per_sm() {
+    static int cached = 0;
+    if (cached == 0) {
+        constexpr size_t smem = score_smem_bytes<Pol>();
+        cudaFuncSetAttribute(score_packed<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_packed<Pol>, kScoreThreads, smem) != cudaSuccess || n < 1)
+            n = 1;
+        cached = n;
+    }
+    return cached;
+}
+
+inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan, int blocks_per_sm) {
     RG_CHECK_ARG(P >= 0 && P <= 65535, "number of pairs must be in [0, 65535]");
     RG_CHECK_ARG(pair_off != nullptr && hyp_off != nullptr, "offset arrays are null");
     RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
@@ -58,7 +73,7 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     plan.Htot = hyp_off[P];
     plan.N32tot = off32;
 
-    const long long grid = (long long)c->sm_count * 2;
+    const long long grid = (long long)c->sm_count * blocks_per_sm;
     // aim for ~8 items per resident block, never below 64 groups (512 points) per item
     long long gps_target = std::max<long long>(64, unit_total / std::max<long long>(1, grid * 8));
     long long hb_total = 0;

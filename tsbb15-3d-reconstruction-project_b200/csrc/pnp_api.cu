@@ -69,12 +69,7 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
     if (score_path == SCORE_FP32_GUARDED) {
         if (plan.n_items > 0) {
             constexpr size_t smem = score_smem_bytes<PnpPolicy>();
-            static bool attr_set = false;
-            if (!attr_set) {
-                RG_CUDA(cudaFuncSetAttribute(score_packed<PnpPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
-            }
-            const int grid = std::min(plan.n_items, c->sm_count * 2);
+            const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<PnpPolicy>());
             score_packed<PnpPolicy><<<grid, kScoreThreads, smem, st>>>((const float4*)c->X32.ptr, (const Pose32*)c->pose32.ptr,
                                                                       pi, 1, plan.n_items, counts,
                                                                       (unsigned*)c->bitmap.ptr);
@@ -110,7 +105,7 @@ static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int N, int n_sel, const doubl
     RG_CUDA(cudaSetDevice(c->device));
     const int pair_off[2] = {0, n_sel}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
+    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>());
     if (rc) return rc;
     if ((rc = pnp_workspace(c, plan))) return rc;
     c->last_stats[7] = 0;
@@ -228,7 +223,7 @@ int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, con
     RG_CHECK_ARG(poses && (N == 0 || (X && y)), "input pointers are null");
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan);
+    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>());
     if (rc) return rc;
     if ((rc = pnp_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 3 * std::max<size_t>((size_t)N, 1)))) return rc;

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
 // ------------------------------------------------------------------------------------------------
 // packed FP32 scorer policy for the reprojection criterion
 // ------------------------------------------------------------------------------------------------
-struct Pose2 { float2 p[12]; };
+struct Pose2 { float p[12]; };
 
 struct PnpPolicy {
     typedef Pose32 Rec;
@@ -361,31 +361,52 @@ struct PnpPolicy {
             const float4 a = p[0], b = p[1], c = p[2], d = p[3];
             const float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-            for (int k = 0; k < 12; ++k) out.p[k] = make_float2(f[k], f[k]);
+            for (int k = 0; k < 12; ++k) out.p[k] = f[k];
             G = d.x;
         } else {
             const float qnan = __int_as_float(0x7FFFFFFF);
 #pragma unroll
-            for (int k = 0; k < 12; ++k) out.p[k] = make_float2(qnan, qnan);
+            for (int k = 0; k < 12; ++k) out.p[k] = qnan;
             G = 0.f;
         }
     }
 
-    __device__ static __forceinline__ void eval2(const Pose2& H, const float4* __restrict__ pr, unsigned& cnt, float& minabs) {
+    template <int K>
+    __device__ static __forceinline__ void evalN(const Pose2 (&H)[K], const float4* __restrict__ pr, unsigned (&cnt)[K],
+                                                 float (&minabs)[K]) {
         const float4 A = pr[0], B = pr[1];
         const float2 Cc = *reinterpret_cast<const float2*>(pr + 2);
         const float2 X0 = make_float2(A.x, A.y), X1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y);
         const float2 y0 = make_float2(B.z, B.w), y1 = Cc;
-        const float2 w  = __ffma2_rn(H.p[8], X0, __ffma2_rn(H.p[9], X1, __ffma2_rn(H.p[10], X2, H.p[11])));
-        const float2 p0 = __ffma2_rn(H.p[0], X0, __ffma2_rn(H.p[1], X1, __ffma2_rn(H.p[2], X2, H.p[3])));
-        const float2 p1 = __ffma2_rn(H.p[4], X0, __ffma2_rn(H.p[5], X1, __ffma2_rn(H.p[6], X2, H.p[7])));
-        const float2 a = __ffma2_rn(y0, w, p0);
-        const float2 b = __ffma2_rn(y1, w, p1);
-        const float2 t2 = __ffma2_rn(b, b, __fmul2_rn(a, a));
-        const float2 q = __ffma2_rn(make_float2(-w.x, -w.y), w, t2);
-        cnt += __float_as_uint(q.x) >> 31;
-        cnt += __float_as_uint(q.y) >> 31;
-        minabs = fminf(minabs, fminf(fabsf(q.x), fabsf(q.y)));
+        float2 w[K], p0[K], p1[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k]  = ffma2_sbs(H[k].p[10], X2, H[k].p[11]);
+            p0[k] = ffma2_sbs(H[k].p[2], X2, H[k].p[3]);
+            p1[k] = ffma2_sbs(H[k].p[6], X2, H[k].p[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k]  = ffma2_sbc(H[k].p[9], X1, w[k]);
+            p0[k] = ffma2_sbc(H[k].p[1], X1, p0[k]);
+            p1[k] = ffma2_sbc(H[k].p[5], X1, p1[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k]  = ffma2_sbc(H[k].p[8], X0, w[k]);
+            p0[k] = ffma2_sbc(H[k].p[0], X0, p0[k]);
+            p1[k] = ffma2_sbc(H[k].p[4], X0, p1[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 a = __ffma2_rn(y0, w[k], p0[k]);
+            const float2 b = __ffma2_rn(y1, w[k], p1[k]);
+            const float2 t2 = __ffma2_rn(b, b, __fmul2_rn(a, a));
+            const float2 q = __ffma2_rn(make_float2(-w[k].x, -w[k].y), w[k], t2);
+            cnt[k] += __float_as_uint(q.x) >> 31;
+            cnt[k] += __float_as_uint(q.y) >> 31;
+            minabs[k] = fminf(minabs[k], fminf(fabsf(q.x), fabsf(q.y)));
+        }
     }
 };
 

@@ -5,10 +5,41 @@
 
 namespace rg {
 
-constexpr int kScoreThreads = 256;
-constexpr int kHypPerThread = 2;
+#ifndef RG_SCORE_BLOCKS
+#define RG_SCORE_BLOCKS 3
+#endif
+#ifndef RG_EPI_CHUNK
+#define RG_EPI_CHUNK 512
+#endif
+#ifndef RG_SCORE_THREADS
+#define RG_SCORE_THREADS 256
+#endif
+#ifndef RG_HPT
+#define RG_HPT 2
+#endif
+constexpr int kScoreThreads = RG_SCORE_THREADS;
+constexpr int kScoreBlocksPerSM = RG_SCORE_BLOCKS;
+constexpr int kHypPerThread = RG_HPT;
 constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
 constexpr int kStages       = 2;
+
+// packed FMA with scalar operands broadcast inside the instruction (SASS: FFMA2 Rd, Rs.F32, Rb.F32x2, ...).  Building the
+// {s, s} pair inside the asm block keeps the coefficient in ONE register: a duplicated pair would cost a second
+// register-file read per use, and the scorer is bound by register-file read ports ("scorer").
+__device__ __forceinline__ float2 ffma2_sbc(float s, float2 b, float2 c) {          // {s,s} * b + c
+    float2 d;
+    asm("{\n.reg .b64 ts, tb, tc, td;\nmov.b64 ts, {%2, %2};\nmov.b64 tb, {%3, %4};\nmov.b64 tc, {%5, %6};\n"
+        "fma.rn.f32x2 td, ts, tb, tc;\nmov.b64 {%0, %1}, td;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(s), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 ffma2_sbs(float s, float2 b, float c) {           // {s,s} * b + {c,c}
+    float2 d;
+    asm("{\n.reg .b64 ts, tb, tc, td;\nmov.b64 ts, {%2, %2};\nmov.b64 tb, {%3, %4};\nmov.b64 tc, {%5, %5};\n"
+        "fma.rn.f32x2 td, ts, tb, tc;\nmov.b64 {%0, %1}, td;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(s), "f"(b.x), "f"(b.y), "f"(c));
+    return d;
+}
 
 struct ScoreItem {
     int pair, h_base, H_end;        // hypotheses [h_base, min(h_base + kHypPerBlock, H_end)) (global indices)
@@ -46,7 +77,7 @@ __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi
 //   static constexpr int kVec4PerPair; float4 per packed point pair
 //   static constexpr int kChunkPts;    points per shared-memory stage
 //   static void load(const Rec* sh, int slot, bool valid, Regs&, float& G);
-//   static void eval2(const Regs&, const float4* pair, unsigned& cnt, float& minabs);
+//   template <int K> static void evalN(const Regs (&H)[K], const float4* pair, unsigned (&cnt)[K], float (&minabs)[K]);
 template <class Pol>
 struct __align__(128) ScoreStage {
     float4 pts[Pol::kChunkPts / 2 * Pol::kVec4PerPair];
@@ -60,7 +91,7 @@ constexpr size_t score_smem_bytes() { return kStages * sizeof(ScoreStage<Pol>) +
 // Points and (at the first chunk of an item) hypothesis records arrive by 1-D bulk TMA on one mbarrier per stage;
 // the next chunk / next item is always in flight while the current one is being scored.
 template <class Pol>
-__global__ void __launch_bounds__(kScoreThreads, 2)
+__global__ void __launch_bounds__(kScoreThreads, kScoreBlocksPerSM)
 score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restrict__ hyp32,
              const PairInfo* __restrict__ pi, int P, int n_items, int* __restrict__ counts,
              unsigned* __restrict__ bitmap) {
@@ -104,12 +135,17 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
             nxt = decode_item(pi, P, next_item);
             nxt_src = pts32 + (size_t)(pi[nxt.pair].pt_off32 / 2) * kV;
         }
-        typename Pol::Regs H0, H1;
-        float G0 = 0.f, G1 = 0.f;
-        const int h0 = cur.h_base + tid, h1 = cur.h_base + kScoreThreads + tid;
-        unsigned cnt0 = 0, cnt1 = 0;
-        unsigned* const w0 = bitmap + cur.wbase + (long long)tid * cur.W;
-        unsigned* const w1 = bitmap + cur.wbase + (long long)(kScoreThreads + tid) * cur.W;
+        typename Pol::Regs Hy[kHypPerThread];
+        float G[kHypPerThread];
+        unsigned cnt[kHypPerThread];
+        int hid[kHypPerThread];
+        unsigned* wptr[kHypPerThread];
+#pragma unroll
+        for (int k = 0; k < kHypPerThread; ++k) {
+            G[k] = 0.f; cnt[k] = 0u;
+            hid[k] = cur.h_base + k * kScoreThreads + tid;
+            wptr[k] = bitmap + cur.wbase + (long long)(k * kScoreThreads + tid) * cur.W;
+        }
 
         const int total_pts = (cur.g1 - cur.g0) * kSub;
         for (int done = 0; done < total_pts; done += kChunkPts) {
@@ -134,8 +170,9 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
             phases ^= 1u << stage;
 
             if (done == 0) {
-                Pol::load(st[stage].hyp, tid, h0 < cur.H_end, H0, G0);
-                Pol::load(st[stage].hyp, kScoreThreads + tid, h1 < cur.H_end, H1, G1);
+#pragma unroll
+                for (int k = 0; k < kHypPerThread; ++k)
+                    Pol::load(st[stage].hyp, k * kScoreThreads + tid, hid[k] < cur.H_end, Hy[k], G[k]);
             }
             const float4* sp = st[stage].pts;
             // chunk = whole bitmap words (32 flag groups of kSub points each), except the last word of an item
@@ -143,27 +180,30 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
             const int wfirst = done / (kSub * 32);
             for (int wq = 0; wq * 32 < ngr; ++wq) {
                 const int ng = min(32, ngr - wq * 32);
-                unsigned flag0 = 0u, flag1 = 0u;
+                unsigned flag[kHypPerThread];
+#pragma unroll
+                for (int k = 0; k < kHypPerThread; ++k) flag[k] = 0u;
                 const float4* wp = sp + wq * 32 * (kSub / 2) * kV;
                 for (int g = 0; g < ng; ++g) {
-                    float ma0 = INFINITY, ma1 = INFINITY;
+                    float ma[kHypPerThread];
+#pragma unroll
+                    for (int k = 0; k < kHypPerThread; ++k) ma[k] = INFINITY;
                     const float4* gp = wp + g * (kSub / 2) * kV;
 #pragma unroll
-                    for (int j = 0; j < kSub / 2; ++j) {
-                        Pol::eval2(H0, gp + j * kV, cnt0, ma0);
-                        Pol::eval2(H1, gp + j * kV, cnt1, ma1);
-                    }
-                    flag0 |= (ma0 <= G0 ? 1u : 0u) << g;
-                    flag1 |= (ma1 <= G1 ? 1u : 0u) << g;
+                    for (int j = 0; j < kSub / 2; ++j) Pol::template evalN<kHypPerThread>(Hy, gp + j * kV, cnt, ma);
+#pragma unroll
+                    for (int k = 0; k < kHypPerThread; ++k) flag[k] |= (ma[k] <= G[k] ? 1u : 0u) << g;
                 }
-                if (h0 < cur.H_end) w0[wfirst + wq] = flag0;
-                if (h1 < cur.H_end) w1[wfirst + wq] = flag1;
+#pragma unroll
+                for (int k = 0; k < kHypPerThread; ++k)
+                    if (hid[k] < cur.H_end) wptr[k][wfirst + wq] = flag[k];
             }
             __syncthreads();          // everyone is done with this stage before it is refilled
             stage ^= 1;
         }
-        if (h0 < cur.H_end && cnt0) atomicAdd(&counts[h0], (int)cnt0);
-        if (h1 < cur.H_end && cnt1) atomicAdd(&counts[h1], (int)cnt1);
+#pragma unroll
+        for (int k = 0; k < kHypPerThread; ++k)
+            if (hid[k] < cur.H_end && cnt[k]) atomicAdd(&counts[hid[k]], (int)cnt[k]);
         if (!has_next) break;
         item = next_item;
         cur = nxt;
