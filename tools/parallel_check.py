@@ -1,0 +1,45 @@
+"""Launched under torchrun (one rank per GPU): checks the pair-sharded and the hypothesis-split multi-GPU paths of
+parallel.py against a single-GPU run of the same problem (NCCL collectives, real CUDA library)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tsbb15_b200 as rg  # noqa: E402
+from tsbb15_b200 import parallel, runtime as rt, sampling, synth  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["RG_DEVICE"] = str(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pairs = synth.multi_pair(7, 3000)
+    idxs = [sampling.fast(3000, 600, 8, seed=p) for p in range(7)]
+    ref = rt.f_ransac_batched(pairs, idxs, thr=1.5, device=local)
+    shard = parallel.f_ransac_pairs_sharded(pairs, idxs, thr=1.5, device=local)
+    ok1 = (np.array_equal(shard["best_idx"], ref["best_idx"]) and np.array_equal(shard["best_count"], ref["best_count"])
+           and np.allclose(shard["F"], ref["F"], rtol=0, atol=0))
+    pts, _ = synth.two_view(20000, seed=5)
+    idx = sampling.fast(20000, 4096, 8, seed=6)
+    one = rt.f_ransac_batched([pts], [idx], thr=1.5, device=local)
+    split = parallel.f_ransac_split_hypotheses(pts, idx, thr=1.5, device=local)
+    ok2 = (split["best_idx"] == int(one["best_idx"][0]) and split["best_count"] == int(one["best_count"][0])
+           and np.array_equal(split["mask"], one["mask"][0]) and np.array_equal(split["F"], one["F"][0]))
+    res = torch.tensor([int(ok1), int(ok2)], device="cuda")
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"world": world, "pairs_sharded_ok": bool(res[0].item()), "hyp_split_ok": bool(res[1].item()),
+                          "split_owner": split["owner"], "best": split["best_idx"], "count": split["best_count"]}))
+    dist.destroy_process_group()
+    sys.exit(0 if int(res.min().item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
