@@ -100,6 +100,17 @@ int rg_pnp_ransac_host(void* ctx, void* stream, int N, int N_sel, const double* 
 int rg_pnp_ransac_dev(void* ctx, void* stream, int N, int N_sel, const double* X_dev, const double* y_dev, int H, int n,
                       const int32_t* idx_dev, double thr2, int score_path, int32_t* best_idx_dev, int32_t* best_count_dev,
                       double* Rt_dev /* 12 doubles: R row-major then t */, unsigned char* mask_dev);
+/* The same over V views in ONE call (CSR: view_off[V+1], hyp_off[V+1] host int32; idx local to the view).  n_vote
+ * (host, V ints, may be NULL = all) = number of leading correspondences of each view that vote.  Outputs per view:
+ * best_idx, best_count, Rt (V x 12: R row-major then t); mask covers all correspondences. */
+int rg_pnp_ransac_batched_host(void* ctx, void* stream, int V, const double* X, const double* y, const int32_t* view_off,
+                               const int32_t* n_vote, const int32_t* idx, const int32_t* hyp_off, int n, double thr2,
+                               int score_path, int32_t* best_idx, int32_t* best_count, double* Rt, unsigned char* mask,
+                               int32_t* counts, double* poses, unsigned char* flags);
+int rg_pnp_ransac_batched_dev(void* ctx, void* stream, int V, const double* X_dev, const double* y_dev,
+                              const int32_t* view_off_host, const int32_t* n_vote_host, const int32_t* idx_dev,
+                              const int32_t* hyp_off_host, int n, double thr2, int score_path, int32_t* best_idx_dev,
+                              int32_t* best_count_dev, double* Rt_dev, unsigned char* mask_dev);
 /* pnp.pnp_minimize(_3d_pts, img_pts, m) (pnp.py:132-152) for any m >= 6: X (m, 3), y (m, 2) -> R (3x3), t (3) */
 int rg_pnp_minimize_host(void* ctx, void* stream, int m, const double* X, const double* y, double* R, double* t);
 /* reprojection scoring of H caller-supplied poses (H x 12: R row-major then t) — ransac.py:96-105 */

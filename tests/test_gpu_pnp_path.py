@@ -111,6 +111,31 @@ def test_ransac_robust_dropin_semantics(rg):
     assert np.array_equal(a[0][0], b[0][0])
 
 
+def test_pnp_ransac_batched_views_equal_single_view_calls(rt, rg, pnp_golden):
+    """Config 2, PnP half in ONE call: all 36 Dino views (ragged N = 37..204) batched == view-by-view results."""
+    views = [rg.synth.dino_view_2d3d(i) for i in range(36)]
+    idx = [rg.sampling.fast(v[0].shape[0], 128, 6, seed=i) for i, v in enumerate(views)]
+    res = rt.pnp_ransac_batched([v[0] for v in views], [v[1] for v in views], idx, THR2, want_counts=True)
+    for i in (0, 7, 35):
+        one = rt.pnp_ransac(views[i][0], views[i][1], idx[i], THR2, want_counts=True)
+        assert np.array_equal(res["counts"][i], one["counts"]) and int(res["best_idx"][i]) == one["best_idx"]
+        assert np.array_equal(res["R"][i], one["R"]) and np.array_equal(res["mask"][i], one["mask"])
+    for i in range(36):
+        assert int(res["best_count"][i]) == views[i][0].shape[0]
+        assert opnp.rotation_angle(res["R"][i], pnp_golden["R"][i]) < 1e-6
+    assert rt.last_stats()["launches"] <= 10
+    # ragged noisy batch vs the oracle, with a view that has no hypotheses in the middle
+    scenes = [rg.synth.pnp_scene(n, seed=40 + k, sigma_px=0.05)[:2] for k, n in enumerate((500, 64, 1300))]
+    ids = [rg.sampling.fast(500, 80, 6, seed=1), np.zeros((0, 6), np.int32), rg.sampling.fast(1300, 150, 6, seed=2)]
+    rb = rt.pnp_ransac_batched([s[0] for s in scenes], [s[1] for s in scenes], ids, THR2, want_counts=True)
+    for k in (0, 2):
+        o = opnp.pnp_ransac(scenes[k][0], _hom(scenes[k][1]), ids[k], THR2)
+        good = opnp.sample_gap(scenes[k][0], _hom(scenes[k][1]), ids[k]) > GAP_MIN
+        assert np.array_equal(rb["counts"][k][good], o["counts"][good]) and int(rb["best_idx"][k]) == o["best"]
+        assert np.array_equal(rb["mask"][k], o["mask"])
+    assert int(rb["best_idx"][1]) == -1
+
+
 def test_pnp_edge_cases(rt, rg):
     X, y, _ = rg.synth.pnp_scene(200, seed=1)
     idx = rg.sampling.fast(200, 32, 6, seed=1)

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rg_fmatrix_stls_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "rg_pnp_ransac_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_pnp_ransac_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp]),
+    "rg_pnp_ransac_batched_host": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _pi, _vp, _pi, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_pnp_ransac_batched_dev": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _pi, _vp, _pi, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "rg_pnp_minimize_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rg_pnp_score_count_host": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _d, _i, _vp]),
 }

@@ -29,3 +29,12 @@ def pnp_ransac_view(X, y, n_hyp=1024, thr2=(1.5 / 3217.0) ** 2, n=6, seed=0, idx
     if idx is None:
         idx = _sampling.fast(X.shape[0], n_hyp, n, seed)
     return _rt.pnp_ransac(X, y, idx, thr2, **kw)
+
+
+def pnp_ransac_views(views, n_hyp=1024, thr2=(1.5 / 3217.0) ** 2, n=6, seed=0, idx_list=None, **kw) -> dict:
+    """DLT-PnP RANSAC of many views in one library call.  views: list of (X (N,3), y (N,2) C-normalised)."""
+    Xs = [np.asarray(v[0], dtype=np.float64) for v in views]
+    ys = [np.asarray(v[1], dtype=np.float64) for v in views]
+    if idx_list is None:
+        idx_list = [_sampling.fast(X.shape[0], n_hyp, n, seed + k) for k, X in enumerate(Xs)]
+    return _rt.pnp_ransac_batched(Xs, ys, idx_list, thr2, **kw)

@@ -142,6 +142,7 @@ struct PairInfo {
     int item_off, nsplit;      // scorer work items of this pair: [item_off, item_off + ceil(H/kHypPerBlock)*nsplit)
     int groups_per_split;      // kSub-point groups handled by one item (multiple of 32 when nsplit > 1)
     int words_per_hyp;         // guard-band bitmap: one bit per (hypothesis, group) -> ceil(n_pad / kSub / 32) words
+    int n_all, pad1;           // PnP: all correspondences of the view (n = those that vote, n <= n_all); F path: n_all == n
     long long word_off;        // offset of this pair's words in the bitmap: word(h, w) = word_off + h * words_per_hyp + w
 
     // frame of the FP32 scorer: x~ = (x - c1)/thr, y~ = (y - c2)/thr  => threshold is exactly 1, |x~|,|y~| <= B

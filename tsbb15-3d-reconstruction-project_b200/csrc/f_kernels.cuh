@@ -539,31 +539,31 @@ struct EpiFix {
         h = p.pi[lo].hyp_off + hl;
         fbase = (int)(local - (long long)hl * p.pi[lo].words_per_hyp) * 32;
     }
-    // one flagged group = kSub consecutive correspondences of one hypothesis
-    __device__ static __forceinline__ int process(const Params& p, int h, int flag, int pair, int& n_band, int& n_flip) {
+    // FP32 pass over one flagged group (kSub consecutive correspondences of one hypothesis)
+    __device__ static __forceinline__ void scan(const Params& p, int h, int flag, int pair, unsigned& band, unsigned& sign) {
         const PairInfo& info = p.pi[pair];
         const Hyp32 hy = p.hyp32[h];
         const float4* gp = p.pts32 + (size_t)info.pt_off32 + (size_t)flag * kSub;      // kSub/2 point pairs, 2 float4 each
-        int delta = 0;
+        float4 v[kSub];
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) v[j] = gp[j];
 #pragma unroll
         for (int j = 0; j < kSub / 2; ++j) {
-            const float4 X = gp[2 * j], Y = gp[2 * j + 1];
+            const float4 X = v[2 * j], Y = v[2 * j + 1];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const int i = flag * kSub + 2 * j + s;
-                if (i >= info.n) continue;
+                const int k = 2 * j + s;
                 const float q = epi_q32<MODE>(hy.f, s ? X.y : X.x, s ? X.w : X.z, s ? Y.y : Y.x, s ? Y.w : Y.z);
-                if (fabsf(q) <= hy.G) {
-                    const double4 v = p.pts64[info.pt_off + i];
-                    const int in64 = epi_inlier64(p.F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
-                    const int d = in64 - (int)(__float_as_uint(q) >> 31);
-                    delta += d;
-                    n_band += 1;
-                    n_flip += d != 0;
-                }
+                const bool valid = flag * kSub + k < info.n;
+                band |= (valid && fabsf(q) <= hy.G ? 1u : 0u) << k;
+                sign |= (__float_as_uint(q) >> 31) << k;
             }
         }
-        return delta;
+    }
+    __device__ static __forceinline__ int exact(const Params& p, int h, int i, int pair) {
+        const PairInfo& info = p.pi[pair];
+        const double4 v = p.pts64[info.pt_off + i];
+        return epi_inlier64(p.F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
     }
 };
 

@@ -33,7 +33,8 @@ inline int score_blocks_per_sm() {
     return cached;
 }
 
-inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan, int blocks_per_sm) {
+inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan, int blocks_per_sm,
+                  const int* n_vote = nullptr /* PnP: per-view number of voting correspondences (<= view size) */) {
     RG_CHECK_ARG(P >= 0 && P <= 65535, "number of pairs must be in [0, 65535]");
     RG_CHECK_ARG(pair_off != nullptr && hyp_off != nullptr, "offset arrays are null");
     RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
@@ -54,7 +55,9 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         PairInfo& o = pi[p];
         memset(&o, 0, sizeof(o));
         o.pt_off = pair_off[p];
-        o.n = pair_off[p + 1] - pair_off[p];
+        o.n_all = pair_off[p + 1] - pair_off[p];
+        o.n = n_vote ? n_vote[p] : o.n_all;
+        RG_CHECK_ARG(o.n >= 0 && o.n <= o.n_all, "voting count must be in [0, view size]");
         o.hyp_off = hyp_off[p];
         o.H = hyp_off[p + 1] - hyp_off[p];
         o.n_pad = ((o.n + kSub - 1) / kSub) * kSub;

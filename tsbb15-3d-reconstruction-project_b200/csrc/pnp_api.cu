@@ -5,18 +5,20 @@
 
 namespace rg {
 
-static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const double* y, const int* idx, int N, int H, int n,
-                            const PnpFrame* fr) {
+static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const double* y, const int* idx, const FPlan& plan,
+                            int n, const PnpFrame* fr) {
+    const int H = (int)plan.Htot;
     if (H == 0) return RG_OK;
     const int gpb = kJacobiThreads / 16;
     const int grid = ceil_div(H, gpb);
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     double* pose64 = (double*)c->pose64.ptr;
     Pose32* pose32 = (Pose32*)c->pose32.ptr;
     unsigned char* flags = (unsigned char*)c->flags.ptr;
     switch (n) {
-        case 6: pnp_solve_jacobi<6><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, N, H, fr, pose64, pose32, flags); break;
-        case 7: pnp_solve_jacobi<7><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, N, H, fr, pose64, pose32, flags); break;
-        case 8: pnp_solve_jacobi<8><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, N, H, fr, pose64, pose32, flags); break;
+        case 6: pnp_solve_jacobi<6><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+        case 7: pnp_solve_jacobi<7><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+        case 8: pnp_solve_jacobi<8><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
         default: set_error("invalid argument: PnP sample size n must be 6, 7 or 8"); return RG_ERR_ARG;
     }
     c->last_stats[7] += 1;
@@ -24,20 +26,23 @@ static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const doub
     return RG_OK;
 }
 
-// frame + packed FP32 points of the first n_sel correspondences
-static int pnp_prepare(Ctx* c, cudaStream_t st, const double* X, const double* y, int N, int n_sel, int n_pad, double thr2,
+// per-view frame + packed FP32 points of the voting correspondences
+static int pnp_prepare(Ctx* c, cudaStream_t st, const double* X, const double* y, const FPlan& plan, double thr2,
                        PnpFrame** fr_out) {
+    const int V = plan.P;
     int rc;
-    if ((rc = ensure(c->bbox, sizeof(int) * 16 + sizeof(PnpFrame)))) return rc;
-    if ((rc = ensure(c->X32, sizeof(float4) * 3 * (size_t)std::max(n_pad / 2, 1)))) return rc;
+    const size_t bbox_bytes = ((sizeof(int) * 10 * (size_t)V + 63) / 64) * 64;
+    if ((rc = ensure(c->bbox, bbox_bytes + sizeof(PnpFrame) * (size_t)V))) return rc;
+    if ((rc = ensure(c->X32, sizeof(float4) * 3 * (size_t)std::max<long long>(plan.N32tot / 2, 1)))) return rc;
     int* bbox = (int*)c->bbox.ptr;
-    PnpFrame* fr = (PnpFrame*)((char*)c->bbox.ptr + 64);
-    pnp_bbox_init<<<1, 32, 0, st>>>(bbox);
-    if (N > 0) pnp_bbox<<<std::max(1, std::min(c->sm_count * 2, ceil_div(N, 1024))), 256, 0, st>>>(X, y, N, bbox);
-    pnp_frame<<<1, 32, 0, st>>>(fr, bbox, thr2);
-    if (n_pad > 0)
-        pnp_normalise<<<std::max(1, std::min(c->sm_count * 4, ceil_div(n_pad / 2, 256))), 256, 0, st>>>(
-            X, y, n_sel, n_pad, fr, (float4*)c->X32.ptr);
+    PnpFrame* fr = (PnpFrame*)((char*)c->bbox.ptr + bbox_bytes);
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    pnp_bbox_init<<<ceil_div(V * 10, 256), 256, 0, st>>>(bbox, V);
+    const int nbx = std::max(1, std::min(c->sm_count * 2, ceil_div(plan.maxN, 1024)));
+    pnp_bbox<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, bbox);
+    pnp_frame<<<ceil_div(V, 128), 128, 0, st>>>(fr, bbox, V, thr2);
+    const int nbn = std::max(1, std::min(c->sm_count * 4, ceil_div(plan.maxN / 2 + kSub, 256)));
+    pnp_normalise<<<dim3(nbn, V), 256, 0, st>>>(X, y, pi, fr, (float4*)c->X32.ptr);
     c->last_stats[7] += 4;
     RG_CUDA(cudaGetLastError());
     *fr_out = fr;
@@ -52,40 +57,39 @@ static int pnp_workspace(Ctx* c, const FPlan& plan) {
     if ((rc = ensure(c->flags, H))) return rc;
     if ((rc = ensure(c->counts, sizeof(int) * H))) return rc;
     if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
-    if ((rc = ensure(c->best, sizeof(int2) * 4))) return rc;
+    if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
     if ((rc = ensure(c->bitmap, sizeof(unsigned) * (size_t)std::max<long long>(plan.total_words, 1)))) return rc;
     return RG_OK;
 }
 
-static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* X, const double* y, int n_sel, int H,
-                            double thr2, int score_path) {
+static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* X, const double* y, double thr2,
+                            int score_path) {
     int* counts = (int*)c->counts.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)std::max(H, 1), st));
+    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)std::max<long long>(plan.Htot, 1), st));
     RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
-    if (H == 0 || n_sel == 0) return RG_OK;
+    if (plan.Htot == 0) return RG_OK;
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     if (score_path == SCORE_FP32_GUARDED) {
         if (plan.n_items > 0) {
             constexpr size_t smem = score_smem_bytes<PnpPolicy>();
             const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<PnpPolicy>());
             score_packed<PnpPolicy><<<grid, kScoreThreads, smem, st>>>((const float4*)c->X32.ptr, (const Pose32*)c->pose32.ptr,
-                                                                      pi, 1, plan.n_items, counts,
+                                                                      pi, plan.P, plan.n_items, counts,
                                                                       (unsigned*)c->bitmap.ptr);
             prof_mark(c, st, 3);
-            const int wph = (int)(plan.total_words / std::max(H, 1));
             const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
                                                                               (plan.total_words + 255) / 256));
-            PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, n_sel, (const Pose32*)c->pose32.ptr,
-                              (const double*)c->pose64.ptr, thr2, wph};
+            PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, (const Pose32*)c->pose32.ptr, (const double*)c->pose64.ptr,
+                              pi, plan.P, thr2};
             fixup_scan<PnpFix><<<fgrid, 256, 0, st>>>(fp, plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
             c->last_stats[7] += 2;
         }
     } else {
-        const int zs = std::max(1, std::min(64, ceil_div(n_sel, 2048)));
-        pnp_score_fp64<<<dim3(ceil_div(H, 128), 1, zs), 128, 0, st>>>(X, y, n_sel, (const double*)c->pose64.ptr, H, thr2,
-                                                                     counts);
+        const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
+        pnp_score_fp64<<<dim3(std::max(1, ceil_div(plan.maxH, 128)), plan.P, zs), 128, 0, st>>>(
+            X, y, pi, (const double*)c->pose64.ptr, thr2, counts);
         prof_mark(c, st, 3);
         c->last_stats[7] += 1;
     }
@@ -93,37 +97,38 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
     return RG_OK;
 }
 
-static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int N, int n_sel, const double* X, const double* y, int H, int n,
-                          const int* idx, double thr2, int score_path, int* best_idx, int* best_count, double* Rt,
-                          unsigned char* mask) {
-    RG_CHECK_ARG(N >= 0 && H >= 0, "negative size");
-    RG_CHECK_ARG(n_sel >= 0 && n_sel <= N, "N_sel must be in [0, N]");
+// views batched in CSR form; n_vote (host, optional) = per-view number of leading correspondences that vote
+static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const double* y, const int* view_off,
+                          const int* n_vote, const int* idx, const int* hyp_off, int n, double thr2, int score_path,
+                          int* best_idx, int* best_count, double* Rt, unsigned char* mask) {
     RG_CHECK_ARG(n >= 6 && n <= 8, "PnP sample size n must be 6, 7 or 8 (DLT needs m >= 6)");
-    RG_CHECK_ARG(H == 0 || N >= n, "need at least n correspondences");
     RG_CHECK_ARG(thr2 >= 0.0 && std::isfinite(thr2), "thr2 must be finite and >= 0");
     RG_CHECK_ARG(score_path == SCORE_FP32_GUARDED || score_path == SCORE_FP64, "unknown scoring path");
     RG_CUDA(cudaSetDevice(c->device));
-    const int pair_off[2] = {0, n_sel}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>());
+    int rc = f_plan(c, st, V, view_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>(), n_vote);
     if (rc) return rc;
+    for (int v = 0; v < V; ++v)
+        RG_CHECK_ARG(hyp_off[v + 1] == hyp_off[v] || view_off[v + 1] - view_off[v] >= n, "a view with hypotheses needs at least n correspondences");
     if ((rc = pnp_workspace(c, plan))) return rc;
     c->last_stats[7] = 0;
+    if (V == 0) return RG_OK;
     // a zero threshold makes the FP32 frame singular: score such calls in FP64 only
     if (!(thr2 > 0.0)) score_path = SCORE_FP64;
     PnpFrame* fr = nullptr;
-    const int n_pad = ((n_sel + kSub - 1) / kSub) * kSub;
     prof_mark(c, st, 0);
-    if ((rc = pnp_prepare(c, st, X, y, N, n_sel, n_pad, thr2 > 0.0 ? thr2 : 1.0, &fr))) return rc;
+    if ((rc = pnp_prepare(c, st, X, y, plan, thr2 > 0.0 ? thr2 : 1.0, &fr))) return rc;
     prof_mark(c, st, 1);
-    if ((rc = pnp_solve_launch(c, st, X, y, idx, N, H, n, fr))) return rc;
+    if ((rc = pnp_solve_launch(c, st, X, y, idx, plan, n, fr))) return rc;
     prof_mark(c, st, 2);
-    if ((rc = pnp_score_launch(c, st, plan, X, y, n_sel, H, thr2, score_path))) return rc;
+    if ((rc = pnp_score_launch(c, st, plan, X, y, thr2, score_path))) return rc;
     prof_mark(c, st, 4);
     int2* best = (int2*)c->best.ptr;
-    argmax_counts<<<1, 256, 0, st>>>((const int*)c->counts.ptr, (const PairInfo*)c->pair_info.ptr, best);
-    pnp_finish<<<std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(N, 1), 256))), 256, 0, st>>>(
-        X, y, N, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx, best_count);
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts.ptr, pi, best);
+    const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
+    pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
+                                            best_count);
     c->last_stats[7] += 2;
     prof_mark(c, st, 5);
     RG_CUDA(cudaGetLastError());
@@ -163,51 +168,79 @@ using namespace rg;
 
 extern "C" {
 
+int rg_pnp_ransac_batched_dev(void* ctx, void* stream, int V, const double* X_dev, const double* y_dev,
+                              const int* view_off_host, const int* n_vote_host, const int* idx_dev, const int* hyp_off_host,
+                              int n, double thr2, int score_path, int* best_idx_dev, int* best_count_dev, double* Rt_dev,
+                              unsigned char* mask_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(V >= 0 && view_off_host && hyp_off_host, "bad view table");
+    RG_CHECK_ARG(best_idx_dev && best_count_dev && Rt_dev, "output pointers are null");
+    return pnp_ransac_dev((Ctx*)ctx, (cudaStream_t)stream, V, X_dev, y_dev, view_off_host, n_vote_host, idx_dev,
+                          hyp_off_host, n, thr2, score_path, best_idx_dev, best_count_dev, Rt_dev, mask_dev);
+}
+
 int rg_pnp_ransac_dev(void* ctx, void* stream, int N, int N_sel, const double* X_dev, const double* y_dev, int H, int n,
                       const int* idx_dev, double thr2, int score_path, int* best_idx_dev, int* best_count_dev, double* Rt_dev,
                       unsigned char* mask_dev) {
+    RG_CHECK_ARG(N >= 0 && H >= 0, "negative size");
+    const int view_off[2] = {0, N}, hyp_off[2] = {0, H}, vote[1] = {N_sel};
+    return rg_pnp_ransac_batched_dev(ctx, stream, 1, X_dev, y_dev, view_off, vote, idx_dev, hyp_off, n, thr2, score_path,
+                                     best_idx_dev, best_count_dev, Rt_dev, mask_dev);
+}
+
+int rg_pnp_ransac_batched_host(void* ctx, void* stream, int V, const double* X, const double* y, const int* view_off,
+                               const int* n_vote, const int* idx, const int* hyp_off, int n, double thr2, int score_path,
+                               int* best_idx, int* best_count, double* Rt, unsigned char* mask, int* counts, double* poses,
+                               unsigned char* flags) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
-    RG_CHECK_ARG(best_idx_dev && best_count_dev && Rt_dev, "output pointers are null");
-    return pnp_ransac_dev((Ctx*)ctx, (cudaStream_t)stream, N, N_sel, X_dev, y_dev, H, n, idx_dev, thr2, score_path,
-                          best_idx_dev, best_count_dev, Rt_dev, mask_dev);
+    RG_CHECK_ARG(V >= 0 && view_off && hyp_off && n >= 6 && n <= 8, "bad view table / sample size (n must be 6, 7 or 8)");
+    RG_CHECK_ARG(best_idx && best_count && Rt, "output pointers are null");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_CUDA(cudaSetDevice(c->device));
+    if (V == 0) return RG_OK;
+    const size_t N = (size_t)view_off[V], H = (size_t)hyp_off[V];
+    RG_CHECK_ARG((N == 0 || (X && y)) && (H == 0 || idx), "input pointers are null");
+    int rc;
+    if ((rc = ensure(c->d_in_a, sizeof(double) * 3 * std::max<size_t>(N, 1)))) return rc;
+    if ((rc = ensure(c->d_in_c, sizeof(double) * 2 * std::max<size_t>(N, 1)))) return rc;
+    if ((rc = ensure(c->d_in_b, sizeof(int) * (size_t)n * std::max<size_t>(H, 1)))) return rc;
+    if ((rc = ensure(c->d_out_a, sizeof(int) * 2 * (size_t)V))) return rc;
+    if ((rc = ensure(c->d_out_b, sizeof(double) * 12 * (size_t)V))) return rc;
+    if (mask && (rc = ensure(c->d_out_d, std::max<size_t>(N, 1)))) return rc;
+    if (N) {
+        RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, X, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+        RG_CUDA(cudaMemcpyAsync(c->d_in_c.ptr, y, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    }
+    if (H) RG_CUDA(cudaMemcpyAsync(c->d_in_b.ptr, idx, sizeof(int) * (size_t)n * H, cudaMemcpyHostToDevice, st));
+    int* d_i = (int*)c->d_out_a.ptr;
+    rc = pnp_ransac_dev(c, st, V, (const double*)c->d_in_a.ptr, (const double*)c->d_in_c.ptr, view_off, n_vote,
+                        (const int*)c->d_in_b.ptr, hyp_off, n, thr2, score_path, d_i, d_i + V, (double*)c->d_out_b.ptr,
+                        mask ? (unsigned char*)c->d_out_d.ptr : nullptr);
+    if (rc) return rc;
+    RG_CUDA(cudaMemcpyAsync(best_idx, d_i, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(best_count, d_i + V, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(Rt, c->d_out_b.ptr, sizeof(double) * 12 * (size_t)V, cudaMemcpyDeviceToHost, st));
+    if (mask && N) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_d.ptr, N, cudaMemcpyDeviceToHost, st));
+    if (counts && H) RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * H, cudaMemcpyDeviceToHost, st));
+    if (poses && H) RG_CUDA(cudaMemcpyAsync(poses, c->pose64.ptr, sizeof(double) * 12 * H, cudaMemcpyDeviceToHost, st));
+    if (flags && H) RG_CUDA(cudaMemcpyAsync(flags, c->flags.ptr, H, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    return RG_OK;
 }
 
 int rg_pnp_ransac_host(void* ctx, void* stream, int N, int N_sel, const double* X, const double* y, int H, int n,
                        const int* idx, double thr2, int score_path, int* best_idx, int* best_count, double* R, double* t,
                        unsigned char* mask, int* counts, double* poses, unsigned char* flags) {
-    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
-    RG_CHECK_ARG(N >= 0 && H >= 0 && n >= 6 && n <= 8, "bad sizes (n must be 6, 7 or 8)");
-    RG_CHECK_ARG(best_idx && best_count && R && t, "output pointers are null");
-    RG_CHECK_ARG((N == 0 || (X && y)) && (H == 0 || idx), "input pointers are null");
-    Ctx* c = (Ctx*)ctx;
-    cudaStream_t st = (cudaStream_t)stream;
-    RG_CUDA(cudaSetDevice(c->device));
-    int rc;
-    if ((rc = ensure(c->d_in_a, sizeof(double) * 3 * std::max<size_t>((size_t)N, 1)))) return rc;
-    if ((rc = ensure(c->d_in_c, sizeof(double) * 2 * std::max<size_t>((size_t)N, 1)))) return rc;
-    if ((rc = ensure(c->d_in_b, sizeof(int) * (size_t)n * std::max<size_t>((size_t)H, 1)))) return rc;
-    if ((rc = ensure(c->d_out_a, sizeof(int) * 4))) return rc;
-    if ((rc = ensure(c->d_out_b, sizeof(double) * 16))) return rc;
-    if (mask && (rc = ensure(c->d_out_d, std::max<size_t>((size_t)N, 1)))) return rc;
-    if (N) {
-        RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, X, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
-        RG_CUDA(cudaMemcpyAsync(c->d_in_c.ptr, y, sizeof(double) * 2 * (size_t)N, cudaMemcpyHostToDevice, st));
-    }
-    if (H) RG_CUDA(cudaMemcpyAsync(c->d_in_b.ptr, idx, sizeof(int) * (size_t)n * (size_t)H, cudaMemcpyHostToDevice, st));
-    int* d_i = (int*)c->d_out_a.ptr;
-    rc = pnp_ransac_dev(c, st, N, N_sel, (const double*)c->d_in_a.ptr, (const double*)c->d_in_c.ptr, H, n,
-                        (const int*)c->d_in_b.ptr, thr2, score_path, d_i, d_i + 1, (double*)c->d_out_b.ptr,
-                        mask ? (unsigned char*)c->d_out_d.ptr : nullptr);
+    RG_CHECK_ARG(N >= 0 && H >= 0, "negative size");
+    RG_CHECK_ARG(R && t, "output pointers are null");
+    const int view_off[2] = {0, N}, hyp_off[2] = {0, H}, vote[1] = {N_sel};
+    double Rt[12];
+    int rc = rg_pnp_ransac_batched_host(ctx, stream, 1, X, y, view_off, vote, idx, hyp_off, n, thr2, score_path, best_idx,
+                                        best_count, Rt, mask, counts, poses, flags);
     if (rc) return rc;
-    RG_CUDA(cudaMemcpyAsync(best_idx, d_i, sizeof(int), cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaMemcpyAsync(best_count, d_i + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaMemcpyAsync(R, c->d_out_b.ptr, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaMemcpyAsync(t, (double*)c->d_out_b.ptr + 9, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
-    if (mask && N) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_d.ptr, (size_t)N, cudaMemcpyDeviceToHost, st));
-    if (counts && H) RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
-    if (poses && H) RG_CUDA(cudaMemcpyAsync(poses, c->pose64.ptr, sizeof(double) * 12 * (size_t)H, cudaMemcpyDeviceToHost, st));
-    if (flags && H) RG_CUDA(cudaMemcpyAsync(flags, c->flags.ptr, (size_t)H, cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 9; ++k) R[k] = Rt[k];
+    for (int k = 0; k < 3; ++k) t[k] = Rt[9 + k];
     return RG_OK;
 }
 
@@ -236,13 +269,13 @@ int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, con
     c->last_stats[7] = 0;
     if (!(thr2 > 0.0)) score_path = SCORE_FP64;
     PnpFrame* fr = nullptr;
-    const int n_pad = ((N + kSub - 1) / kSub) * kSub;
     const double* dX = (const double*)c->d_in_a.ptr;
     const double* dy = (const double*)c->d_in_c.ptr;
-    if ((rc = pnp_prepare(c, st, dX, dy, N, N, n_pad, thr2 > 0.0 ? thr2 : 1.0, &fr))) return rc;
-    pnp_make_pose32<<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->pose64.ptr, H, fr, (Pose32*)c->pose32.ptr);
+    if ((rc = pnp_prepare(c, st, dX, dy, plan, thr2 > 0.0 ? thr2 : 1.0, &fr))) return rc;
+    pnp_make_pose32<<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->pose64.ptr, (const PairInfo*)c->pair_info.ptr, 1, H, fr,
+                                                      (Pose32*)c->pose32.ptr);
     c->last_stats[7] += 1;
-    if ((rc = pnp_score_launch(c, st, plan, dX, dy, N, H, thr2, score_path))) return rc;
+    if ((rc = pnp_score_launch(c, st, plan, dX, dy, thr2, score_path))) return rc;
     RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));

@@ -52,19 +52,22 @@ __device__ __forceinline__ float pnp_q32(const float* __restrict__ p, float X0, 
 // ------------------------------------------------------------------------------------------------
 // frame + packed FP32 points:  pair (a,b) = [X0a X0b X1a X1b] [X2a X2b y0a y0b] [y1a y1b 0 0]
 // ------------------------------------------------------------------------------------------------
-__global__ void pnp_bbox_init(int* __restrict__ bbox) {
-    const int i = threadIdx.x;
-    if (i < 10) bbox[i] = (i < 5) ? 0x7FFFFFFF : (int)0x80000000;
+__global__ void pnp_bbox_init(int* __restrict__ bbox, int V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V * 10) bbox[i] = ((i % 10) < 5) ? 0x7FFFFFFF : (int)0x80000000;
 }
 
-__global__ void __launch_bounds__(256) pnp_bbox(const double* __restrict__ X, const double* __restrict__ y, int N,
-                                                 int* __restrict__ bbox) {
+// bounding box of the voting correspondences of every view (grid.y = view)
+__global__ void __launch_bounds__(256) pnp_bbox(const double* __restrict__ X, const double* __restrict__ y,
+                                                 const PairInfo* __restrict__ pi, int* __restrict__ bbox) {
+    const int v = blockIdx.y;
+    const PairInfo info = pi[v];
     float mn[5], mx[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const double c[5] = {X[3 * (size_t)i], X[3 * (size_t)i + 1], X[3 * (size_t)i + 2], y[2 * (size_t)i],
-                             y[2 * (size_t)i + 1]};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < info.n; i += gridDim.x * blockDim.x) {
+        const size_t g = (size_t)info.pt_off + i;
+        const double c[5] = {X[3 * g], X[3 * g + 1], X[3 * g + 2], y[2 * g], y[2 * g + 1]};
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             if (isfinite(c[k])) {
@@ -84,17 +87,18 @@ __global__ void __launch_bounds__(256) pnp_bbox(const double* __restrict__ X, co
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            atomicMin(&bbox[k], f2key(mn[k]));
-            atomicMax(&bbox[5 + k], f2key(mx[k]));
+            atomicMin(&bbox[v * 10 + k], f2key(mn[k]));
+            atomicMax(&bbox[v * 10 + 5 + k], f2key(mx[k]));
         }
     }
 }
 
-__global__ void pnp_frame(PnpFrame* __restrict__ fr, const int* __restrict__ bbox, double thr2) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void pnp_frame(PnpFrame* __restrict__ fr, const int* __restrict__ bbox, int V, double thr2) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
     double c[5], half[5];
     for (int k = 0; k < 5; ++k) {
-        float lo = key2f(bbox[k]), hi = key2f(bbox[5 + k]);
+        float lo = key2f(bbox[v * 10 + k]), hi = key2f(bbox[v * 10 + 5 + k]);
         if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }
         c[k] = 0.5 * ((double)lo + (double)hi);
         half[k] = fmax((double)hi - c[k], c[k] - (double)lo);
@@ -106,34 +110,37 @@ __global__ void pnp_frame(PnpFrame* __restrict__ fr, const int* __restrict__ bbo
     f.sthr = sqrt(thr2);
     f.By = fmax(half[3], half[4]) / f.sthr * (1.0 + 1e-6) + 1e-30;
     f.thr2 = thr2;
-    *fr = f;
+    fr[v] = f;
 }
 
-__global__ void __launch_bounds__(256) pnp_normalise(const double* __restrict__ X, const double* __restrict__ y, int N,
-                                                      int n_pad, const PnpFrame* __restrict__ frp,
+__global__ void __launch_bounds__(256) pnp_normalise(const double* __restrict__ X, const double* __restrict__ y,
+                                                      const PairInfo* __restrict__ pi, const PnpFrame* __restrict__ frp,
                                                       float4* __restrict__ out) {
-    const PnpFrame fr = *frp;
+    const int v = blockIdx.y;
+    const PairInfo info = pi[v];
+    const PnpFrame fr = frp[v];
     const float qnan = __int_as_float(0x7FFFFFFF);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad / 2; j += gridDim.x * blockDim.x) {
-        float v[2][5];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < info.n_pad / 2; j += gridDim.x * blockDim.x) {
+        float val[2][5];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int i = 2 * j + s;
-            if (i < N) {
-                v[s][0] = (float)((X[3 * (size_t)i] - fr.cX[0]) / fr.sX);
-                v[s][1] = (float)((X[3 * (size_t)i + 1] - fr.cX[1]) / fr.sX);
-                v[s][2] = (float)((X[3 * (size_t)i + 2] - fr.cX[2]) / fr.sX);
-                v[s][3] = (float)((y[2 * (size_t)i] - fr.cy[0]) / fr.sthr);
-                v[s][4] = (float)((y[2 * (size_t)i + 1] - fr.cy[1]) / fr.sthr);
+            if (i < info.n) {
+                const size_t g = (size_t)info.pt_off + i;
+                val[s][0] = (float)((X[3 * g] - fr.cX[0]) / fr.sX);
+                val[s][1] = (float)((X[3 * g + 1] - fr.cX[1]) / fr.sX);
+                val[s][2] = (float)((X[3 * g + 2] - fr.cX[2]) / fr.sX);
+                val[s][3] = (float)((y[2 * g] - fr.cy[0]) / fr.sthr);
+                val[s][4] = (float)((y[2 * g + 1] - fr.cy[1]) / fr.sthr);
             } else {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) v[s][k] = qnan;
+                for (int k = 0; k < 5; ++k) val[s][k] = qnan;
             }
         }
-        float4* o = out + (size_t)j * 3;
-        o[0] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
-        o[1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
-        o[2] = make_float4(v[0][4], v[1][4], 0.f, 0.f);
+        float4* o = out + ((size_t)info.pt_off32 / 2 + j) * 3;
+        o[0] = make_float4(val[0][0], val[1][0], val[0][1], val[1][1]);
+        o[1] = make_float4(val[0][2], val[1][2], val[0][3], val[1][3]);
+        o[2] = make_float4(val[0][4], val[1][4], 0.f, 0.f);
     }
 }
 
@@ -184,14 +191,17 @@ __device__ __forceinline__ void make_pose32(const double* __restrict__ Rt, const
     *out = h;
 }
 
-__global__ void __launch_bounds__(256) pnp_make_pose32(const double* __restrict__ pose64, int H,
-                                                        const PnpFrame* __restrict__ fr, Pose32* __restrict__ pose32) {
+__global__ void __launch_bounds__(256) pnp_make_pose32(const double* __restrict__ pose64, const PairInfo* __restrict__ pi,
+                                                        int V, int H, const PnpFrame* __restrict__ fr,
+                                                        Pose32* __restrict__ pose32) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
+    int lo = 0, hi = V;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
     double Rt[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) Rt[k] = pose64[(size_t)h * 12 + k];
-    make_pose32(Rt, *fr, pose32 + h);
+    make_pose32(Rt, fr[lo], pose32 + h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -290,7 +300,8 @@ __device__ __forceinline__ bool enforce_pose(const double* __restrict__ c0, doub
 // ------------------------------------------------------------------------------------------------
 template <int NPTS>
 __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double* __restrict__ X, const double* __restrict__ y,
-                                                                    const int* __restrict__ idx, int N, int H,
+                                                                    const int* __restrict__ idx,
+                                                                    const PairInfo* __restrict__ pi, int V, int H,
                                                                     const PnpFrame* __restrict__ fr,
                                                                     double* __restrict__ pose64, Pose32* __restrict__ pose32,
                                                                     unsigned char* __restrict__ flags) {
@@ -301,6 +312,14 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
     const int hq = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool live = hq < H;
     const int h = live ? hq : H - 1;
+    int view = 0;
+    {
+        int lo = 0, hi = V;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        view = lo;
+    }
+    const int N = pi[view].n_all;
+    const size_t pbase = (size_t)pi[view].pt_off;
     const int ca = (j < 12) ? j / 4 : 0;       // which row of C0 this column multiplies
     const int cb = j & 3;                      // which component of the homogeneous world point
 
@@ -309,8 +328,9 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
     for (int k = 0; k < NPTS; ++k) {
         int q = idx[(size_t)h * NPTS + k];
         q = q < 0 ? 0 : (q >= N ? N - 1 : q);
-        const double Xh[4] = {X[3 * (size_t)q], X[3 * (size_t)q + 1], X[3 * (size_t)q + 2], 1.0};
-        const double y0 = y[2 * (size_t)q], y1 = y[2 * (size_t)q + 1];
+        const size_t gq = pbase + q;
+        const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
+        const double y0 = y[2 * gq], y1 = y[2 * gq + 1];
         const double xb = cb == 0 ? Xh[0] : (cb == 1 ? Xh[1] : (cb == 2 ? Xh[2] : 1.0));
         // rows of [y]_x for y = (y0, y1, 1):  r0 = (0,-1,y1)  r1 = (1,0,-y0)  r2 = (-y1,y0,0)
         const double r0 = ca == 0 ? 0.0 : (ca == 1 ? -1.0 : y1);
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
         if (!(sqrt(s1) - sqrt(s0) > 1e-9 * sqrt(smax))) fl |= 1;
         if (!ok) fl |= 2;
         flags[h] = fl;
-        make_pose32(Rt, *fr, pose32 + h);
+        make_pose32(Rt, fr[view], pose32 + h);
     }
 }
 
@@ -410,90 +430,102 @@ struct PnpPolicy {
     }
 };
 
-// FP64 re-evaluation of the flagged groups (single view; policy of fixup_scan, score_core.cuh)
+// FP64 re-evaluation of the flagged groups (policy of fixup_scan, score_core.cuh)
 struct PnpFix {
     struct Params {
-        const float4* pts32; const double* X; const double* y; int n_sel; const Pose32* pose32; const double* pose64;
-        double thr2; int words_per_hyp;
+        const float4* pts32; const double* X; const double* y; const Pose32* pose32; const double* pose64;
+        const PairInfo* pi; int V; double thr2;
     };
-    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& aux) {
-        h = (int)(wi / p.words_per_hyp);
-        fbase = (int)(wi - (long long)h * p.words_per_hyp) * 32;
-        aux = 0;
+    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& view) {
+        int lo = 0, hi = p.V;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].word_off <= wi) lo = mid; else hi = mid; }
+        const long long local = wi - p.pi[lo].word_off;
+        const int hl = (int)(local / p.pi[lo].words_per_hyp);
+        view = lo;
+        h = p.pi[lo].hyp_off + hl;
+        fbase = (int)(local - (long long)hl * p.pi[lo].words_per_hyp) * 32;
     }
-    __device__ static __forceinline__ int process(const Params& p, int h, int flag, int, int& n_band, int& n_flip) {
+    __device__ static __forceinline__ void scan(const Params& p, int h, int flag, int view, unsigned& band, unsigned& sign) {
+        const PairInfo& info = p.pi[view];
         const Pose32 ps = p.pose32[h];
-        const float4* gp = p.pts32 + (size_t)flag * (kSub / 2) * 3;
-        int delta = 0;
+        const float4* gp = p.pts32 + ((size_t)info.pt_off32 / 2 + (size_t)flag * (kSub / 2)) * 3;
+        float4 v[kSub / 2 * 3];
+#pragma unroll
+        for (int j = 0; j < kSub / 2 * 3; ++j) v[j] = gp[j];
 #pragma unroll
         for (int j = 0; j < kSub / 2; ++j) {
-            const float4 A = gp[3 * j], B = gp[3 * j + 1], Cc = gp[3 * j + 2];
+            const float4 A = v[3 * j], B = v[3 * j + 1], Cc = v[3 * j + 2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const int i = flag * kSub + 2 * j + s;
-                if (i >= p.n_sel) continue;
+                const int k = 2 * j + s;
                 const float q = pnp_q32(ps.p, s ? A.y : A.x, s ? A.w : A.z, s ? B.y : B.x, s ? B.w : B.z, s ? Cc.y : Cc.x);
-                if (fabsf(q) <= ps.G) {
-                    const int in64 = pnp_inlier64(p.pose64 + (size_t)h * 12, p.X[3 * (size_t)i], p.X[3 * (size_t)i + 1],
-                                                  p.X[3 * (size_t)i + 2], p.y[2 * (size_t)i], p.y[2 * (size_t)i + 1], p.thr2);
-                    const int d = in64 - (int)(__float_as_uint(q) >> 31);
-                    delta += d;
-                    n_band += 1;
-                    n_flip += d != 0;
-                }
+                const bool valid = flag * kSub + k < info.n;
+                band |= (valid && fabsf(q) <= ps.G ? 1u : 0u) << k;
+                sign |= (__float_as_uint(q) >> 31) << k;
             }
         }
-        return delta;
+    }
+    __device__ static __forceinline__ int exact(const Params& p, int h, int i, int view) {
+        const size_t g = (size_t)p.pi[view].pt_off + i;
+        return pnp_inlier64(p.pose64 + (size_t)h * 12, p.X[3 * g], p.X[3 * g + 1], p.X[3 * g + 2], p.y[2 * g], p.y[2 * g + 1],
+                            p.thr2);
     }
 };
 
-// Plain FP64 scorer (see f_score_fp64)
-__global__ void __launch_bounds__(128) pnp_score_fp64(const double* __restrict__ X, const double* __restrict__ y, int n_sel,
-                                                       const double* __restrict__ pose64, int H, double thr2,
-                                                       int* __restrict__ counts) {
+// Plain FP64 scorer (see f_score_fp64): grid (hypothesis blocks, views, N splits)
+__global__ void __launch_bounds__(128) pnp_score_fp64(const double* __restrict__ X, const double* __restrict__ y,
+                                                       const PairInfo* __restrict__ pi, const double* __restrict__ pose64,
+                                                       double thr2, int* __restrict__ counts) {
     __shared__ double sp[256 * 5];
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = h < H;
+    const PairInfo info = pi[blockIdx.y];
+    const int hl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= info.H) return;
+    const bool active = hl < info.H;
     double Rt[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) Rt[k] = active ? pose64[(size_t)h * 12 + k] : 0.0;
-    const int per = (n_sel + gridDim.z - 1) / gridDim.z;
-    const int n0 = min((int)blockIdx.z * per, n_sel), n1 = min(n0 + per, n_sel);
+    for (int k = 0; k < 12; ++k) Rt[k] = active ? pose64[(size_t)(info.hyp_off + hl) * 12 + k] : 0.0;
+    const int per = (info.n + gridDim.z - 1) / gridDim.z;
+    const int n0 = min((int)blockIdx.z * per, info.n), n1 = min(n0 + per, info.n);
     int cnt = 0;
     for (int base = n0; base < n1; base += 256) {
         const int m = min(256, n1 - base);
         __syncthreads();
         for (int i = threadIdx.x; i < m; i += blockDim.x) {
-            sp[5 * i + 0] = X[3 * (size_t)(base + i)];
-            sp[5 * i + 1] = X[3 * (size_t)(base + i) + 1];
-            sp[5 * i + 2] = X[3 * (size_t)(base + i) + 2];
-            sp[5 * i + 3] = y[2 * (size_t)(base + i)];
-            sp[5 * i + 4] = y[2 * (size_t)(base + i) + 1];
+            const size_t g = (size_t)info.pt_off + base + i;
+            sp[5 * i + 0] = X[3 * g];
+            sp[5 * i + 1] = X[3 * g + 1];
+            sp[5 * i + 2] = X[3 * g + 2];
+            sp[5 * i + 3] = y[2 * g];
+            sp[5 * i + 4] = y[2 * g + 1];
         }
         __syncthreads();
         if (active)
             for (int i = 0; i < m; ++i)
                 cnt += pnp_inlier64(Rt, sp[5 * i], sp[5 * i + 1], sp[5 * i + 2], sp[5 * i + 3], sp[5 * i + 4], thr2);
     }
-    if (active && cnt) atomicAdd(&counts[h], cnt);
+    if (active && cnt) atomicAdd(&counts[info.hyp_off + hl], cnt);
 }
 
-// winner's pose + consensus mask over ALL N correspondences (FP64)
-__global__ void __launch_bounds__(256) pnp_finish(const double* __restrict__ X, const double* __restrict__ y, int N,
-                                                   const double* __restrict__ pose64, const int2* __restrict__ best,
-                                                   double thr2, unsigned char* __restrict__ mask, double* __restrict__ Rt_out,
+// winner's pose + consensus mask over ALL correspondences of every view (FP64); grid (blocks, views)
+__global__ void __launch_bounds__(256) pnp_finish(const double* __restrict__ X, const double* __restrict__ y,
+                                                   const PairInfo* __restrict__ pi, const double* __restrict__ pose64,
+                                                   const int2* __restrict__ best, double thr2,
+                                                   unsigned char* __restrict__ mask, double* __restrict__ Rt_out,
                                                    int* __restrict__ best_idx, int* __restrict__ best_count) {
-    const int2 b = best[0];
-    if (blockIdx.x == 0 && threadIdx.x < 12)
-        Rt_out[threadIdx.x] = b.x >= 0 ? pose64[(size_t)b.x * 12 + threadIdx.x] : nan("");
-    if (blockIdx.x == 0 && threadIdx.x == 0) { best_idx[0] = b.x; best_count[0] = b.y; }
+    const int v = blockIdx.y;
+    const PairInfo info = pi[v];
+    const int2 b = best[v];
+    const double* src = pose64 + (size_t)(info.hyp_off + (b.x >= 0 ? b.x : 0)) * 12;
+    if (blockIdx.x == 0 && threadIdx.x < 12) Rt_out[v * 12 + threadIdx.x] = b.x >= 0 ? src[threadIdx.x] : nan("");
+    if (blockIdx.x == 0 && threadIdx.x == 0) { best_idx[v] = b.x; best_count[v] = b.y; }
     if (mask == nullptr) return;
     double Rt[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) Rt[k] = b.x >= 0 ? pose64[(size_t)b.x * 12 + k] : nan("");
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
-        mask[i] = (unsigned char)pnp_inlier64(Rt, X[3 * (size_t)i], X[3 * (size_t)i + 1], X[3 * (size_t)i + 2],
-                                              y[2 * (size_t)i], y[2 * (size_t)i + 1], thr2);
+    for (int k = 0; k < 12; ++k) Rt[k] = b.x >= 0 ? src[k] : nan("");
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < info.n_all; i += gridDim.x * blockDim.x) {
+        const size_t g = (size_t)info.pt_off + i;
+        mask[g] = (unsigned char)pnp_inlier64(Rt, X[3 * g], X[3 * g + 1], X[3 * g + 2], y[2 * g], y[2 * g + 1], thr2);
+    }
 }
 
 }  // namespace rg

@@ -211,66 +211,116 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
     }
 }
 
-// FP64 fix-up: scan the guard-band bitmap (one word per thread, coalesced), compact the set bits of a warp's 32
-// words into a per-warp shared-memory queue and let every lane re-evaluate ONE flagged group (kSub correspondences:
-// FP32 again to find the band evaluations, FP64 with the reference formula for those).  Full SIMD utilisation although
-// only ~0.4 % of the bits are set.  stats: [0] flagged groups, [1] band evaluations, [2] changed decisions.
-//   Fix::decode(params, word_index, h, flag_base, aux)      hypothesis / first flag index / pair of a bitmap word
-//   Fix::process(params, h, flag, aux, n_band, n_flip)      -> count delta of that group
+// FP64 fix-up.  Two levels of warp compaction keep all 32 lanes busy although only ~0.4 % of the bitmap bits are set
+// and only ~1 in 8 evaluations of a flagged group is inside the band:
+//   level 1  scan the bitmap (coalesced, 4 words per lane in flight), queue the set bits; one lane per flagged group
+//            re-evaluates its kSub correspondences in FP32 (bit-identical op sequence) -> band mask + FP32 decisions;
+//   level 2  queue the band evaluations; one lane per evaluation applies the reference formula in FP64 and corrects
+//            counts[h] by (exact decision - FP32 decision).
+// stats: [0] flagged groups, [1] band evaluations, [2] changed decisions.
+//   Fix::decode(params, word_index, h, flag_base, aux)            hypothesis / first flag index / pair of a bitmap word
+//   Fix::scan(params, h, flag, aux, band, sign)                   FP32 pass over one group (bit k = correspondence k)
+//   Fix::exact(params, h, i, aux)                                 FP64 decision for correspondence i of the pair/view
 template <class Fix>
 __global__ void __launch_bounds__(256) fixup_scan(typename Fix::Params prm, long long total_words,
                                                    const unsigned* __restrict__ bitmap, int* __restrict__ counts,
                                                    unsigned long long* __restrict__ stats) {
     __shared__ int4 queue[8][64];
+    __shared__ int4 queue2[8][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int4* q = queue[warp];
-    int qn = 0;
+    int4* q2 = queue2[warp];
+    int qn = 0, q2n = 0;
     unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
     const unsigned lt = (1u << lane) - 1u;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    auto drain = [&](int n) {                       // lanes < n each take one record
+    const unsigned full = 0xffffffffu;
+
+    auto drain2 = [&](int n) {                      // lanes < n: one band evaluation each, FP64
         if (lane < n) {
-            const int4 r = q[lane];
-            int nb = 0, nf = 0;
-            const int d = Fix::process(prm, r.x, r.y, r.z, nb, nf);
-            if (d) atomicAdd(&counts[r.x], d);
-            n_band += nb; n_flip += nf; n_groups += 1;
+            const int4 e = q2[lane];
+            const int d = Fix::exact(prm, e.x, e.y, e.z) - e.w;
+            if (d) { atomicAdd(&counts[e.x], d); n_flip += 1; }
+            n_band += 1;
         }
         __syncwarp();
     };
-    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += stride) {
-        const long long wi = wbase + lane;
-        unsigned word = (wi < total_words) ? bitmap[wi] : 0u;
-        int h = 0, fbase = 0, aux = 0;
-        if (word) Fix::decode(prm, wi, h, fbase, aux);
-        while (__any_sync(0xffffffffu, word != 0u)) {
-            const bool has = word != 0u;
-            const unsigned m = __ballot_sync(0xffffffffu, has);
-            if (has) {
-                const int b = __ffs(word) - 1;
-                word &= word - 1;
-                q[qn + __popc(m & lt)] = make_int4(h, fbase + b, aux, 0);
-            }
-            qn += __popc(m);
+    auto push2 = [&](bool has, int4 rec) {          // warp-collective append to the level-2 queue
+        const unsigned m = __ballot_sync(full, has);
+        if (has) q2[q2n + __popc(m & lt)] = rec;
+        q2n += __popc(m);
+        __syncwarp();
+        if (q2n >= 32) {
+            drain2(32);
+            const int rest = q2n - 32;
+            int4 mv = make_int4(0, 0, 0, 0);
+            if (lane < rest) mv = q2[32 + lane];
             __syncwarp();
-            if (qn >= 32) {
-                drain(32);
-                const int rest = qn - 32;
-                int4 mv = make_int4(0, 0, 0, 0);
-                if (lane < rest) mv = q[32 + lane];
+            if (lane < rest) q2[lane] = mv;
+            __syncwarp();
+            q2n = rest;
+        }
+    };
+    auto drain = [&](int n) {                       // lanes < n: one flagged group each, FP32 re-evaluation
+        unsigned band = 0u, sign = 0u;
+        int4 r = make_int4(0, 0, 0, 0);
+        if (lane < n) {
+            r = q[lane];
+            Fix::scan(prm, r.x, r.y, r.z, band, sign);
+            n_groups += 1;
+        }
+        __syncwarp();
+        while (__any_sync(full, band != 0u)) {
+            const bool has = band != 0u;
+            int k = 0;
+            if (has) { k = __ffs(band) - 1; band &= band - 1; }
+            push2(has, make_int4(r.x, r.y * kSub + k, r.z, (int)((sign >> k) & 1u)));
+        }
+    };
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += 4 * stride) {
+        unsigned words[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {               // four independent loads in flight per lane
+            const long long wi = wbase + u * stride + lane;
+            words[u] = (wi < total_words) ? bitmap[wi] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned word = words[u];
+            if (!__any_sync(full, word != 0u)) continue;
+            int h = 0, fbase = 0, aux = 0;
+            if (word) Fix::decode(prm, wbase + u * stride + lane, h, fbase, aux);
+            while (__any_sync(full, word != 0u)) {
+                const bool has = word != 0u;
+                const unsigned m = __ballot_sync(full, has);
+                if (has) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    q[qn + __popc(m & lt)] = make_int4(h, fbase + b, aux, 0);
+                }
+                qn += __popc(m);
                 __syncwarp();
-                if (lane < rest) q[lane] = mv;
-                __syncwarp();
-                qn = rest;
+                if (qn >= 32) {
+                    drain(32);
+                    const int rest = qn - 32;
+                    int4 mv = make_int4(0, 0, 0, 0);
+                    if (lane < rest) mv = q[32 + lane];
+                    __syncwarp();
+                    if (lane < rest) q[lane] = mv;
+                    __syncwarp();
+                    qn = rest;
+                }
             }
         }
     }
     drain(qn);
+    drain2(q2n);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        n_groups += __shfl_xor_sync(0xffffffffu, n_groups, o);
-        n_band += __shfl_xor_sync(0xffffffffu, n_band, o);
-        n_flip += __shfl_xor_sync(0xffffffffu, n_flip, o);
+        n_groups += __shfl_xor_sync(full, n_groups, o);
+        n_band += __shfl_xor_sync(full, n_band, o);
+        n_flip += __shfl_xor_sync(full, n_flip, o);
     }
     if (lane == 0) {
         if (n_groups) atomicAdd(&stats[0], n_groups);

@@ -204,6 +204,62 @@ def pnp_ransac(X, y, idx, thr2, n_sel=None, score_path=SCORE_FP32_GUARDED, want_
     return out
 
 
+def pnp_ransac_batched(X_list, y_list, idx_list, thr2, n_vote=None, score_path=SCORE_FP32_GUARDED, want_counts=False,
+                       want_poses=False, want_mask=True, want_flags=False, device=None, stream=0) -> dict:
+    """DLT-PnP RANSAC over V views in ONE library call.  X_list[v] (N_v,3), y_list[v] (N_v,2), idx_list[v] (H_v,n)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    V = len(X_list)
+    if len(y_list) != V or len(idx_list) != V:
+        raise ValueError("X_list, y_list and idx_list must have the same length")
+    Xs = [_f64(a).reshape(-1, 3) for a in X_list]
+    ys = [_f64(a).reshape(-1, 2) for a in y_list]
+    ids = [np.ascontiguousarray(a, dtype=np.int32) for a in idx_list]
+    n = ids[0].shape[1] if V and ids[0].ndim == 2 else 6
+    view_off = np.zeros(V + 1, dtype=np.int32)
+    hyp_off = np.zeros(V + 1, dtype=np.int32)
+    for v in range(V):
+        if Xs[v].shape[0] != ys[v].shape[0]:
+            raise ValueError(f"view {v}: X and y must have the same number of rows")
+        if ids[v].ndim != 2 or ids[v].shape[1] != n:
+            raise ValueError("every idx must be (H, n) with the same n")
+        if ids[v].size and (ids[v].min() < 0 or ids[v].max() >= Xs[v].shape[0]):
+            raise ValueError(f"view {v}: sample index out of range")
+        view_off[v + 1] = view_off[v] + Xs[v].shape[0]
+        hyp_off[v + 1] = hyp_off[v] + ids[v].shape[0]
+    N, H = int(view_off[-1]), int(hyp_off[-1])
+    X = np.ascontiguousarray(np.concatenate(Xs)) if V else np.zeros((0, 3))
+    y = np.ascontiguousarray(np.concatenate(ys)) if V else np.zeros((0, 2))
+    idx = np.ascontiguousarray(np.concatenate(ids)) if V else np.zeros((0, n), dtype=np.int32)
+    vote = None if n_vote is None else np.ascontiguousarray(n_vote, dtype=np.int32)
+    best_idx = np.full(V, -1, dtype=np.int32)
+    best_count = np.zeros(V, dtype=np.int32)
+    Rt = np.full((V, 12), np.nan)
+    mask = np.zeros(N, dtype=np.uint8) if want_mask else None
+    counts = np.zeros(H, dtype=np.int32) if want_counts else None
+    poses = np.zeros((H, 12)) if want_poses else None
+    flags = np.zeros(H, dtype=np.uint8) if want_flags else None
+    pi = C.POINTER(C.c_int32)
+    cabi.check(lib.rg_pnp_ransac_batched_host(
+        _vp(ctx), _vp(stream), V, _vp(cabi.ptr(X)), _vp(cabi.ptr(y)), view_off.ctypes.data_as(pi),
+        vote.ctypes.data_as(pi) if vote is not None else None, _vp(cabi.ptr(idx)), hyp_off.ctypes.data_as(pi), int(n),
+        float(thr2), int(score_path), _vp(cabi.ptr(best_idx)), _vp(cabi.ptr(best_count)), _vp(cabi.ptr(Rt)),
+        _vp(cabi.ptr(mask)), _vp(cabi.ptr(counts)), _vp(cabi.ptr(poses)), _vp(cabi.ptr(flags))))
+    out = {"best_idx": best_idx, "best_count": best_count, "R": Rt[:, :9].reshape(V, 3, 3).copy(), "t": Rt[:, 9:].copy(),
+           "view_off": view_off, "hyp_off": hyp_off}
+    split_n = lambda a: [a[view_off[v]:view_off[v + 1]] for v in range(V)]
+    split_h = lambda a: [a[hyp_off[v]:hyp_off[v + 1]] for v in range(V)]
+    if want_mask:
+        out["mask"] = split_n(mask)
+    if want_counts:
+        out["counts"] = split_h(counts)
+    if want_poses:
+        out["poses"] = split_h(poses)
+    if want_flags:
+        out["flags"] = split_h(flags)
+    return out
+
+
 def pnp_minimize(X, y, device=None, stream=0):
     lib = cabi.load_library()
     ctx = cabi.context(device)
