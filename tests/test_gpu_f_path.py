@@ -238,6 +238,21 @@ def test_guard_band_bitmap_covers_every_work_split(rt, rg):
         assert st["band_evals"] <= st["recheck_groups"] * 32 and st["flips"] <= st["band_evals"]
 
 
+def test_extreme_thresholds_and_scales_stay_exact(rt, rg):
+    """Thresholds / coordinate scales far outside the comfortable FP32 range: the guarded path must still equal FP64
+    (hypotheses whose FP32 frame would underflow are rechecked entirely in FP64)."""
+    pts, _ = rg.synth.two_view(1500, seed=77)
+    idx = rg.sampling.fast(1500, 64, 8, seed=3)
+    for scale, thr in ((1.0, 1e-7), (1.0, 1e6), (1e-6, 1.5e-6), (1e5, 1.5e5), (1.0, 1e-13)):
+        p = pts * scale
+        a = rt.f_ransac_batched([p], [idx], thr=thr, want_counts=True)
+        b = rt.f_ransac_batched([p], [idx], thr=thr, want_counts=True, score_path=rg.SCORE_FP64)
+        assert np.array_equal(a["counts"][0], b["counts"][0]), (scale, thr)
+        o = orc.score_hypotheses(orc.solve_hypotheses(p[:, :2].T.copy(), p[:, 2:].T.copy(), idx[:8]), p[:, :2].T.copy(),
+                                 p[:, 2:].T.copy(), thr)
+        assert np.array_equal(a["counts"][0][:8], o), (scale, thr)
+
+
 def test_config3_shape_fp32_equals_fp64_and_invariances(rt, rg):
     """BASELINE config 3 (N = 100 000 x H = 16 384, 30 % outliers): too big for the oracle, so size-independent
     properties: guarded-FP32 counts == FP64 counts for every hypothesis; permuting the correspondences or the

@@ -216,6 +216,9 @@ __device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const P
     else                      { Mb = fmin(S1, S2); Smax = fmax(S1, S2); }
     const double G = 1.25 * 16.0 * eps * sqrt(Mb) + 2.0 * (100.0 * eps * eps + 10.0 * eps * Smax + 2.0 * eps * Mb);
     h.G = __double2float_ru(G);
+    // the bound assumes no FP32 underflow: with an extreme threshold / point spread (s1, s2 ~ 1/B^2 near the denormal
+    // range) every evaluation of this hypothesis is sent to the FP64 recheck instead
+    if (!(Mb > 1e-28) || !(B < 1e12)) h.G = INFINITY;
     h.pad0 = 0.f; h.pad1 = 0.f;
     *out = h;
 }

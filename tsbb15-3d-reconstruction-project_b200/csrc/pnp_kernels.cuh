@@ -187,6 +187,7 @@ __device__ __forceinline__ void make_pose32(const double* __restrict__ Rt, const
     const double G = 1.25 * 14.0 * eps * rho2 * (A0 + A1) +
                      2.0 * (49.0 * eps * eps * (A0 * A0 + A1 * A1) + 16.0 * eps * rho2 * rho2 + 25.0 * eps * eps * rho2 * rho2);
     h.G = __double2float_ru(G);
+    if (!(rho2 * rho2 > 1e-28) || !(fr.By < 1e12)) h.G = INFINITY;      // FP32 underflow range: recheck everything in FP64
     h.pad0 = h.pad1 = h.pad2 = 0.f;
     *out = h;
 }
