@@ -117,6 +117,43 @@ int rg_pnp_minimize_host(void* ctx, void* stream, int m, const double* X, const 
 int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, const double* y, int H, const double* poses,
                             double thr2, int score_path, int32_t* counts);
 
+/* ---- two-view geometry either side of the RANSAC path, all FP64 -------------- */
+#define RG_TRI_OPTIMAL 0    /* lab3.triangulate_optimal (lab3.py:382-475): Hartley-Sturm, degree-6 root solve per point */
+#define RG_TRI_LINEAR 1     /* lab3.triangulate_linear (lab3.py:477-503) */
+/* Triangulation of every correspondence of P camera pairs in ONE call: replaces the per-correspondence Python loops
+ * around lab3.triangulate_optimal / triangulate_linear (fun.py:352, tables.py:170, tables.py:243, fun.py:240-255).
+ * C1, C2: (P, 3, 4) cameras; pair_off[P+1] HOST int32 CSR table; x1, x2: (pair_off[P], 2) image points (x1 seen by C1,
+ * x2 by C2); X: (pair_off[P], 3) world points.  Device x1 / x2 (and y1 / y2 below) must be 16-byte aligned. */
+int rg_triangulate_host(void* ctx, void* stream, int P, const double* C1, const double* C2, const int32_t* pair_off,
+                        const double* x1, const double* x2, int method, double* X);
+int rg_triangulate_dev(void* ctx, void* stream, int P, const double* C1_dev, const double* C2_dev,
+                       const int32_t* pair_off_host, const double* x1_dev, const double* x2_dev, int method,
+                       double* X_dev);
+/* lab3.fmatrix_from_cameras (lab3.py:331-351) for P camera pairs: F (P, 3, 3) with x1^T F x2 = 0, the reference's
+ * scale ([C1 n]_x C1 pinv(C2), |n| = 1) up to the arbitrary sign of its SVD null vector */
+int rg_fmatrix_from_cameras_host(void* ctx, void* stream, int P, const double* C1, const double* C2, double* F);
+/* fun.relative_camera_pose (fun.py:209-258, with fun.specSVD fun.py:186-207) for P pairs in one call.
+ * M: (P, 3, 3) essential matrices; if K != NULL, M holds fundamental matrices and E = K^T M K is formed on the device
+ * (fun.getEAndK, fun.py:100-101; K is (3,3) shared, or (P,3,3) when k_per_pair != 0).  y1, y2: (P, 2) one C-normalised
+ * correspondence per pair.  Rt: (P, 12) R row-major then t of the first of the four candidates whose optimally
+ * triangulated point is in front of both cameras (NaN if none: the reference returns None); which: candidate index
+ * 0..3 in the reference's order for THIS library's SVD sign convention, -1 if none; npass (optional): number of
+ * candidates that pass (1 for a well-posed pair). */
+int rg_relative_pose_host(void* ctx, void* stream, int P, const double* M, const double* K, int k_per_pair,
+                          const double* y1, const double* y2, double* Rt, int32_t* which, int32_t* npass);
+int rg_relative_pose_dev(void* ctx, void* stream, int P, const double* M_dev, const double* K_dev, int k_per_pair,
+                         const double* y1_dev, const double* y2_dev, double* Rt_dev, int32_t* which_dev,
+                         int32_t* npass_dev /* may be NULL */);
+/* fun.camera_resectioning (fun.py:260-283, fun.specRQ fun.py:174-184) for V cameras: C (V,3,4) -> K (V,3,3) upper
+ * triangular with positive diagonal and K[2][2] = 1, R (V,3,3), t (V,3); signs follow LAPACK's RQ as the reference's do */
+int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C, double* K, double* R, double* t);
+/* The 2D<->3D match loop of tables.Tables.addNewView (tables.py:116-124): for every row y[i] (N, dim) the index of the
+ * FIRST row of obs (M, dim) with ||obs[v] - y[i]||_2 < tol (strict), -1 if none.  dim = 2 or 3. */
+int rg_match_first_within_host(void* ctx, void* stream, int dim, int M, const double* obs, int N, const double* y,
+                               double tol, int32_t* idx);
+int rg_match_first_within_dev(void* ctx, void* stream, int dim, int M, const double* obs_dev, int N, const double* y_dev,
+                              double tol, int32_t* idx_dev);
+
 #ifdef __cplusplus
 }
 #endif

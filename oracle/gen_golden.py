@@ -10,6 +10,8 @@ What is recorded
   f_path_golden.npz  outputs of lab3.fmatrix_stls, lab3.fmatrix_residuals, the fun.py:303-328 loop replayed with the
                      real lab3 functions on seeded np.random.choice draws, and fun.getFFromLabCode itself (seeded)
   pnp_golden.npz     fun.camera_resectioning(newPs[i]) = ground-truth (K, R, t) of the exact synthetic Dino cameras
+  geom_golden.npz    lab3.triangulate_optimal / triangulate_linear per correspondence (clean, noisy and gross-outlier
+                     points of pair (0,1)) and fun.relative_camera_pose on all 35 consecutive clean pairs
 """
 from __future__ import annotations
 
@@ -117,6 +119,32 @@ def main() -> None:
         K_, R_, t_ = fun.camera_resectioning(Ps[i])
         Ks.append(K_); Rs.append(R_); ts.append(t_)
     np.savez_compressed(os.path.join(OUT, "pnp_golden.npz"), K=np.stack(Ks), R=np.stack(Rs), t=np.stack(ts))
+    # ---- two-view geometry around the RANSAC path ----------------------------------------------
+    gg = {}
+    rng = np.random.RandomState(11)
+    a = np.concatenate([yc1, yc1 + rng.normal(0, 0.5, yc1.shape), yc1 + rng.normal(0, 4.0, yc1.shape),
+                        rng.uniform(0, 600, yc1.shape)])
+    b = np.concatenate([yc2, yc2 + rng.normal(0, 0.5, yc2.shape), yc2 + rng.normal(0, 4.0, yc2.shape),
+                        rng.uniform(0, 600, yc2.shape)])
+    gg["tri_C1"], gg["tri_C2"], gg["tri_x1"], gg["tri_x2"] = Ps[0], Ps[1], a, b
+    gg["tri_X_optimal"] = np.stack([lab3.triangulate_optimal(Ps[0], Ps[1], p.copy(), q.copy()) for p, q in zip(a, b)])
+    gg["tri_X_linear"] = np.stack([lab3.triangulate_linear(Ps[0], Ps[1], p.copy(), q.copy()) for p, q in zip(a, b)])
+    rel = {k: [] for k in ("E", "F", "K", "y1", "y2", "R", "t")}
+    with ri.reference_cwd():
+        for i in range(35):
+            y1, y2 = c.getCorrByIndices(i, i + 1)
+            K_, _, _ = fun.camera_resectioning(Ps[i])
+            F_ = lab3.fmatrix_from_cameras(Ps[i], Ps[i + 1])
+            E_ = np.matmul(np.matmul(np.transpose(K_), F_), K_)                 # fun.py:100-101
+            h1, h2 = fun.MakeHomogenous(K_, y1), fun.MakeHomogenous(K_, y2)
+            out = fun.relative_camera_pose(E_, h1[0, :2].T, h2[0, :2].T)        # as main.py:62 calls it
+            if out is None:
+                continue
+            for k, v in zip(("E", "F", "K", "y1", "y2", "R", "t"), (E_, F_, K_, h1[0, :2], h2[0, :2], out[0], out[1])):
+                rel[k].append(np.array(v, dtype=np.float64))
+    for k, v in rel.items():
+        gg["rel_" + k] = np.stack(v)
+    np.savez_compressed(os.path.join(OUT, "geom_golden.npz"), **gg)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -55,6 +55,11 @@ def pnp_golden():
 
 
 @pytest.fixture(scope="session")
+def geom_golden():
+    return _load("geom_golden.npz")
+
+
+@pytest.fixture(scope="session")
 def noisy01(dino):
     """Noisy tracked pair (0,1) of imgdata/points.txt as (2,N),(2,N) — the BASELINE config-1 input (N = 257)."""
     tr = dino["tracks"]

@@ -102,3 +102,36 @@ def test_pnp_oracle_consensus_is_inclusive():
     assert opnp.consensus(R, t, X, y, 0.2499).tolist() == [True, False]
     with pytest.raises(ValueError):
         opnp.pnp_minimize(np.ones((5, 4)), np.ones((5, 3)))
+
+
+# ---- two-view geometry oracle (oracle/geom_path.py) against the reference's outputs -----------------------------------
+def test_geom_oracle_triangulation_matches_reference_golden(geom_golden):
+    from oracle import geom_path as og
+    g = geom_golden
+    Xo = og.triangulate_optimal_batch(g["tri_C1"], g["tri_C2"], g["tri_x1"], g["tri_x2"])
+    Xl = og.triangulate_linear_batch(g["tri_C1"], g["tri_C2"], g["tri_x1"], g["tri_x2"])
+    scale = np.abs(g["tri_X_optimal"]).max()
+    assert np.abs(Xo - g["tri_X_optimal"]).max() < 1e-10 * scale
+    assert np.abs(Xl - g["tri_X_linear"]).max() < 1e-10 * scale
+
+
+def test_geom_oracle_relative_pose_and_resectioning_match_reference_golden(geom_golden, pnp_golden, dino):
+    from oracle import geom_path as og
+    g = geom_golden
+    for k in range(len(g["rel_E"])):
+        R, t = og.relative_camera_pose(g["rel_E"][k], g["rel_y1"][k], g["rel_y2"][k])
+        assert np.abs(R - g["rel_R"][k]).max() < 1e-12 and np.abs(t - g["rel_t"][k]).max() < 1e-12
+        assert np.allclose(og.essential_from_F(g["rel_K"][k], g["rel_F"][k]), g["rel_E"][k], rtol=1e-13, atol=0)
+    assert np.abs(g["rel_R"][0] - dino["clean_data_eval"][1]).max() < 1e-6     # the reference's shipped artefact
+    for k in (0, 9, 35):
+        K, R, t = og.camera_resectioning(dino["Ps"][k])
+        assert np.allclose(K, pnp_golden["K"][k], rtol=1e-13) and np.allclose(R, pnp_golden["R"][k], atol=1e-13)
+        assert np.allclose(t, pnp_golden["t"][k], rtol=1e-12)
+
+
+def test_geom_oracle_match_loop_semantics():
+    from oracle import geom_path as og
+    obs = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 1.0], [0.0, 0.0, 1.0]])
+    y = np.array([[0.0, 5e-5, 1.0], [1.0, 1e-4, 1.0], [5.0, 5.0, 1.0]])
+    assert og.match_first_within(obs, y, 1e-4).tolist() == [0, -1, -1]       # first of duplicates; strict <
+    assert og.match_first_within(np.zeros((0, 3)), y).tolist() == [-1, -1, -1]

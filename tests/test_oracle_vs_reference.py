@@ -84,3 +84,38 @@ def test_package_ransac_helpers_match_reference(rg):
         r.gen_rnd_indices(3, 6)
     with pytest.raises(ValueError):
         ransac_ref.gen_rnd_indices(3, 6)
+
+
+def test_geom_oracle_matches_reference_functions(ref_lab3, dino):
+    """oracle/geom_path.py against the unmodified lab3 / fun functions on fresh random inputs."""
+    from oracle import geom_path as og
+    fun = ri.import_reference("fun")
+    rng = np.random.default_rng(21)
+    Ps = dino["Ps"]
+    for (i, j) in ((0, 1), (10, 14)):
+        F = ref_lab3.fmatrix_from_cameras(Ps[i], Ps[j])
+        assert np.allclose(og.fmatrix_from_cameras(Ps[i], Ps[j]), F, rtol=1e-12, atol=1e-12 * np.abs(F).max())
+        e1, e2 = ref_lab3.fmatrix_epipoles(F.copy())
+        o1, o2 = og.fmatrix_epipoles(F)
+        assert np.allclose(e1, o1) and np.allclose(e2, o2)
+        A1, A2 = ref_lab3.fmatrix_cameras(F)
+        B1, B2 = og.fmatrix_cameras(F)
+        assert np.allclose(A1, B1) and np.allclose(A2, B2)
+        X = np.array([rng.uniform(-0.04, 0.04), rng.uniform(-0.07, 0.02), rng.uniform(-0.7, -0.55)])
+        for noise in (0.0, 1.0, 30.0):
+            x1 = ref_lab3.project(X, Ps[i]) + rng.normal(0, noise, 2)
+            x2 = ref_lab3.project(X, Ps[j]) + rng.normal(0, noise, 2)
+            a = ref_lab3.triangulate_optimal(Ps[i], Ps[j], x1.copy(), x2.copy())
+            b = og.triangulate_optimal(Ps[i], Ps[j], x1, x2)
+            assert np.abs(a - b).max() < 1e-10 * np.abs(a).max()
+            a = ref_lab3.triangulate_linear(Ps[i], Ps[j], x1.copy(), x2.copy())
+            b = og.triangulate_linear(Ps[i], Ps[j], x1, x2)
+            assert np.abs(a - b).max() < 1e-10 * np.abs(a).max()
+    M = rng.normal(size=(3, 3))
+    U, S, Vt = fun.specSVD(M.copy())
+    Uo, So, Vto = og.spec_svd(M)
+    assert np.allclose(U, Uo) and np.allclose(S, So) and np.allclose(Vt, Vto)
+    for k in (0, 17):
+        K, R, t = fun.camera_resectioning(Ps[k])
+        Ko, Ro, to = og.camera_resectioning(Ps[k])
+        assert np.allclose(K, Ko) and np.allclose(R, Ro) and np.allclose(t, to)

@@ -6,7 +6,7 @@ are the multi-pair and multi-GPU entry points; ``runtime`` is the numpy-level vi
 """
 from . import _cabi, runtime, sampling  # noqa: F401
 from ._cabi import (MODE_EPI_MAX, MODE_SAMPSON, RGError, SCORE_FP32_GUARDED, SCORE_FP64, SOLVER_JACOBI, SOLVER_QR,  # noqa: F401
-                    TIE_FIRST, TIE_REFERENCE)
+                    TIE_FIRST, TIE_REFERENCE, TRI_LINEAR, TRI_OPTIMAL)
 
 __all__ = ["runtime", "sampling", "lab3", "fun", "ransac", "pnp", "batched", "parallel", "synth"]
 

@@ -18,6 +18,7 @@ MODE_EPI_MAX, MODE_SAMPSON = 0, 1
 TIE_FIRST, TIE_REFERENCE = 0, 1
 SOLVER_QR, SOLVER_JACOBI = 0, 1
 SCORE_FP32_GUARDED, SCORE_FP64 = 0, 1
+TRI_OPTIMAL, TRI_LINEAR = 0, 1
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -51,6 +52,14 @@ SIGNATURES = {
     "rg_pnp_ransac_batched_dev": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _pi, _vp, _pi, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "rg_pnp_minimize_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rg_pnp_score_count_host": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _d, _i, _vp]),
+    "rg_triangulate_host": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _vp, _vp, _i, _vp]),
+    "rg_triangulate_dev": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _vp, _vp, _i, _vp]),
+    "rg_fmatrix_from_cameras_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "rg_relative_pose_host": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rg_relative_pose_dev": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rg_camera_resectioning_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rg_match_first_within_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp]),
+    "rg_match_first_within_dev": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp]),
 }
 
 _lib = None

@@ -158,6 +158,7 @@ struct Ctx {
     Buffer d_in_a, d_in_b, d_in_c;                 // device copies of host inputs (host-buffer entry points)
     Buffer d_out_a, d_out_b, d_out_c, d_out_d;     // device outputs of host-buffer entry points
     Buffer pose64, pose32, X32;                    // PnP path
+    Buffer geom;                                   // two-view geometry: PairGeom table + CSR offsets
     // pinned host staging for the small per-call tables and the statistics read-back
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage

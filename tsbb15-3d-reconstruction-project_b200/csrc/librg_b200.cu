@@ -3,4 +3,5 @@
 #include "ctx.cu"
 #include "f_api.cu"
 #include "pnp_api.cu"
+#include "geom_api.cu"
 #include "microbench.cu"

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _cabi as cabi
 from ._cabi import (MODE_EPI_MAX, MODE_SAMPSON, SCORE_FP32_GUARDED, SCORE_FP64, SOLVER_JACOBI, SOLVER_QR, TIE_FIRST,
-                    TIE_REFERENCE)
+                    TIE_REFERENCE, TRI_LINEAR, TRI_OPTIMAL)
 
 _vp = C.c_void_p
 
@@ -283,6 +283,111 @@ def pnp_score_count(X, y, poses, thr2, score_path=SCORE_FP32_GUARDED, device=Non
                                            poses.shape[0], _vp(cabi.ptr(poses)), float(thr2), int(score_path),
                                            _vp(cabi.ptr(counts))))
     return counts
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# two-view geometry
+# ---------------------------------------------------------------------------------------------------------------
+def triangulate(C1, C2, x1_list, x2_list, method=TRI_OPTIMAL, device=None, stream=0):
+    """Triangulates every correspondence of P camera pairs in ONE library call.
+
+    C1, C2 : (P, 3, 4) (or (3, 4) for one pair);  x1_list[p], x2_list[p] : (N_p, 2) image points.
+    Returns a list of (N_p, 3) arrays (lab3.triangulate_optimal / triangulate_linear per correspondence)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    C1 = _f64(C1).reshape(-1, 3, 4)
+    C2 = _f64(C2).reshape(-1, 3, 4)
+    P = C1.shape[0]
+    if C2.shape[0] != P or len(x1_list) != P or len(x2_list) != P:
+        raise ValueError("C1, C2, x1_list and x2_list must describe the same number of camera pairs")
+    a = [_f64(x).reshape(-1, 2) for x in x1_list]
+    b = [_f64(x).reshape(-1, 2) for x in x2_list]
+    off = np.zeros(P + 1, dtype=np.int32)
+    for p in range(P):
+        if a[p].shape != b[p].shape:
+            raise ValueError(f"pair {p}: x1 and x2 must have the same shape")
+        off[p + 1] = off[p] + a[p].shape[0]
+    N = int(off[-1])
+    x1 = np.ascontiguousarray(np.concatenate(a)) if P else np.zeros((0, 2))
+    x2 = np.ascontiguousarray(np.concatenate(b)) if P else np.zeros((0, 2))
+    X = np.full((N, 3), np.nan)
+    cabi.check(lib.rg_triangulate_host(_vp(ctx), _vp(stream), P, _vp(cabi.ptr(C1)), _vp(cabi.ptr(C2)),
+                                       off.ctypes.data_as(C.POINTER(C.c_int32)), _vp(cabi.ptr(x1)), _vp(cabi.ptr(x2)),
+                                       int(method), _vp(cabi.ptr(X))))
+    return [X[off[p]:off[p + 1]] for p in range(P)]
+
+
+def fmatrix_from_cameras(C1, C2, device=None, stream=0):
+    """lab3.fmatrix_from_cameras for P camera pairs: (P, 3, 4) x 2 -> (P, 3, 3)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    C1 = _f64(C1).reshape(-1, 3, 4)
+    C2 = _f64(C2).reshape(-1, 3, 4)
+    if C1.shape != C2.shape:
+        raise ValueError("C1 and C2 must have the same shape")
+    F = np.full((C1.shape[0], 3, 3), np.nan)
+    cabi.check(lib.rg_fmatrix_from_cameras_host(_vp(ctx), _vp(stream), C1.shape[0], _vp(cabi.ptr(C1)), _vp(cabi.ptr(C2)),
+                                                _vp(cabi.ptr(F))))
+    return F
+
+
+def relative_pose(M, y1, y2, K=None, device=None, stream=0) -> dict:
+    """fun.relative_camera_pose for P pairs in one call.  M (P,3,3) essential matrices — or fundamental matrices when
+    K ((3,3) shared or (P,3,3)) is given, E = K^T M K being formed on the device; y1, y2 (P,2) C-normalised.
+    Returns dict(R (P,3,3), t (P,3), which (P,) candidate index or -1, npass (P,))."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    M = _f64(M).reshape(-1, 3, 3)
+    P = M.shape[0]
+    y1 = _f64(y1).reshape(-1, 2)
+    y2 = _f64(y2).reshape(-1, 2)
+    if y1.shape[0] != P or y2.shape[0] != P:
+        raise ValueError("one correspondence per pair expected")
+    per_pair = 0
+    if K is not None:
+        K = _f64(K)
+        if K.shape == (P, 3, 3) and P != 0 and K.ndim == 3:
+            per_pair = 1
+        elif K.shape != (3, 3):
+            raise ValueError("K must be (3, 3) or (P, 3, 3)")
+    Rt = np.full((P, 12), np.nan)
+    which = np.full(P, -1, dtype=np.int32)
+    npass = np.zeros(P, dtype=np.int32)
+    cabi.check(lib.rg_relative_pose_host(_vp(ctx), _vp(stream), P, _vp(cabi.ptr(M)), _vp(cabi.ptr(K)), per_pair,
+                                         _vp(cabi.ptr(y1)), _vp(cabi.ptr(y2)), _vp(cabi.ptr(Rt)), _vp(cabi.ptr(which)),
+                                         _vp(cabi.ptr(npass))))
+    return {"R": Rt[:, :9].reshape(P, 3, 3).copy(), "t": Rt[:, 9:].copy(), "which": which, "npass": npass}
+
+
+def camera_resectioning(Cs, device=None, stream=0):
+    """fun.camera_resectioning for V cameras: (V, 3, 4) -> K (V,3,3), R (V,3,3), t (V,3)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    Cs = _f64(Cs).reshape(-1, 3, 4)
+    V = Cs.shape[0]
+    K = np.full((V, 3, 3), np.nan)
+    R = np.full((V, 3, 3), np.nan)
+    t = np.full((V, 3), np.nan)
+    cabi.check(lib.rg_camera_resectioning_host(_vp(ctx), _vp(stream), V, _vp(cabi.ptr(Cs)), _vp(cabi.ptr(K)),
+                                               _vp(cabi.ptr(R)), _vp(cabi.ptr(t))))
+    return K, R, t
+
+
+def match_first_within(obs, y, tol=1e-4, device=None, stream=0) -> np.ndarray:
+    """For every row of y (N, d) the index of the first row of obs (M, d) closer than tol (strict), -1 if none
+    (the 2D<->3D match loop of tables.py:116-124).  d = 2 or 3."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    obs = _f64(obs)
+    y = _f64(y)
+    if y.ndim != 2 or y.shape[1] not in (2, 3):
+        raise ValueError("y must be (N, 2) or (N, 3)")
+    d = y.shape[1]
+    obs = obs.reshape(-1, d) if obs.size else np.zeros((0, d))
+    idx = np.full(y.shape[0], -1, dtype=np.int32)
+    cabi.check(lib.rg_match_first_within_host(_vp(ctx), _vp(stream), d, obs.shape[0], _vp(cabi.ptr(obs)), y.shape[0],
+                                              _vp(cabi.ptr(y)), float(tol), _vp(cabi.ptr(idx))))
+    return idx
 
 
 def microbench(device=None, stream=0) -> dict:
