@@ -27,6 +27,56 @@ def MakeHomogenous(K, coord):
     return np.linalg.solve(np.asarray(K, dtype=np.float64), hom).T
 
 
+def crossProductMat(vec3):
+    """[v]_x (fun.py:23-34)."""
+    return lab3.cross_matrix(np.asarray(vec3, dtype=np.float64))
+
+
+def getEFromCameras(C1, C2):
+    """Essential matrix of two CameraPose objects: R = R2 R1^T, t = t2 - R t1, E = R^T [t]_x (fun.py:12-21)."""
+    R = C2.R @ C1.R.T
+    t = C2.t - (C2.R @ C1.R.T @ C1.t)
+    return R.T @ crossProductMat(t)
+
+
+def camera_resectioning(C):
+    """K, R, t of a (3, 4) camera C = K [R | t] (fun.py:260-283): K upper triangular with positive diagonal and
+    K[2, 2] = 1; signs follow LAPACK's RQ as the reference's do.  GPU (one thread per camera)."""
+    C = np.asarray(C, dtype=np.float64)
+    if C.shape != (3, 4):
+        raise ValueError('C must be a (3, 4) camera matrix')
+    K, R, t = _rt.camera_resectioning(C)
+    return K[0], R[0], t[0]
+
+
+def getEAndK(C, F):
+    """E = K^T F K with K taken from the LAST camera of C (1, n, 3, 4), as the reference does (fun.py:91-102)."""
+    C = np.asarray(C, dtype=np.float64)
+    if C.ndim != 4 or C.shape[2:] != (3, 4):
+        raise ValueError('C must have shape (1, n, 3, 4)')
+    K, _, _ = _rt.camera_resectioning(C[0])
+    K = K[-1]
+    return np.matmul(np.matmul(np.transpose(K), np.asarray(F, dtype=np.float64)), K), K
+
+
+def relative_camera_pose(E, y1, y2):
+    """R, t of the second camera from an essential matrix and ONE C-normalised correspondence (fun.py:209-258): the
+    first of the four (V W U^T | +-v3), (V W^T U^T | +-v3) candidates whose optimally triangulated point lies in front
+    of both cameras.  Returns None when no candidate passes (the reference falls off the end of the function).  GPU:
+    four lanes per pair, one candidate each (``relative_camera_pose_batch`` takes P pairs at once)."""
+    res = _rt.relative_pose(np.asarray(E, dtype=np.float64).reshape(1, 3, 3), np.asarray(y1, dtype=np.float64).ravel()[:2],
+                            np.asarray(y2, dtype=np.float64).ravel()[:2])
+    if res["which"][0] < 0:
+        return None
+    return res["R"][0], res["t"][0]
+
+
+def relative_camera_pose_batch(M, y1, y2, K=None):
+    """P pairs in one call: M (P,3,3) essential matrices (or fundamental matrices with K given), y1, y2 (P, 2).
+    Returns dict(R, t, which, npass); which[p] = -1 where the reference would return None."""
+    return _rt.relative_pose(M, y1, y2, K=K)
+
+
 def f_ransac(p1, p2, r=10000, thr=1.5, sample_idx=None, seed=None, sampler="reference", tie="reference",
              mode=MODE_EPI_MAX, solver=SOLVER_QR, score_path=SCORE_FP32_GUARDED, device=None):
     """The RANSAC part of getFFromLabCode (fun.py:298-328) on the GPU.
@@ -72,7 +122,7 @@ def gold_standard(F_guess, p1, p2, inliers):
     C1, C2 = lab3.fmatrix_cameras(F_guess)
     in1 = p1[:, inliers]
     in2 = p2[:, inliers]
-    X = np.vstack([lab3.triangulate_optimal(C1, C2, a, b) for a, b in zip(in1.T, in2.T)]).T
+    X = lab3.triangulate_optimal_batch(C1, C2, in1.T, in2.T).T          # fun.py:352 loop, one GPU call
     params = np.hstack((C1.ravel(), X.T.ravel()))
     sol = least_squares(lab3.fmatrix_residuals_gs, params, xtol=2.22e-14, tr_solver='lsmr', args=(in1, in2)).x
     C1 = sol[:12].reshape(3, 4)

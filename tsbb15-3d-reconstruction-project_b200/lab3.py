@@ -4,10 +4,14 @@ On the hot path — arithmetic runs in CUDA through the C ABI, no CPU fallback:
     fmatrix_stls(pl, pr)        reference lab3.py:269-329
     fmatrix_residuals(F, x, y)  reference lab3.py:188-227
 
-Host-side helpers kept in numpy because the reference keeps them on the host too and they run once per image pair
-inside the gold-standard refinement of ``fun.getFFromLabCode`` (fun.py:342-369; SURVEY.md section 8f rows N3/N4,
-"next"): homog, project, cross_matrix, fmatrix_from_cameras, fmatrix_cameras, fmatrix_epipoles, triangulate_linear,
-triangulate_optimal, fmatrix_residuals_gs.  Same names, argument layouts, return shapes and error behaviour.
+Next to the hot path — CUDA as well, one thread per correspondence, FP64:
+    triangulate_optimal(C1, C2, x1, x2)   reference lab3.py:382-475   (+ triangulate_optimal_batch: all points, one call)
+    triangulate_linear(C1, C2, x1, x2)    reference lab3.py:477-503   (+ triangulate_linear_batch)
+    fmatrix_from_cameras(C1, C2)          reference lab3.py:331-351
+
+Host-side helpers kept in numpy because they run once per image pair inside SciPy's Levenberg-Marquardt callback of
+the gold-standard refinement (fun.py:342-369; SURVEY.md section 8f row N4, not built): homog, project, cross_matrix,
+fmatrix_cameras, fmatrix_epipoles, fmatrix_residuals_gs.  Same names, argument layouts, return shapes and errors.
 """
 from __future__ import annotations
 
@@ -82,10 +86,13 @@ def cross_matrix(v):
 
 
 def fmatrix_from_cameras(C1, C2):
-    """F of a camera pair: e = C1 n with n the centre of C2, F = [e]_x C1 C2^+ (lab3.py:331-351)."""
-    centre = np.linalg.svd(C2)[2][3]
-    e = C1 @ centre
-    return cross_matrix(e) @ (C1 @ np.linalg.pinv(C2))
+    """F of a camera pair: e = C1 n with n the centre of C2, F = [e]_x C1 C2^+ (lab3.py:331-351).  GPU; the sign of F
+    is arbitrary exactly as in the reference (it comes from the sign of an SVD null vector)."""
+    C1 = np.asarray(C1, dtype=np.float64)
+    C2 = np.asarray(C2, dtype=np.float64)
+    if C1.shape != (3, 4) or C2.shape != (3, 4):
+        raise ValueError('C1 and C2 must be (3, 4) camera matrices')
+    return _rt.fmatrix_from_cameras(C1, C2)[0]
 
 
 def fmatrix_cameras(F):
@@ -104,75 +111,40 @@ def fmatrix_epipoles(F):
     return e1[:2], e2[:2]
 
 
+def _points2(x, name):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1 or (x.ndim == 2 and x.shape[1] == 1 and x.shape[0] in (2, 3)):
+        x = x.reshape(1, -1)
+    if x.ndim != 2 or x.shape[1] not in (2, 3):
+        raise ValueError(f'{name} must hold 2-D image points ((2,), (3,) homogeneous, or (N, 2))')
+    if x.shape[1] == 3:                      # tables.py:170 passes homogeneous points; like the reference only the
+        x = x[:, :2]                         # first two components are read (lab3.py:401-403), no division
+    return np.ascontiguousarray(x)
+
+
+def triangulate_linear_batch(C1, C2, x1, x2):
+    """Linear triangulation of N correspondences in one GPU call: x1, x2 (N, 2) -> (N, 3)."""
+    return _rt.triangulate(C1, C2, [_points2(x1, 'x1')], [_points2(x2, 'x2')], method=_rt.TRI_LINEAR)[0]
+
+
+def triangulate_optimal_batch(C1, C2, x1, x2):
+    """Optimal triangulation of N correspondences in one GPU call: x1, x2 (N, 2) -> (N, 3).  Replaces the Python loops
+    around lab3.triangulate_optimal at fun.py:352 and tables.py:170, 243."""
+    return _rt.triangulate(C1, C2, [_points2(x1, 'x1')], [_points2(x2, 'x2')], method=_rt.TRI_OPTIMAL)[0]
+
+
 def triangulate_linear(C1, C2, x1, x2):
-    """Homogeneous linear triangulation (lab3.py:477-503)."""
-    x1 = np.asarray(x1, dtype=np.float64)
-    x2 = np.asarray(x2, dtype=np.float64)
-    if x1.shape[0] == 2:
-        x1, x2 = homog(x1), homog(x2)
-    M = np.vstack([cross_matrix(x1) @ C1, cross_matrix(x2) @ C2])
-    X = np.linalg.svd(M)[2][-1]
-    return X[:3] / X[-1]
+    """Homogeneous linear triangulation of one correspondence (lab3.py:477-503): (2,) + (2,) -> (3,)."""
+    return triangulate_linear_batch(C1, C2, x1, x2)[0]
 
 
 def triangulate_optimal(C1, C2, x1, x2):
-    """Hartley-Sturm triangulation as the reference performs it (lab3.py:382-475).
-
-    Both image points are moved to the origin, both epipoles are rotated onto the x axis, the stationary points of the
-    summed squared distances to a pencil of corresponding epipolar lines are the roots of a degree-6 polynomial, the
-    best of them (or the asymptote) gives the corrected points, which are triangulated linearly.  Like the reference
-    the epipole scale factors are taken as f = f' = 1 (lab3.py:421) and the real parts of ALL roots are tried."""
-    x1 = np.asarray(x1, dtype=np.float64).ravel()
-    x2 = np.asarray(x2, dtype=np.float64).ravel()
-
-    def shift(p):
-        T = np.eye(3)
-        T[0, 2], T[1, 2] = p[0], p[1]
-        return T
-
-    def epipole_rotation(e):
-        return np.array([[e[0], e[1], 0.0], [-e[1], e[0], 0.0], [0.0, 0.0, 1.0]])
-
-    T1, T2 = shift(x1), shift(x2)
-    F = T1.T @ fmatrix_from_cameras(C1, C2) @ T2
-    e1, e2 = fmatrix_epipoles(F)
-    R1 = epipole_rotation(e1 / np.linalg.norm(e1))
-    R2 = epipole_rotation(e2 / np.linalg.norm(e2))
-    F = R1 @ F @ R2.T
-    a, b, c, d = F[1, 1], F[1, 2], F[2, 1], F[2, 2]
-    f1 = f2 = 1.0
-
-    # g(t) = t ((at+b)^2 + f1^2 (ct+d)^2)^2 - (ad-bc) (1 + f2^2 t^2)^2 (at+b)(ct+d)
-    P = np.polynomial.polynomial
-    atb, ctd = np.array([b, a]), np.array([d, c])                 # ascending coefficients
-    quad = P.polyadd(P.polymul(atb, atb), f1 ** 2 * P.polymul(ctd, ctd))
-    term1 = P.polymul([0.0, 1.0], P.polymul(quad, quad))
-    one = np.array([1.0, 0.0, f2 ** 2])
-    term2 = (a * d - b * c) * P.polymul(P.polymul(one, one), P.polymul(atb, ctd))
-    g = P.polysub(term1, term2)
-    g = np.concatenate([g, np.zeros(7 - g.size)])[:7]
-    roots = np.real(np.roots(g[::-1]))                            # np.roots wants descending order
-
-    def cost(t):
-        return t ** 2 / (1 + f2 ** 2 * t ** 2) + (c * t + d) ** 2 / ((a * t + b) ** 2 + f1 ** 2 * (c * t + d) ** 2)
-
-    values = [cost(t) for t in roots]
-    values.append(1.0 / f2 ** 2 + c ** 2 / (a ** 2 + f1 ** 2 * c ** 2))       # t -> infinity
-    k = int(np.argmin(values))
-    if k < roots.size:
-        t = roots[k]
-        l1 = np.array([-f1 * (c * t + d), a * t + b, c * t + d])
-        l2 = np.array([t * f2, 1.0, -t])
-    else:
-        l1 = np.array([-f1 * c, a, c])
-        l2 = np.array([f2, 0.0, -1.0])
-
-    def foot(l):                                                  # closest point of the line to the origin
-        return np.array([-l[0] * l[2], -l[1] * l[2], l[0] ** 2 + l[1] ** 2]).reshape(3, 1)
-
-    x1n = T1 @ (R1.T @ foot(l1))
-    x2n = T2 @ (R2.T @ foot(l2))
-    return triangulate_linear(C1, C2, x1n, x2n)
+    """Hartley-Sturm triangulation of one correspondence as the reference performs it (lab3.py:382-475): both image
+    points are moved to the origin, both epipoles rotated onto the x axis, the stationary points of the summed squared
+    distances to a pencil of corresponding epipolar lines are the roots of a degree-6 polynomial, the best of them (or
+    the asymptote) gives the corrected points, which are triangulated linearly.  Like the reference the epipole scale
+    factors are f = f' = 1 (lab3.py:421) and the real parts of ALL roots are tried.  Returns (3,)."""
+    return triangulate_optimal_batch(C1, C2, x1, x2)[0]
 
 
 def fmatrix_residuals_gs(params, pl, pr):
