@@ -429,6 +429,130 @@ def run_extras(args, rg, rt, cabi, lib, ctx, stream, dev, torch, fp32_peak) -> d
             "pnp_consensus": [int(c) for c in rp["best_count"][:5]], "pnp_view_sizes": [int(v[0].shape[0]) for v in views[:5]]}
     except Exception as e:                                            # fixture missing: report, do not fail the bench
         out["config2_dino_sequence"] = {"error": repr(e)}
+
+    # ---- rows next to the hot path: triangulation, relative pose, 2D<->3D matching -----
+    try:
+        out["next_rows"] = run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch)
+    except Exception as e:
+        out["next_rows"] = {"error": repr(e)}
+    return out
+
+
+def _tri_cpu_worker(a):
+    from oracle import geom_path as og
+    C1, C2, x1, x2 = a
+    return og.triangulate_optimal_batch(C1, C2, x1, x2)
+
+
+def run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch) -> dict:
+    """Device-resident and end-to-end rates of the kernels either side of the RANSAC path, with the numpy oracle port of
+    the reference loop timed beside them (bounded sample)."""
+    vp = C.c_void_p
+    pi32 = C.POINTER(C.c_int32)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dino_data.npz"))
+    Ps = g["Ps"]
+    rng = np.random.default_rng(0)
+    out = {}
+
+    def ev_time(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # triangulation: 1M correspondences of one camera pair, 0.5 px noise (config-4 sized point set)
+    N = 1_000_000
+    Xw = np.column_stack([rng.uniform(-0.045, 0.045, N), rng.uniform(-0.08, 0.03, N), rng.uniform(-0.72, -0.54, N),
+                          np.ones(N)])
+    proj = lambda Pm: (Xw @ Pm.T)[:, :2] / (Xw @ Pm.T)[:, 2:]
+    x1 = proj(Ps[0]) + rng.normal(0, 0.5, (N, 2))
+    x2 = proj(Ps[1]) + rng.normal(0, 0.5, (N, 2))
+    d1, d2 = torch.from_numpy(x1).to(dev), torch.from_numpy(x2).to(dev)
+    dC1, dC2 = torch.from_numpy(Ps[0:1].copy()).to(dev), torch.from_numpy(Ps[1:2].copy()).to(dev)
+    dX = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    off = np.array([0, N], dtype=np.int32)
+    tri = {}
+    for method, name in ((0, "optimal"), (1, "linear")):
+        def call():
+            cabi.check(lib.rg_triangulate_dev(vp(ctx), vp(stream), 1, vp(dC1.data_ptr()), vp(dC2.data_ptr()),
+                                              off.ctypes.data_as(pi32), vp(d1.data_ptr()), vp(d2.data_ptr()), method,
+                                              vp(dX.data_ptr())))
+        ms = ev_time(call, 5)
+        t0 = time.perf_counter()
+        rt.triangulate(Ps[0], Ps[1], [x1], [x2], method=method)
+        dt = time.perf_counter() - t0
+        tri[name] = {"ms": ms, "points_per_s": N / (ms * 1e-3), "e2e_points_per_s_host_call": N / dt,
+                     "algorithmic_bytes_per_point": 56, "hbm_gbs": 56.0 * N / (ms * 1e-3) * 1e-9}
+    cores = os.cpu_count() or 1
+    per = 48
+    pool = _cpu_pool(cores)
+    jobs = [(Ps[0], Ps[1], x1[k * per:(k + 1) * per], x2[k * per:(k + 1) * per]) for k in range(cores)]
+    t0 = time.perf_counter()
+    ref = pool.map(_tri_cpu_worker, jobs) if pool is not None else [_tri_cpu_worker(jobs[0])]
+    dt = time.perf_counter() - t0
+    tri["cpu_baseline"] = {"value": per * len(jobs) / dt, "unit": "points/s", "cores": cores, "kind": "port",
+                           "sample": "%d points, numpy oracle port of lab3.triangulate_optimal, one process per core"
+                                     % (per * len(jobs))}
+    got = rt.triangulate(Ps[0], Ps[1], [x1[:per]], [x2[:per]])[0]
+    tri["max_rel_err_vs_oracle_sample"] = float(np.abs(got - ref[0]).max() / np.abs(ref[0]).max())
+    out["triangulate_1M_points"] = tri
+
+    # relative pose for 4096 pairs (config-5 pair count): E of random camera pairs + one correspondence each
+    from oracle import geom_path as og
+    Pn = 4096
+    Ks = og.camera_resectioning(Ps[0])[0]
+    ii = rng.integers(0, 35, Pn)
+    Es, y1s, y2s = np.empty((Pn, 3, 3)), np.empty((Pn, 2)), np.empty((Pn, 2))
+    Kinv = np.linalg.inv(Ks)
+    Fs = [og.fmatrix_from_cameras(Ps[i], Ps[i + 1]) for i in range(35)]
+    for k, i in enumerate(ii):
+        Es[k] = Ks.T @ Fs[i] @ Ks
+        Xp = np.array([rng.uniform(-0.04, 0.04), rng.uniform(-0.07, 0.02), rng.uniform(-0.7, -0.56), 1.0])
+        a, b = Ps[i] @ Xp, Ps[i + 1] @ Xp
+        y1s[k] = (Kinv @ (a / a[2]))[:2]
+        y2s[k] = (Kinv @ (b / b[2]))[:2]
+    dE, dy1, dy2 = (torch.from_numpy(a).to(dev) for a in (Es, y1s, y2s))
+    dRt = torch.empty((Pn, 12), dtype=torch.float64, device=dev)
+    dw = torch.empty(2 * Pn, dtype=torch.int32, device=dev)
+
+    def rcall():
+        cabi.check(lib.rg_relative_pose_dev(vp(ctx), vp(stream), Pn, vp(dE.data_ptr()), None, 0, vp(dy1.data_ptr()),
+                                            vp(dy2.data_ptr()), vp(dRt.data_ptr()), vp(dw.data_ptr()),
+                                            vp(dw[Pn:].data_ptr())))
+    ms = ev_time(rcall, 5)
+    t0 = time.perf_counter()
+    for k in range(32):
+        og.relative_camera_pose(Es[k], y1s[k], y2s[k])
+    dt = time.perf_counter() - t0
+    out["relative_pose_4096_pairs"] = {"ms": ms, "pairs_per_s": Pn / (ms * 1e-3), "resolved": int((dw[:Pn] >= 0).sum().item()),
+                                       "cpu_baseline": {"value": 32 / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                                        "sample": "32 pairs, numpy oracle port of fun.relative_camera_pose"}}
+
+    # 2D<->3D match loop of Tables.addNewView: 20 000 queries against 20 000 observations, 2/3 of them present
+    M = Nq = 20000
+    obs = np.column_stack([rng.uniform(-0.1, 0.1, (M, 2)), np.ones(M)])
+    q = np.column_stack([rng.uniform(-0.1, 0.1, (Nq, 2)), np.ones(Nq)])
+    take = rng.uniform(size=Nq) < 0.67
+    q[take] = obs[rng.integers(0, M, int(take.sum()))]
+    dobs, dq = torch.from_numpy(obs).to(dev), torch.from_numpy(q).to(dev)
+    dm = torch.empty(Nq, dtype=torch.int32, device=dev)
+
+    def mcall():
+        cabi.check(lib.rg_match_first_within_dev(vp(ctx), vp(stream), 3, M, vp(dobs.data_ptr()), Nq, vp(dq.data_ptr()),
+                                                 1e-4, vp(dm.data_ptr())))
+    ms = ev_time(mcall, 5)
+    t0 = time.perf_counter()
+    refm = og.match_first_within(obs, q[:24], 1e-4)
+    dt = time.perf_counter() - t0
+    out["match_20000_x_20000"] = {"ms": ms, "queries_per_s": Nq / (ms * 1e-3),
+                                  "matched": int((dm >= 0).sum().item()),
+                                  "bit_exact_vs_oracle_sample": bool(np.array_equal(dm[:24].cpu().numpy(), refm)),
+                                  "cpu_baseline": {"value": 24 / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                                                   "sample": "24 queries x 20000 observations, the literal loop of "
+                                                             "tables.py:116-124"}}
     return out
 
 

@@ -52,11 +52,11 @@ static int triangulate_dev(Ctx* c, cudaStream_t st, int P, const double* C1, con
     PairGeom* G = nullptr;
     int* off = nullptr;
     if ((rc = geom_stage(c, st, P, C1, C2, pair_off, &G, &off))) return rc;
-    const int grid = ceil_div(N, 128);
+    const int grid = ceil_div(N, kGeomThreads);
     if (method == TRI_OPTIMAL)
-        triangulate_kernel<TRI_OPTIMAL><<<grid, 128, 0, st>>>(G, off, P, (const double2*)x1, (const double2*)x2, N, X);
+        triangulate_kernel<TRI_OPTIMAL><<<grid, kGeomThreads, 0, st>>>(G, off, P, (const double2*)x1, (const double2*)x2, N, X);
     else
-        triangulate_kernel<TRI_LINEAR><<<grid, 128, 0, st>>>(G, off, P, (const double2*)x1, (const double2*)x2, N, X);
+        triangulate_kernel<TRI_LINEAR><<<grid, kGeomThreads, 0, st>>>(G, off, P, (const double2*)x1, (const double2*)x2, N, X);
     c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
     return RG_OK;
@@ -140,7 +140,7 @@ int rg_relative_pose_dev(void* ctx, void* stream, int P, const double* M_dev, co
     if (P == 0) return RG_OK;
     RG_CHECK_ARG(M_dev && y1_dev && y2_dev && Rt_dev && which_dev, "null buffers");
     RG_CHECK_ARG((((uintptr_t)y1_dev | (uintptr_t)y2_dev) & 15u) == 0, "y1 / y2 must be 16-byte aligned");
-    relative_pose_kernel<<<ceil_div((long long)P * 4, 128), 128, 0, st>>>(M_dev, K_dev, k_per_pair ? 9 : 0,
+    relative_pose_kernel<<<ceil_div((long long)P * 4, kGeomThreads), kGeomThreads, 0, st>>>(M_dev, K_dev, k_per_pair ? 9 : 0,
                                                                           (const double2*)y1_dev, (const double2*)y2_dev, P,
                                                                           Rt_dev, which_dev, npass_dev);
     c->last_stats[7] += 1;

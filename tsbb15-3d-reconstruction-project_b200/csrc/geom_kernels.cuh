@@ -232,8 +232,13 @@ __device__ __forceinline__ bool newton_term(const double (&a)[7], Cx z, Cx& w) {
 }
 
 // Real parts of the n = 6 - (leading zeros) roots of a (coefficients already stripped of trailing zeros by the caller,
-// |a|_max = 1).  re[k], k < n, are valid on return.  Returns n.
-__device__ __forceinline__ int sextic_roots_real_parts(const double (&a)[7], double (&re)[6]) {
+// |a|_max = 1).  The iterates live in shared memory (zs[(2 k + c) * kGeomThreads], c = 0 re / 1 im, one column per
+// thread): the root loops stay ROLLED, which keeps the kernel a few thousand instructions long — fully unrolled it was
+// 12 400 instructions (198 KB) and spent 11 of every 12 issue slots waiting for the instruction cache (ncu, round 1).
+// On return zs[2 k * kGeomThreads], k < n, hold the real parts.  Returns n.
+constexpr int kGeomThreads = 128;
+
+__device__ __forceinline__ int sextic_roots_real_parts(const double (&a)[7], double* __restrict__ zs) {
     int lead = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k)
@@ -243,77 +248,77 @@ __device__ __forceinline__ int sextic_roots_real_parts(const double (&a)[7], dou
     // ---- starting points: upper convex hull of (i, log2 |c_i|), c_i = coefficient of t^i = a[6 - i], i = 0..n ----
     double lg[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) lg[i] = (a[6 - i] != 0.0) ? log2(fabs(a[6 - i])) : -1e300;
-    Cx z[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) z[k] = {0.0, 0.0};
+    for (int i = 0; i < 7; ++i) {                          // starting radii only need ~1e-3 accuracy: float log of the mantissa
+        int e;
+        const double m = frexp(fabs(a[6 - i]), &e);
+        lg[i] = (a[6 - i] != 0.0) ? (double)e + (double)__log2f((float)m) : -1e300;
+    }
     {
         int i = 0;                                        // current hull vertex (c_0 = a[6] != 0)
+        int seg = 0;
+#pragma unroll 1
+        while (i < n) {
+            double li = 0.0;
 #pragma unroll
-        for (int seg = 0; seg < 6; ++seg) {
-            if (i < n) {
-                double li = 0.0;
+            for (int t = 0; t < 7; ++t) if (t == i) li = lg[t];
+            int jb = i + 1;
+            double sb = -INFINITY;
 #pragma unroll
-                for (int t = 0; t < 7; ++t) if (t == i) li = lg[t];
-                int jb = i + 1;
-                double sb = -INFINITY;
-#pragma unroll
-                for (int j = 1; j < 7; ++j) {
-                    if (j > i && j <= n && lg[j] > -1e299) {
-                        const double s = (lg[j] - li) / (double)(j - i);
-                        if (s >= sb) { sb = s; jb = j; }
-                    }
+            for (int j = 1; j < 7; ++j) {
+                if (j > i && j <= n && lg[j] > -1e299) {
+                    const double sl = (lg[j] - li) / (double)(j - i);
+                    if (sl >= sb) { sb = sl; jb = j; }
                 }
-                const double r = exp2(-sb);               // |roots| on this edge ~ (|c_i| / |c_j|)^(1/(j-i))
-                const int m = jb - i;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    if (k >= i && k < jb) {
-                        double sn, cs;
-                        sincospi(2.0 * (double)(k - i) / (double)m + 0.25 + 0.137 * (double)seg, &sn, &cs);
-                        z[k] = {r * cs, r * sn};
-                    }
-                }
-                i = jb;
             }
+            const double fl = floor(-sb);                 // |roots| on this edge ~ (|c_i| / |c_j|)^(1/(j-i)) = 2^-slope
+            const double r = ldexp((double)exp2f((float)(-sb - fl)), (int)fmax(fmin(fl, 1000.0), -1000.0));
+            const double im = 2.0 / (double)(jb - i);
+#pragma unroll 1
+            for (int k = i; k < jb; ++k) {
+                float sn, cs;
+                sincospif((float)((double)(k - i) * im + 0.25 + 0.137 * (double)seg), &sn, &cs);
+                zs[(2 * k) * kGeomThreads] = r * cs;
+                zs[(2 * k + 1) * kGeomThreads] = r * sn;
+            }
+            i = jb;
+            ++seg;
         }
     }
     // ---- Aberth-Ehrlich iteration (Gauss-Seidel order) ----
     unsigned done = 0u;
     const unsigned all = (1u << n) - 1u;
+#pragma unroll 1
     for (int it = 0; it < 60 && done != all; ++it) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            if (k < n && !((done >> k) & 1u)) {
-                Cx w;
-                if (newton_term(a, z[k], w)) { done |= 1u << k; continue; }
-                Cx s = {0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    if (j != k && j < n) {
-                        const Cx d = {z[k].re - z[j].re, z[k].im - z[j].im};
-                        const double dd = d.re * d.re + d.im * d.im;
-                        if (dd > 0.0) {
-                            const double id = 1.0 / dd;
-                            s.re += d.re * id; s.im -= d.im * id;
-                        }
-                    }
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            if ((done >> k) & 1u) continue;
+            const Cx z = {zs[(2 * k) * kGeomThreads], zs[(2 * k + 1) * kGeomThreads]};
+            Cx w;
+            if (newton_term(a, z, w)) { done |= 1u << k; continue; }
+            Cx sm = {0.0, 0.0};
+#pragma unroll 1
+            for (int j = 0; j < n; ++j) {
+                if (j == k) continue;
+                const double dr = z.re - zs[(2 * j) * kGeomThreads], di = z.im - zs[(2 * j + 1) * kGeomThreads];
+                const double dd = dr * dr + di * di;
+                if (dd > 0.0) {
+                    const double id = 1.0 / dd;
+                    sm.re += dr * id; sm.im -= di * id;
                 }
-                const Cx ws = cmul(w, s);
-                const Cx den = {1.0 - ws.re, -ws.im};
-                const Cx dz = cdiv(w, den);
-                if (isfinite(dz.re) && isfinite(dz.im)) {
-                    z[k].re -= dz.re; z[k].im -= dz.im;
-                    const double zz = z[k].re * z[k].re + z[k].im * z[k].im;
-                    if (dz.re * dz.re + dz.im * dz.im <= 1e-31 * zz) done |= 1u << k;
-                } else {
-                    done |= 1u << k;
-                }
+            }
+            const Cx ws = cmul(w, sm);
+            const Cx den = {1.0 - ws.re, -ws.im};
+            const Cx dz = cdiv(w, den);
+            if (isfinite(dz.re) && isfinite(dz.im)) {
+                const double zr = z.re - dz.re, zi = z.im - dz.im;
+                zs[(2 * k) * kGeomThreads] = zr;
+                zs[(2 * k + 1) * kGeomThreads] = zi;
+                if (dz.re * dz.re + dz.im * dz.im <= 1e-31 * (zr * zr + zi * zi)) done |= 1u << k;
+            } else {
+                done |= 1u << k;
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) re[k] = z[k].re;
     return n;
 }
 
@@ -334,6 +339,7 @@ __device__ __forceinline__ double hs_cost(double a, double b, double c, double d
 
 // lab3.triangulate_optimal (lab3.py:382-475) for one correspondence of a prepared camera pair.
 __device__ __forceinline__ void triangulate_optimal_pt(const PairGeom& G, double x10, double x11, double x20, double x21,
+                                                       double* __restrict__ zs /* shared: 12 x kGeomThreads doubles, + tid */,
                                                        double* __restrict__ X) {
     const double* F = G.F;
     // epipoles of T1^T F T2 are the pair's epipoles moved by -x; the reference divides by the last component and
@@ -385,14 +391,12 @@ __device__ __forceinline__ void triangulate_optimal_pt(const PairGeom& G, double
                 zero_root = true;
             }
         }
-        double re[6];
-        const int n = sextic_roots_real_parts(g, re);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            if (k < n) {
-                const double s = hs_cost(a, b, c, d, re[k]);
-                if (s < best) { best = s; tb = re[k]; at_inf = false; }
-            }
+        const int n = sextic_roots_real_parts(g, zs);
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            const double tk = zs[(2 * k) * kGeomThreads];
+            const double s = hs_cost(a, b, c, d, tk);
+            if (s < best) { best = s; tb = tk; at_inf = false; }
         }
         if (zero_root) {
             const double s = hs_cost(a, b, c, d, 0.0);
@@ -447,10 +451,11 @@ __global__ void __launch_bounds__(256) geom_export_F(const PairGeom* __restrict_
 
 // one correspondence per thread; pair_off (device, P+1) is the CSR table of the camera pairs
 template <int METHOD>
-__global__ void __launch_bounds__(128) triangulate_kernel(const PairGeom* __restrict__ G, const int* __restrict__ pair_off,
+__global__ void __launch_bounds__(kGeomThreads) triangulate_kernel(const PairGeom* __restrict__ G, const int* __restrict__ pair_off,
                                                           int P, const double2* __restrict__ x1,
                                                           const double2* __restrict__ x2, int N, double* __restrict__ X) {
     __shared__ PairGeom sG;
+    __shared__ double zsh[METHOD == TRI_OPTIMAL ? 12 * kGeomThreads : 1];
     // most launches have one pair per block; the block's first pair is staged in shared memory, others read global
     const int i0 = blockIdx.x * blockDim.x;
     const int pb = find_segment(pair_off, P, min(i0, N - 1));
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const PairGeom* __rest
     const double2 a = x1[i], b = x2[i];
     double out[3];
     if (METHOD == TRI_OPTIMAL) {
-        triangulate_optimal_pt(g, a.x, a.y, b.x, b.y, out);
+        triangulate_optimal_pt(g, a.x, a.y, b.x, b.y, zsh + threadIdx.x, out);
     } else {
         const double h1[3] = {a.x, a.y, 1.0}, h2[3] = {b.x, b.y, 1.0};
         triangulate_linear_h(g.C1, g.C2, h1, h2, out);
@@ -479,11 +484,12 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const PairGeom* __rest
 // pair.  Rt (P x 12: R row-major then t) of the first candidate in the reference's order (V W U^T, v3), (V W^T U^T, v3),
 // (V W U^T, -v3), (V W^T U^T, -v3) whose optimally triangulated point is in front of both cameras; which[p] = index of
 // that candidate, -1 if none (the reference returns None); npass[p] = how many candidates pass.
-__global__ void __launch_bounds__(128) relative_pose_kernel(const double* __restrict__ M, const double* __restrict__ K9,
+__global__ void __launch_bounds__(kGeomThreads) relative_pose_kernel(const double* __restrict__ M, const double* __restrict__ K9,
                                                             int k_stride, const double2* __restrict__ y1,
                                                             const double2* __restrict__ y2, int P,
                                                             double* __restrict__ Rt, int* __restrict__ which,
                                                             int* __restrict__ npass) {
+    __shared__ double zsh[12 * kGeomThreads];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int pq = tid >> 2;
     const int cand = tid & 3;
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(128) relative_pose_kernel(const double* __rest
     f_from_cameras(G.C1, G.C2, G.F, G.e1, G.e2);
     const double2 a = y1[p], b = y2[p];
     double X[3];
-    triangulate_optimal_pt(G, a.x, a.y, b.x, b.y, X);
+    triangulate_optimal_pt(G, a.x, a.y, b.x, b.y, zsh + threadIdx.x, X);
     const double z2 = G.C2[8] * X[0] + G.C2[9] * X[1] + G.C2[10] * X[2] + G.C2[11];
     const bool pass = (X[2] > 0.0) && (z2 > 0.0);
     const unsigned lane = threadIdx.x & 31u;
