@@ -571,10 +571,15 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        if _POOL is not None:                       # CPU-baseline workers: shut down before interpreter teardown
+            _POOL.close()
+            _POOL.join()
 
 
 if __name__ == "__main__":

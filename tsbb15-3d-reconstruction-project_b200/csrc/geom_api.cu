@@ -2,6 +2,7 @@
 // 2D<->3D observation matching): SURVEY.md section 8f rows N1-N3.
 #include "geom_kernels.cuh"
 #include "plan.cuh"
+#include <cmath>
 
 namespace rg {
 
@@ -208,21 +209,39 @@ int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C,
     return RG_OK;
 }
 
+// smallest double whose correctly rounded square root is >= tol: sqrt(s) < tol  <=>  s < sqrt_threshold(tol)
+static double sqrt_threshold(double tol) {
+    double t = tol * tol;
+    while (t > 0.0 && std::sqrt(t) >= tol) t = std::nextafter(t, 0.0);
+    while (std::sqrt(t) < tol) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
 int rg_match_first_within_dev(void* ctx, void* stream, int dim, int M, const double* obs_dev, int N, const double* y_dev,
                               double tol, int32_t* idx_dev) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     RG_CHECK_ARG(dim == 2 || dim == 3, "dim must be 2 or 3");
     RG_CHECK_ARG(M >= 0 && N >= 0, "negative size");
+    RG_CHECK_ARG(tol == tol, "tol is NaN");
     Ctx* c = (Ctx*)ctx;
     cudaStream_t st = (cudaStream_t)stream;
     RG_CUDA(cudaSetDevice(c->device));
     c->last_stats[7] = 0;
     if (N == 0) return RG_OK;
     RG_CHECK_ARG(idx_dev && y_dev && (M == 0 || obs_dev), "null buffers");
+    RG_CUDA(cudaMemsetAsync(idx_dev, 0xFF, sizeof(int32_t) * (size_t)N, st));           // -1 everywhere
+    if (M == 0 || !(tol > 0.0)) return RG_OK;                                            // norm < tol <= 0 never holds
+    const double t2 = std::isinf(tol) ? INFINITY : sqrt_threshold(tol);
+    // enough (query block x observation segment) blocks to fill the GPU a few times over; segments are whole tiles
+    const int qblocks = ceil_div(N, 128);
+    int nseg = std::max(1, std::min(ceil_div(M, 256), ceil_div((long long)c->sm_count * 16, qblocks)));
+    int seg_len = ceil_div(ceil_div(M, nseg), 256) * 256;
+    nseg = ceil_div(M, seg_len);
+    RG_CHECK_ARG(nseg <= 65535, "too many observation segments");
     if (dim == 3)
-        match_first_kernel<3><<<ceil_div(N, 128), 128, 0, st>>>(obs_dev, M, y_dev, N, tol, idx_dev);
+        match_first_kernel<3><<<dim3(qblocks, nseg), 128, 0, st>>>(obs_dev, M, seg_len, y_dev, N, t2, (unsigned*)idx_dev);
     else
-        match_first_kernel<2><<<ceil_div(N, 128), 128, 0, st>>>(obs_dev, M, y_dev, N, tol, idx_dev);
+        match_first_kernel<2><<<dim3(qblocks, nseg), 128, 0, st>>>(obs_dev, M, seg_len, y_dev, N, t2, (unsigned*)idx_dev);
     c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
     return RG_OK;

@@ -671,26 +671,33 @@ __global__ void __launch_bounds__(64) camera_resection_kernel(const double* __re
 
 // ------------------------------------------------------------------------------------------------
 // tables.py:116-124: for every query row the FIRST observation row within tol (strict <, Euclidean norm); -1 if none.
-// Block = 128 queries, observations streamed through shared memory in tiles; a query stops at its first hit (tiles are
-// visited in ascending order, so the first hit is the lowest index).  norm = sqrt(((dx*dx) + dy*dy) + dz*dz) as
-// np.linalg.norm evaluates it for a short vector (no fused multiply-add).
-// ------------------------------------------------------------------------------------------------
+// grid = (queries / 128, observation segments): each thread scans one segment of the observations (streamed through
+// shared memory in tiles) for its query in ascending order and stops at its first hit; the lowest hit over the
+// segments wins through an unsigned atomicMin (0xFFFFFFFF = -1 = "none").  Segments that start after an already
+// recorded hit are skipped.  Arithmetic as np.linalg.norm evaluates a short vector: s = ((dx*dx) + dy*dy) + dz*dz with
+// separate roundings, sqrt(s) < tol — the square root is folded into the threshold: t2 is the smallest double whose
+// correctly rounded square root is >= tol (computed on the host), so s < t2 is the SAME predicate, bit for bit.
 template <int DIM>
-__global__ void __launch_bounds__(128) match_first_kernel(const double* __restrict__ obs, int M, const double* __restrict__ y,
-                                                          int N, double tol, int* __restrict__ out) {
-    constexpr int kTile = 512;
+__global__ void __launch_bounds__(128) match_first_kernel(const double* __restrict__ obs, int M, int seg_len,
+                                                          const double* __restrict__ y, int N, double t2,
+                                                          unsigned* __restrict__ out) {
+    constexpr int kTile = 256;
     __shared__ double tile[kTile * DIM];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = blockIdx.y * seg_len;
+    const int m1 = min(M, m0 + seg_len);
     double q[DIM];
 #pragma unroll
     for (int k = 0; k < DIM; ++k) q[k] = (i < N) ? y[(size_t)i * DIM + k] : 0.0;
-    int hit = -1;
-    for (int base = 0; base < M; base += kTile) {
-        const int cnt = min(kTile, M - base);
-        __syncthreads();
+    bool active = i < N;
+    if (active && blockIdx.y > 0) active = out[i] >= (unsigned)m0;       // an earlier segment already has a hit
+    unsigned hit = 0xFFFFFFFFu;
+    for (int base = m0; base < m1; base += kTile) {
+        if (__syncthreads_and(!active)) break;
+        const int cnt = min(kTile, m1 - base);
         for (int k = threadIdx.x; k < cnt * DIM; k += blockDim.x) tile[k] = obs[(size_t)base * DIM + k];
         __syncthreads();
-        if (i < N && hit < 0) {
+        if (active) {
             for (int v = 0; v < cnt; ++v) {
                 double s = 0.0;
 #pragma unroll
@@ -698,12 +705,11 @@ __global__ void __launch_bounds__(128) match_first_kernel(const double* __restri
                     const double dlt = __dsub_rn(tile[v * DIM + k], q[k]);
                     s = __dadd_rn(s, __dmul_rn(dlt, dlt));
                 }
-                if (__dsqrt_rn(s) < tol) { hit = base + v; break; }
+                if (s < t2) { hit = (unsigned)(base + v); active = false; break; }
             }
         }
-        if (__syncthreads_and(i >= N || hit >= 0)) break;
     }
-    if (i < N) out[i] = hit;
+    if (hit != 0xFFFFFFFFu) atomicMin(&out[i], hit);
 }
 
 }  // namespace rg
