@@ -1,0 +1,158 @@
+// Experiment: throughput of the epipolar evaluation body (2 hypotheses per thread, points broadcast from shared memory)
+// for different packings of the 17 FP32 lane-ops: which FFMA2 forms are limited by register-file reads on sm_100a?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I tsbb15-3d-reconstruction-project_b200/csrc \
+//        -o tools/exp/eval_variants tools/exp/eval_variants.cu
+#include "score_core.cuh"
+#include <cstdio>
+using namespace rg;
+
+struct H2 { float f[9]; };
+
+// VARIANT bit 0: r ops scalar; bit 1: second-step accumulates scalar; bit 2: first-step (s, pt, s) scalar;
+//         bit 3: squares/norms scalar; bit 4: final q scalar
+template <int VARIANT, int K>
+__device__ __forceinline__ void eval_var(const H2 (&H)[K], const float4* __restrict__ pr, unsigned (&cnt)[K], float (&minabs)[K]) {
+    const float4 X = pr[0], Y = pr[1];
+    const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
+    const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
+    float2 l1x[K], l1y[K], l1z[K], l2x[K], l2y[K], r[K], s1[K], s2[K];
+    auto sbs = [](float s, float2 b, float c) -> float2 {
+        if (VARIANT & 4) return make_float2(__fmaf_rn(s, b.x, c), __fmaf_rn(s, b.y, c));
+        return ffma2_sbs(s, b, c);
+    };
+    auto sbc = [](float s, float2 b, float2 c) -> float2 {
+        if (VARIANT & 2) return make_float2(__fmaf_rn(s, b.x, c.x), __fmaf_rn(s, b.y, c.y));
+        return ffma2_sbc(s, b, c);
+    };
+    auto ppp = [](float2 a, float2 b, float2 c) -> float2 {
+        if (VARIANT & 1) return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+        return __ffma2_rn(a, b, c);
+    };
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l1x[k] = sbs(H[k].f[1], y1, H[k].f[2]);
+        l1y[k] = sbs(H[k].f[4], y1, H[k].f[5]);
+        l1z[k] = sbs(H[k].f[7], y1, H[k].f[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l1x[k] = sbc(H[k].f[0], y0, l1x[k]);
+        l1y[k] = sbc(H[k].f[3], y0, l1y[k]);
+        l1z[k] = sbc(H[k].f[6], y0, l1z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l2x[k] = sbs(H[k].f[3], x1, H[k].f[6]);
+        l2y[k] = sbs(H[k].f[4], x1, H[k].f[7]);
+        r[k]   = ppp(l1y[k], x1, l1z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l2x[k] = sbc(H[k].f[0], x0, l2x[k]);
+        l2y[k] = sbc(H[k].f[1], x0, l2y[k]);
+        r[k]   = ppp(l1x[k], x0, r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (VARIANT & 8) {
+            s1[k] = make_float2(__fmaf_rn(l1x[k].x, l1x[k].x, l1y[k].x * l1y[k].x), __fmaf_rn(l1x[k].y, l1x[k].y, l1y[k].y * l1y[k].y));
+            s2[k] = make_float2(__fmaf_rn(l2x[k].x, l2x[k].x, l2y[k].x * l2y[k].x), __fmaf_rn(l2x[k].y, l2x[k].y, l2y[k].y * l2y[k].y));
+        } else {
+            s1[k] = __ffma2_rn(l1x[k], l1x[k], __fmul2_rn(l1y[k], l1y[k]));
+            s2[k] = __ffma2_rn(l2x[k], l2x[k], __fmul2_rn(l2y[k], l2y[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 nm = make_float2(-fminf(s1[k].x, s2[k].x), -fminf(s1[k].y, s2[k].y));
+        float2 q;
+        if (VARIANT & 16) q = make_float2(__fmaf_rn(r[k].x, r[k].x, nm.x), __fmaf_rn(r[k].y, r[k].y, nm.y));
+        else q = __ffma2_rn(r[k], r[k], nm);
+        cnt[k] += __float_as_uint(q.x) >> 31;
+        cnt[k] += __float_as_uint(q.y) >> 31;
+        minabs[k] = fminf(minabs[k], fminf(fabsf(q.x), fabsf(q.y)));
+    }
+}
+
+constexpr int kPts = 512;      // points per chunk in shared memory (8 KB)
+
+template <int VARIANT, int K>
+__global__ void __launch_bounds__(256, 3) bench_kernel(const float4* __restrict__ pts, const float* __restrict__ hyp, int iters,
+                                                       int* __restrict__ out) {
+    __shared__ float4 sp[kPts];     // kPts/2 point pairs x 2 float4
+    for (int i = threadIdx.x; i < kPts; i += blockDim.x) sp[i] = pts[i];
+    __syncthreads();
+    H2 H[K];
+    float G[K];
+    unsigned cnt[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) H[k].f[j] = hyp[((blockIdx.x * 256 + threadIdx.x) * K + k) * 12 + j];
+        G[k] = hyp[((blockIdx.x * 256 + threadIdx.x) * K + k) * 12 + 9];
+        cnt[k] = 0;
+    }
+    unsigned flags = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int g = 0; g < kPts / 8; ++g) {
+            float ma[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) ma[k] = INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) eval_var<VARIANT, K>(H, sp + (g * 4 + j) * 2, cnt, ma);
+#pragma unroll
+            for (int k = 0; k < K; ++k) flags |= (ma[k] <= G[k] ? 1u : 0u) << (g & 31);
+        }
+    }
+    int s = (int)flags;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += (int)cnt[k];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+template <int VARIANT, int K>
+static void run(const float4* dp, const float* dh, int* dout, int blocks) {
+    const int iters = 64;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench_kernel<VARIANT, K><<<blocks, 256>>>(dp, dh, iters, dout);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        bench_kernel<VARIANT, K><<<blocks, 256>>>(dp, dh, iters, dout);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    const double evals = (double)blocks * 256 * K * kPts * iters;
+    printf("variant %2d K %d: %.3f ms  %.1f Gevals/s  (%s)\n", VARIANT, K, best, evals / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+    const int blocks = prop.multiProcessorCount * 3 * 4;
+    float4* hp = new float4[kPts];
+    for (int i = 0; i < kPts; ++i) hp[i] = make_float4(0.3f + 0.001f * i, -0.2f + 0.002f * i, 0.1f * (i % 7), -0.05f * (i % 5));
+    const size_t nh = (size_t)blocks * 256 * 4 * 12;
+    float* hh = new float[nh];
+    for (size_t i = 0; i < nh; ++i) hh[i] = 0.01f * (float)((i * 2654435761u) % 201) - 1.0f;
+    float4* dp; float* dh; int* dout;
+    cudaMalloc(&dp, kPts * sizeof(float4)); cudaMalloc(&dh, nh * 4); cudaMalloc(&dout, (size_t)blocks * 256 * 4);
+    cudaMemcpy(dp, hp, kPts * sizeof(float4), cudaMemcpyHostToDevice); cudaMemcpy(dh, hh, nh * 4, cudaMemcpyHostToDevice);
+    run<0, 2>(dp, dh, dout, blocks);
+    run<1, 2>(dp, dh, dout, blocks);
+    run<2, 2>(dp, dh, dout, blocks);
+    run<3, 2>(dp, dh, dout, blocks);
+    run<4, 2>(dp, dh, dout, blocks);
+    run<7, 2>(dp, dh, dout, blocks);
+    run<8, 2>(dp, dh, dout, blocks);
+    run<9, 2>(dp, dh, dout, blocks);
+    run<16, 2>(dp, dh, dout, blocks);
+    run<17, 2>(dp, dh, dout, blocks);
+    run<25, 2>(dp, dh, dout, blocks);
+    run<31, 2>(dp, dh, dout, blocks);
+    run<0, 1>(dp, dh, dout, blocks);
+    run<1, 1>(dp, dh, dout, blocks);
+    run<0, 3>(dp, dh, dout, blocks);
+    run<1, 3>(dp, dh, dout, blocks);
+    return 0;
+}

@@ -17,11 +17,15 @@ namespace rg {
 #ifndef RG_HPT
 #define RG_HPT 2
 #endif
+#ifndef RG_PAIR_UNROLL
+#define RG_PAIR_UNROLL 4          // point pairs of a flag group evaluated per unrolled loop body (kSub / 2 = all)
+#endif
 constexpr int kScoreThreads = RG_SCORE_THREADS;
 constexpr int kScoreBlocksPerSM = RG_SCORE_BLOCKS;
 constexpr int kHypPerThread = RG_HPT;
 constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
 constexpr int kStages       = 2;
+constexpr int kPairUnroll   = RG_PAIR_UNROLL;
 
 // packed FMA with scalar operands broadcast inside the instruction (SASS: FFMA2 Rd, Rs.F32, Rb.F32x2, ...).  Building the
 // {s, s} pair inside the asm block keeps the coefficient in ONE register: a duplicated pair would cost a second
@@ -189,7 +193,7 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
 #pragma unroll
                     for (int k = 0; k < kHypPerThread; ++k) ma[k] = INFINITY;
                     const float4* gp = wp + g * (kSub / 2) * kV;
-#pragma unroll
+#pragma unroll kPairUnroll
                     for (int j = 0; j < kSub / 2; ++j) Pol::template evalN<kHypPerThread>(Hy, gp + j * kV, cnt, ma);
 #pragma unroll
                     for (int k = 0; k < kHypPerThread; ++k) flag[k] |= (ma[k] <= G[k] ? 1u : 0u) << g;
