@@ -254,6 +254,8 @@ def run_ours(args) -> None:
         barrier()
         return ms, (w0, w1)
 
+    if args.host_slices:
+        rt.set_option(2, args.host_slices, device=local)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -567,6 +569,7 @@ def main() -> None:
     ap.add_argument("--hyp", type=int, default=8192)
     ap.add_argument("--pool", type=int, default=80)
     ap.add_argument("--solver", type=int, default=0)
+    ap.add_argument("--host-slices", type=int, default=0, help="sub-batches of the host entry point (0 = automatic)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

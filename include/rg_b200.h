@@ -41,7 +41,9 @@ const char* rg_last_error(void);
 int rg_init(int device, void** out_ctx);
 int rg_shutdown(void* ctx);
 int rg_device_sm_count(void* ctx);
-/* option 1 = phase profiling on/off: CUDA events on the launching stream around the phases of every RANSAC call */
+/* option 1 = phase profiling on/off: CUDA events on the launching stream around the phases of every RANSAC call
+ * option 2 = number of sub-batches of rg_f_ransac_host (0 = automatic, 1 = monolithic, up to 8): the upload of sub-batch
+ *            k+1 runs on a second stream while sub-batch k is scored; results do not depend on it */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the calls since the last read
  * (at most 256 calls are remembered); synchronises `stream` */
@@ -65,7 +67,8 @@ int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, con
                     const int32_t* idx_dev, const int32_t* hyp_off_host, double thr, int mode, int tie_mode, int solver,
                     int score_path, int32_t* best_idx_dev, int32_t* best_count_dev, double* best_F_dev,
                     unsigned char* mask_dev /* may be NULL */);
-/* per-hypothesis results of the last call on this context (device pointers, valid until the next call):
+/* per-hypothesis results of the last rg_f_ransac_dev call on this context (device pointers, valid until the next call;
+ * after rg_f_ransac_host they cover only its last sub-batch — use that function's counts / F_all / flags outputs):
  * counts (hyp_off[P] int32), F_all (hyp_off[P] x 9 doubles), flags (bit0: rank-deficient sample, bit1: non-finite F) */
 int rg_f_last_hypotheses_dev(void* ctx, const int32_t** counts_dev, const double** F_all_dev,
                              const unsigned char** flags_dev);

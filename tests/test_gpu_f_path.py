@@ -278,3 +278,33 @@ def test_config3_shape_fp32_equals_fp64_and_invariances(rt, rg):
         e32 = rt.f_ransac_batched([pts], [idx[sub]], thr=thr, want_counts=True)
         e64 = rt.f_ransac_batched([pts], [idx[sub]], thr=thr, want_counts=True, score_path=rg.SCORE_FP64)
         assert np.array_equal(e32["counts"][0], e64["counts"][0])
+
+
+def test_host_entry_sub_batches_do_not_change_results(rt, rg):
+    """rg_f_ransac_host uploads its inputs in sub-batches on a second stream (option 2); pairs are independent, so every
+    output — winners, masks, per-hypothesis counts / F / flags, guard-band statistics — must be identical for any split."""
+    sizes = [900, 1500, 64, 2100, 1200, 777, 1800, 8, 1000]
+    pts = [rg.synth.two_view(n, seed=40 + k)[0] for k, n in enumerate(sizes)]
+    idx = [rg.sampling.fast(n, 96 + 32 * (k % 3), 8, seed=k) for k, n in enumerate(sizes)]
+    ref, ref_stats = None, None
+    try:
+        for s in (1, 2, 3, 4, 8):
+            rt.set_option(2, s)
+            out = rt.f_ransac_batched(pts, idx, thr=1.5, want_counts=True, want_F_all=True, want_flags=True, want_mask=True)
+            stats = rt.last_stats()
+            if ref is None:
+                ref, ref_stats = out, stats
+                continue
+            assert np.array_equal(out["best_idx"], ref["best_idx"]) and np.array_equal(out["best_count"], ref["best_count"])
+            assert np.array_equal(out["F"], ref["F"], equal_nan=True)
+            for k in range(len(sizes)):
+                assert np.array_equal(out["mask"][k], ref["mask"][k])
+                assert np.array_equal(out["counts"][k], ref["counts"][k])
+                assert np.array_equal(out["F_all"][k], ref["F_all"][k], equal_nan=True)
+                assert np.array_equal(out["flags"][k], ref["flags"][k])
+            assert (stats["recheck_groups"], stats["band_evals"], stats["flips"]) == \
+                   (ref_stats["recheck_groups"], ref_stats["band_evals"], ref_stats["flips"])
+    finally:
+        rt.set_option(2, 0)
+    with pytest.raises(ValueError):
+        rt.set_option(2, 99)

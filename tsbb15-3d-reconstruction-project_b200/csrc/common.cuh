@@ -162,6 +162,14 @@ struct Ctx {
     // pinned host staging for the small per-call tables and the statistics read-back
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage
+    // host-buffer entry points: inputs are uploaded on a second stream in sub-batches so that the copy of sub-batch
+    // k+1 overlaps the kernels of sub-batch k
+    static constexpr int kMaxSlices = 8;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t slice_ready[kMaxSlices] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_gate = nullptr;               // recorded on the caller's stream before the first upload
+    int opt_host_slices = 0;                       // option 2: 0 = automatic, n >= 1 = force n sub-batches
+    bool accumulate_stats = false;                 // sub-batches after the first add to the call's statistics
     long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // optional phase profiling (option 1): CUDA events on the launching stream around the phases of every call
     int opt_profile = 0;

@@ -114,6 +114,10 @@ int rg_shutdown(void* ctx) {
         delete[] c->prof_ev;
     }
     if (c->staging_free) cudaEventDestroy(c->staging_free);
+    if (c->copy_gate) cudaEventDestroy(c->copy_gate);
+    for (int i = 0; i < Ctx::kMaxSlices; ++i)
+        if (c->slice_ready[i]) cudaEventDestroy(c->slice_ready[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     return RG_OK;
 }
@@ -121,6 +125,7 @@ int rg_shutdown(void* ctx) {
 int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 
 // option 1: phase profiling (CUDA events on the launching stream around the phases of every RANSAC call)
+// option 2: number of sub-batches of rg_f_ransac_host (0 = automatic): uploads overlap the previous sub-batch's kernels
 int rg_set_option(void* ctx, int option, long long value) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
@@ -132,6 +137,14 @@ int rg_set_option(void* ctx, int option, long long value) {
             c->prof_ev = new cudaEvent_t[n];
             for (int i = 0; i < n; ++i) RG_CUDA(cudaEventCreate(&c->prof_ev[i]));
         }
+        return RG_OK;
+    }
+    if (option == 2) {
+        if (value < 0 || value > Ctx::kMaxSlices) {
+            set_error("invalid argument: option 2 (host sub-batches) must be in [0, %d]", Ctx::kMaxSlices);
+            return RG_ERR_ARG;
+        }
+        c->opt_host_slices = (int)value;
         return RG_OK;
     }
     set_error("invalid argument: unknown option %d", option);

@@ -64,7 +64,7 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     int* counts = (int*)c->counts.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
     RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)std::max<long long>(plan.Htot, 1), st));
-    RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
+    if (!c->accumulate_stats) RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
     if (plan.Htot == 0 || plan.Ntot == 0) return RG_OK;
     if (score_path == SCORE_FP32_GUARDED) {
         if (plan.n_items > 0) {
@@ -138,7 +138,7 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, int P, const double* pts64, con
         RG_CHECK_ARG(H == 0 || n >= 8, "a pair with hypotheses needs at least 8 correspondences");
     }
     if ((rc = f_workspace(c, plan))) return rc;
-    c->last_stats[7] = 0;
+    if (!c->accumulate_stats) c->last_stats[7] = 0;
     if (P == 0) return RG_OK;
     prof_mark(c, st, 0);
     if ((rc = f_prepare(c, st, plan, pts64, thr))) return rc;
@@ -197,6 +197,10 @@ int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
     return RG_OK;
 }
 
+// Host-buffer entry point.  The pairs are processed in up to Ctx::kMaxSlices contiguous sub-batches: all uploads are
+// queued on a second stream (one event per sub-batch), the kernels of sub-batch k wait only for their own inputs, so the
+// upload of sub-batch k+1 overlaps the scoring of sub-batch k (needs pinned host buffers to actually overlap; pageable
+// ones are still correct).  Results are identical to a single batch: pairs are independent.
 int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const int* pair_off, const int* idx,
                      const int* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path, int* best_idx,
                      int* best_count, double* best_F, unsigned char* mask, int* counts, double* F_all, unsigned char* flags) {
@@ -207,6 +211,9 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     cudaStream_t st = (cudaStream_t)stream;
     RG_CUDA(cudaSetDevice(c->device));
     if (P == 0) return RG_OK;
+    RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
+    for (int p = 0; p < P; ++p)
+        RG_CHECK_ARG(pair_off[p + 1] >= pair_off[p] && hyp_off[p + 1] >= hyp_off[p], "offset arrays must be non-decreasing");
     const size_t Ntot = (size_t)pair_off[P], Htot = (size_t)hyp_off[P];
     RG_CHECK_ARG((Ntot == 0 || pts64) && (Htot == 0 || idx), "input pointers are null");
     int rc;
@@ -215,21 +222,74 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     if ((rc = ensure(c->d_out_a, sizeof(int) * 2 * (size_t)P))) return rc;
     if ((rc = ensure(c->d_out_b, sizeof(double) * 9 * (size_t)P))) return rc;
     if (mask && (rc = ensure(c->d_out_c, std::max<size_t>(Ntot, 1)))) return rc;
-    if (Ntot) RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * Ntot, cudaMemcpyHostToDevice, st));
-    if (Htot) RG_CUDA(cudaMemcpyAsync(c->d_in_b.ptr, idx, sizeof(int) * 8 * Htot, cudaMemcpyHostToDevice, st));
+
+    // sub-batches: automatic = one per ~8 MB of input, at most 4, never more than the number of pairs
+    const size_t in_bytes = Ntot * 32 + Htot * 32;
+    int S = c->opt_host_slices > 0 ? c->opt_host_slices : (int)std::min<size_t>(3, in_bytes / (8u << 20));
+    S = std::max(1, std::min(std::min(S, P), (int)Ctx::kMaxSlices));
+    if (c->opt_profile) S = 1;                       // phase events describe one monolithic call
+    if (S > 1) {
+        if (!c->copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        if (!c->copy_gate) RG_CUDA(cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming));
+        for (int k = 0; k < S; ++k)
+            if (!c->slice_ready[k]) RG_CUDA(cudaEventCreateWithFlags(&c->slice_ready[k], cudaEventDisableTiming));
+    }
+    // the first sub-batch is small (its upload is the only one that nothing hides), the others share the rest evenly
+    int bounds[Ctx::kMaxSlices + 1];
+    bounds[0] = 0;
+    if (S == 1) {
+        bounds[1] = P;
+    } else {
+        const int first = std::max(1, P / 16);
+        for (int k = 1; k <= S; ++k) bounds[k] = first + (int)((long long)(P - first) * (k - 1) / (S - 1));
+    }
+    double* d_pts = (double*)c->d_in_a.ptr;
+    int* d_ix = (int*)c->d_in_b.ptr;
+    cudaStream_t cs = S > 1 ? c->copy_stream : st;
+    if (S > 1) {                                      // uploads may not overtake earlier work queued on the caller's stream
+        RG_CUDA(cudaEventRecord(c->copy_gate, st));
+        RG_CUDA(cudaStreamWaitEvent(cs, c->copy_gate, 0));
+    }
+    for (int k = 0; k < S; ++k) {
+        const int p0 = bounds[k], p1 = bounds[k + 1];
+        const size_t n0 = (size_t)pair_off[p0], n1 = (size_t)pair_off[p1], h0 = (size_t)hyp_off[p0], h1 = (size_t)hyp_off[p1];
+        if (n1 > n0) RG_CUDA(cudaMemcpyAsync(d_pts + 4 * n0, pts64 + 4 * n0, sizeof(double) * 4 * (n1 - n0), cudaMemcpyHostToDevice, cs));
+        if (h1 > h0) RG_CUDA(cudaMemcpyAsync(d_ix + 8 * h0, idx + 8 * h0, sizeof(int) * 8 * (h1 - h0), cudaMemcpyHostToDevice, cs));
+        if (S > 1) RG_CUDA(cudaEventRecord(c->slice_ready[k], cs));
+    }
     int* d_idx = (int*)c->d_out_a.ptr;
     int* d_cnt = d_idx + P;
-    rc = f_ransac_dev(c, st, P, (const double*)c->d_in_a.ptr, pair_off, (const int*)c->d_in_b.ptr, hyp_off, thr, mode,
-                      tie_mode, solver, score_path, d_idx, d_cnt, (double*)c->d_out_b.ptr,
-                      mask ? (unsigned char*)c->d_out_c.ptr : nullptr);
-    if (rc) return rc;
+    std::vector<int> po, ho;
+    rc = RG_OK;
+    for (int k = 0; k < S && rc == RG_OK; ++k) {
+        const int p0 = bounds[k], p1 = bounds[k + 1], Pk = p1 - p0;
+        if (Pk == 0) continue;
+        const size_t n0 = (size_t)pair_off[p0], h0 = (size_t)hyp_off[p0];
+        const int* pok = pair_off;
+        const int* hok = hyp_off;
+        if (k > 0 || S > 1) {                          // offsets relative to the sub-batch
+            po.resize(Pk + 1); ho.resize(Pk + 1);
+            for (int q = 0; q <= Pk; ++q) { po[q] = pair_off[p0 + q] - (int)n0; ho[q] = hyp_off[p0 + q] - (int)h0; }
+            pok = po.data(); hok = ho.data();
+        }
+        if (S > 1) RG_CUDA(cudaStreamWaitEvent(st, c->slice_ready[k], 0));
+        c->accumulate_stats = k > 0;
+        rc = f_ransac_dev(c, st, Pk, d_pts + 4 * n0, pok, d_ix + 8 * h0, hok, thr, mode, tie_mode, solver, score_path,
+                          d_idx + p0, d_cnt + p0, (double*)c->d_out_b.ptr + 9 * (size_t)p0,
+                          mask ? (unsigned char*)c->d_out_c.ptr + n0 : nullptr);
+        c->accumulate_stats = false;
+        if (rc) break;
+        // per-hypothesis results live in per-call workspaces: fetch them before the next sub-batch overwrites them
+        const size_t Hk = (size_t)hyp_off[p1] - h0;
+        if (counts && Hk) RG_CUDA(cudaMemcpyAsync(counts + h0, c->counts.ptr, sizeof(int) * Hk, cudaMemcpyDeviceToHost, st));
+        if (F_all && Hk) RG_CUDA(cudaMemcpyAsync(F_all + 9 * h0, c->F64.ptr, sizeof(double) * 9 * Hk, cudaMemcpyDeviceToHost, st));
+        if (flags && Hk) RG_CUDA(cudaMemcpyAsync(flags + h0, c->flags.ptr, Hk, cudaMemcpyDeviceToHost, st));
+    }
+    if (rc) { cudaStreamSynchronize(st); if (S > 1) cudaStreamSynchronize(cs); return rc; }
     RG_CUDA(cudaMemcpyAsync(best_idx, d_idx, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_count, d_cnt, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_F, c->d_out_b.ptr, sizeof(double) * 9 * (size_t)P, cudaMemcpyDeviceToHost, st));
     if (mask && Ntot) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_c.ptr, Ntot, cudaMemcpyDeviceToHost, st));
-    if (counts && Htot) RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * Htot, cudaMemcpyDeviceToHost, st));
-    if (F_all && Htot) RG_CUDA(cudaMemcpyAsync(F_all, c->F64.ptr, sizeof(double) * 9 * Htot, cudaMemcpyDeviceToHost, st));
-    if (flags && Htot) RG_CUDA(cudaMemcpyAsync(flags, c->flags.ptr, Htot, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     return RG_OK;
 }
