@@ -195,3 +195,47 @@ def test_match_first_within_bit_exact(rt):
         assert np.array_equal(ref, got), (M, N, d)
     with pytest.raises(ValueError):
         rt.match_first_within(np.zeros((3, 4)), np.zeros((2, 4)))
+
+
+def test_degenerate_inputs_terminate_and_stay_defined(rt, dino):
+    """Inputs the reference handles badly or not at all must neither hang nor corrupt neighbours: NaN / huge coordinates,
+    a point on the epipole, identical cameras (F = 0), pure-translation pairs (epipole at infinity for parallel image
+    planes).  Regular correspondences in the same launch keep their exact result."""
+    Ps = dino["Ps"]
+    a, b = _pair(dino, 0, 1)
+    good = rt.triangulate(Ps[0], Ps[1], [a], [b])[0]
+    F = og.fmatrix_from_cameras(Ps[0], Ps[1])
+    e1, e2 = og.fmatrix_epipoles(F)
+    bad1 = a.copy(); bad2 = b.copy()
+    bad1[0] = [np.nan, 1.0]; bad2[1] = [np.inf, 0.0]
+    bad1[2] = e1; bad2[2] = e2                         # both points on the epipoles
+    bad1[3] = [1e300, -1e300]; bad2[4] = [1e-300, 1e-300]
+    out = rt.triangulate(Ps[0], Ps[1], [bad1], [bad2])[0]
+    assert out.shape == good.shape
+    assert np.array_equal(out[5:], good[5:])           # untouched rows: bit-identical to the clean launch
+    assert not np.isfinite(out[0]).all() and not np.isfinite(out[1]).all()
+    # identical cameras: F = 0, every output is NaN/Inf but the call returns
+    same = rt.triangulate(Ps[0], Ps[0], [a], [a])[0]
+    assert same.shape == good.shape
+    # pure sideways translation with identity rotation: both epipoles at infinity (last component 0)
+    C1 = np.hstack([np.eye(3), np.zeros((3, 1))]); C2 = np.hstack([np.eye(3), [[1.0], [0.0], [0.0]]])
+    X = np.array([[0.1, -0.2, 4.0], [-0.3, 0.05, 6.0]])
+    x1 = X[:, :2] / X[:, 2:]; x2 = (X + [1.0, 0, 0])[:, :2] / X[:, 2:]
+    lin = rt.triangulate(C1, C2, [x1], [x2], method=1)[0]
+    assert np.abs(lin - X).max() < 1e-12
+    opt = rt.triangulate(C1, C2, [x1], [x2])[0]        # the reference divides by the zero epipole component there:
+    assert opt.shape == X.shape                        # np.roots raises LinAlgError on the NaN polynomial; here: NaN out
+    with pytest.raises(np.linalg.LinAlgError):
+        og.triangulate_optimal(C1, C2, x1[0], x2[0])
+    # relative pose: zero matrix, NaN matrix, rank-3 matrix -> defined status, no hang
+    M = np.stack([np.zeros((3, 3)), np.full((3, 3), np.nan), np.eye(3)])
+    res = rt.relative_pose(M, np.zeros((3, 2)), np.zeros((3, 2)))
+    assert res["which"].shape == (3,) and set(res["which"].tolist()) <= {-1, 0, 1, 2, 3}
+    assert (res["which"][:2] == -1).all() and np.isnan(res["R"][:2]).all()
+    # matching: NaN query / NaN observation never match, tol <= 0 matches nothing, huge tol matches the first row
+    obs = np.array([[0.0, 0.0, 1.0], [np.nan, 0.0, 1.0], [0.0, 0.0, 1.0]])
+    q = np.array([[0.0, 0.0, 1.0], [np.nan, 0.0, 1.0]])
+    assert rt.match_first_within(obs, q, 1e-4).tolist() == [0, -1]
+    assert rt.match_first_within(obs, q, 0.0).tolist() == [-1, -1]
+    assert rt.match_first_within(obs, q, np.inf).tolist() == [0, -1]
+    assert np.array_equal(rt.match_first_within(obs, q, 1e-4), og.match_first_within(obs, q, 1e-4))

@@ -154,3 +154,32 @@ def test_guard_band_dominates_fp32_error(rg):
         d = orc.distance(F, p1, p2)
         assert np.array_equal(q < 0, d < thr) or np.count_nonzero((q < 0) != (d < thr)) <= 1
     assert worst < 1.0
+
+
+def test_tables_bookkeeping_matches_reference_semantics(rg):
+    """tables.Tables / help_classes mirrors: the table bookkeeping is pure host logic (no GPU)."""
+    Tables = rg.tables.Tables
+    hc = rg.help_classes
+    T = Tables()
+    T.K = np.eye(3)
+    v0 = T.addView(0, hc.CameraPose())
+    v1 = T.addView(1, hc.CameraPose(np.eye(3), np.array([1.0, 0.0, 0.0])))
+    assert (v0, v1) == (0, 1) and T.T_views.size == 2
+    # the reference initialises observations_index to [0] (help_classes.py:27, 62): kept
+    assert T.T_views[0].observations_index.tolist() == [0]
+    p = T.addPoint(np.array([0.0, 0.0, 5.0]))
+    T.addObs(np.array([0.0, 0.0, 1.0]), v0, p)
+    T.addObs(np.array([0.2, 0.0, 1.0]), v1, p)
+    assert T.T_obs.size == 2 and T.T_obs[1].view_index == 1 and T.T_obs[1].color is None
+    assert T.T_views[1].observations_index.tolist() == [0, 1] and T.T_points[0].observations_index.tolist() == [0, 0, 1]
+    yij, Rktk, xj = T.getObsAsArrays()
+    assert yij.shape == (2, 3) and Rktk.shape == (2, 3, 4) and xj.shape == (2, 4) and xj[0, 3] == 1.0
+    assert np.array_equal(Rktk[1], np.hstack([np.eye(3), [[1.0], [0.0], [0.0]]]))
+    Rs, ts = T.getCamerasForEvaluation()
+    assert Rs.shape == (2, 3, 3) and np.array_equal(ts[1], [1.0, 0.0, 0.0])
+    assert np.allclose(T.T_views[1].getWorldPosition(), [-1.0, 0.0, 0.0])
+    C = hc.CameraPose().GetCameraMatrix()
+    assert C.shape == (3, 4) and np.array_equal(C[:, :3], np.eye(3))
+    # fun.getEFromCameras / crossProductMat are host helpers
+    E = rg.fun.getEFromCameras(T.T_views[0].camera_pose, T.T_views[1].camera_pose)
+    assert np.allclose(E, rg.fun.crossProductMat(np.array([1.0, 0.0, 0.0])))
