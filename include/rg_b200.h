@@ -147,6 +147,18 @@ int rg_relative_pose_host(void* ctx, void* stream, int P, const double* M, const
 int rg_relative_pose_dev(void* ctx, void* stream, int P, const double* M_dev, const double* K_dev, int k_per_pair,
                          const double* y1_dev, const double* y2_dev, double* Rt_dev, int32_t* which_dev,
                          int32_t* npass_dev /* may be NULL */);
+/* The two-view initialisation of main.py:54-76 (INIT2 + INIT3) for P image pairs in one call, entirely on the device:
+ * E = K^T F K (fun.getEAndK), C-normalised points K^-1 (u, v, 1)^T (fun.MakeHomogenous, fun.py:48-55, first two
+ * components as main.py passes them), fun.relative_camera_pose on the pair's FIRST correspondence (main.py:62; with a
+ * mask: the first correspondence whose mask byte is non-zero), then lab3.triangulate_optimal of every correspondence
+ * with C1 = [I | 0], C2 = [R | t] (tables.py:233-247).  pts64: (pair_off[P], 4) pixels; F: (P, 3, 3), e.g. best_F of
+ * rg_f_ransac_dev; K9: HOST (3, 3); mask (optional): correspondences with 0 are not triangulated (X = NaN).
+ * Outputs: Rt (P, 12), which (P, -1 = no candidate passes), X (pair_off[P], 3) in the frame of the first camera. */
+int rg_two_view_init_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const double* F,
+                          const double* K9, const unsigned char* mask, double* Rt, int32_t* which, double* X);
+int rg_two_view_init_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                         const double* F_dev, const double* K9_host, const unsigned char* mask_dev, double* Rt_dev,
+                         int32_t* which_dev, double* X_dev);
 /* fun.camera_resectioning (fun.py:260-283, fun.specRQ fun.py:174-184) for V cameras: C (V,3,4) -> K (V,3,3) upper
  * triangular with positive diagonal and K[2][2] = 1, R (V,3,3), t (V,3); signs follow LAPACK's RQ as the reference's do */
 int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C, double* K, double* R, double* t);

@@ -90,3 +90,67 @@ def test_match_last_view_equals_reference_loop(rg, dino, pnp_golden):
     ref = og.match_first_within(coords, qh, 1e-4)
     ref = np.where(ref >= 0, obs_idx[np.maximum(ref, 0)], -1)
     assert np.array_equal(got, ref) and (got >= 0).sum() > 10
+
+
+def test_two_view_init_batched_equals_oracle_chain(rg, dino, pnp_golden):
+    """rg_two_view_init (main.py:54-76 for P pairs in one call) against the same chain spelled out with the oracle:
+    E = K^T F K, MakeHomogenous, relative_camera_pose on the first correspondence, triangulate_optimal per point."""
+    from oracle import geom_path as og
+    K = pnp_golden["K"][0]
+    Kinv = np.linalg.inv(K)
+    Ps = dino["Ps"]
+    rng = np.random.default_rng(3)
+    pairs, Fs = [], []
+    for (i, j, noise) in ((0, 1, 0.0), (4, 5, 0.0), (10, 11, 0.4), (20, 22, 0.0), (30, 31, 1.0)):
+        a, b, _ = _pair(dino, i, j)
+        pairs.append(np.hstack([a + rng.normal(0, noise, a.shape), b + rng.normal(0, noise, b.shape)]))
+        Fs.append(og.fmatrix_from_cameras(Ps[i], Ps[j]))
+    pairs.insert(2, np.zeros((0, 4))); Fs.insert(2, Fs[0])          # an empty pair in the middle of the batch
+    res = rg.batched.two_view_init(pairs, np.stack(Fs), K)
+    for p, (pts, F) in enumerate(zip(pairs, Fs)):
+        if len(pts) == 0:
+            assert res["which"][p] == -1 and res["X"][p].shape == (0, 3)
+            continue
+        h1 = (Kinv @ np.column_stack([pts[:, :2], np.ones(len(pts))]).T).T
+        h2 = (Kinv @ np.column_stack([pts[:, 2:], np.ones(len(pts))]).T).T
+        E = K.T @ F @ K
+        R, t = og.relative_camera_pose(E, h1[0, :2], h2[0, :2])
+        assert np.abs(res["R"][p] - R).max() < 1e-9 and np.abs(res["t"][p] - t).max() < 1e-9, p
+        C1 = np.hstack([np.eye(3), np.zeros((3, 1))]); C2 = np.hstack([R, t[:, None]])
+        X = og.triangulate_optimal_batch(C1, C2, h1[:, :2], h2[:, :2])
+        err = np.abs(res["X"][p] - X).max(axis=1) / np.abs(X).max()
+        assert np.mean(err < 1e-8) >= 0.98 and np.median(err) < 1e-10, (p, np.sort(err)[-3:])
+
+
+def test_ransac_then_two_view_init_with_masks(rg, dino, pnp_golden):
+    """F-RANSAC winners and inlier masks fed straight into the batched initialisation: outliers come back as NaN, inliers
+    reproject onto their measurements."""
+    from oracle import geom_path as og
+    K = pnp_golden["K"][0]
+    rng = np.random.default_rng(8)
+    pairs = []
+    for i in (0, 7, 15):
+        a, b, _ = _pair(dino, i, i + 1)
+        pts = np.hstack([a, b]) + rng.normal(0, 0.2, (len(a), 4))
+        pts[::5, 2:] = rng.uniform(0, 600, (len(pts[::5]), 2))            # 20 % gross outliers
+        pairs.append(pts)
+    fr = rg.batched.f_ransac_pairs(pairs, n_hyp=2000, thr=1.5, seed=1)
+    res = rg.batched.two_view_init(pairs, fr["F"], K, masks=fr["mask"])
+    Kinv = np.linalg.inv(K)
+    for p, pts in enumerate(pairs):
+        m = fr["mask"][p].astype(bool)
+        assert res["which"][p] >= 0 and m.sum() > 0.6 * len(pts)
+        X = res["X"][p]
+        assert np.isnan(X[~m]).all() and np.isfinite(X[m]).all()
+        R, t = res["R"][p], res["t"][p]
+        y1 = (Kinv @ np.column_stack([pts[m, :2], np.ones(m.sum())]).T).T[:, :2]
+        y2 = (Kinv @ np.column_stack([pts[m, 2:], np.ones(m.sum())]).T).T[:, :2]
+        # (no reprojection bound: with its f = f' = 1 simplification the reference's "optimal" correction moves noisy
+        #  C-normalised points by up to ~1e-2; the contract is equality with the reference algorithm, checked here)
+        C1 = np.hstack([np.eye(3), np.zeros((3, 1))]); C2 = np.hstack([R, t[:, None]])
+        sub = np.arange(0, m.sum(), 7)
+        ref = og.triangulate_optimal_batch(C1, C2, y1[sub], y2[sub])
+        err = np.abs(X[m][sub] - ref).max(axis=1) / np.abs(ref).max()
+        assert np.mean(err < 1e-8) >= 0.95 and np.median(err) < 1e-10
+        x2 = X[m] @ R.T + t
+        assert (X[m][:, 2] > 0).mean() > 0.95 and (x2[:, 2] > 0).mean() > 0.95

@@ -38,3 +38,17 @@ def pnp_ransac_views(views, n_hyp=1024, thr2=(1.5 / 3217.0) ** 2, n=6, seed=0, i
     if idx_list is None:
         idx_list = [_sampling.fast(X.shape[0], n_hyp, n, seed + k) for k, X in enumerate(Xs)]
     return _rt.pnp_ransac_batched(Xs, ys, idx_list, thr2, **kw)
+
+
+def two_view_init(pairs, F, K, masks=None, **kw) -> dict:
+    """INIT2 + INIT3 of main.py:54-76 for many image pairs in one library call: relative pose (R, t) of the second camera
+    from F and K, and the optimally triangulated 3-D point of every (inlier) correspondence in the first camera's frame.
+    pairs: list of (p1, p2) with (2, N_p) arrays or of (N_p, 4) arrays; F: (P, 3, 3), e.g. ``f_ransac_pairs(...)["F"]``;
+    masks: optional inlier masks (``...["mask"]``)."""
+    pts = []
+    for pr in pairs:
+        if isinstance(pr, (tuple, list)):
+            pts.append(_rt.pack_pairs(pr[0], pr[1]))
+        else:
+            pts.append(np.ascontiguousarray(pr, dtype=np.float64).reshape(-1, 4))
+    return _rt.two_view_init(pts, F, K, masks=masks, **kw)

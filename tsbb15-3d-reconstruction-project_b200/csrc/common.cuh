@@ -159,6 +159,7 @@ struct Ctx {
     Buffer d_out_a, d_out_b, d_out_c, d_out_d;     // device outputs of host-buffer entry points
     Buffer pose64, pose32, X32;                    // PnP path
     Buffer geom;                                   // two-view geometry: PairGeom table + CSR offsets
+    Buffer geom_ws;                                // two-view initialisation: normalised points, cameras, picks
     // pinned host staging for the small per-call tables and the statistics read-back
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage

@@ -183,6 +183,99 @@ int rg_relative_pose_host(void* ctx, void* stream, int P, const double* M, const
     return RG_OK;
 }
 
+// main.py:54-76 for P pairs: E = K^T F K, C-normalised points, relative pose (cheirality on the pair's first
+// correspondence, or first inlier when a mask is given), optimal triangulation of every (inlier) correspondence
+int rg_two_view_init_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                         const double* F_dev, const double* K9_host, const unsigned char* mask_dev, double* Rt_dev,
+                         int32_t* which_dev, double* X_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_offsets(P, pair_off_host);
+    if (rc) return rc;
+    RG_CHECK_ARG(K9_host != nullptr, "K is null");
+    RG_CUDA(cudaSetDevice(c->device));
+    c->last_stats[7] = 0;
+    if (P == 0) return RG_OK;
+    const size_t N = (size_t)pair_off_host[P], p = (size_t)P;
+    RG_CHECK_ARG(F_dev && Rt_dev && which_dev && (N == 0 || (pts64_dev && X_dev)), "null buffers");
+    // K^-1 by the adjugate (3x3, host)
+    const double* K = K9_host;
+    Mat3 Ki;
+    {
+        const double c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+        const double det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+        RG_CHECK_ARG(det != 0.0 && std::isfinite(det), "K is singular");
+        const double id = 1.0 / det;
+        Ki.m[0] = c00 * id; Ki.m[1] = (K[2] * K[7] - K[1] * K[8]) * id; Ki.m[2] = (K[1] * K[5] - K[2] * K[4]) * id;
+        Ki.m[3] = c01 * id; Ki.m[4] = (K[0] * K[8] - K[2] * K[6]) * id; Ki.m[5] = (K[2] * K[3] - K[0] * K[5]) * id;
+        Ki.m[6] = c02 * id; Ki.m[7] = (K[1] * K[6] - K[0] * K[7]) * id; Ki.m[8] = (K[0] * K[4] - K[1] * K[3]) * id;
+    }
+    // workspace: x1n, x2n (N double2 each) | y1, y2 (P double2 each) | C1, C2 (P x 12) | K (9) | pair_off (P + 1 ints)
+    const size_t nd = 4 * N + 4 * p + 24 * p + 10;
+    if ((rc = ensure(c->geom_ws, sizeof(double) * nd + sizeof(int) * (p + 1)))) return rc;
+    double* w = (double*)c->geom_ws.ptr;
+    double2* x1n = (double2*)w;
+    double2* x2n = x1n + N;
+    double2* y1 = x2n + N;
+    double2* y2 = y1 + p;
+    double* C1 = (double*)(y2 + p);
+    double* C2 = C1 + 12 * p;
+    double* dK = C2 + 12 * p;
+    int* doff = (int*)(dK + 10);
+    RG_CUDA(cudaEventSynchronize(c->staging_free));
+    if ((rc = ensure_pinned(c->h_stage, sizeof(double) * 10 + sizeof(int) * (p + 1)))) return rc;
+    memcpy(c->h_stage.ptr, K, sizeof(double) * 9);
+    memcpy((char*)c->h_stage.ptr + sizeof(double) * 10, pair_off_host, sizeof(int) * (p + 1));
+    RG_CUDA(cudaMemcpyAsync(dK, c->h_stage.ptr, sizeof(double) * 10 + sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
+    RG_CUDA(cudaEventRecord(c->staging_free, st));
+    if (N) tv_normalise<<<ceil_div((long long)N, 256), 256, 0, st>>>((const double4*)pts64_dev, mask_dev, (int)N, Ki, x1n, x2n);
+    tv_pick<<<ceil_div((long long)P * 32, 128), 128, 0, st>>>(x1n, x2n, mask_dev, doff, P, y1, y2);
+    relative_pose_kernel<<<ceil_div((long long)P * 4, kGeomThreads), kGeomThreads, 0, st>>>(F_dev, dK, 0, y1, y2, P, Rt_dev,
+                                                                                            which_dev, nullptr);
+    tv_cameras<<<ceil_div((long long)P * 12, 256), 256, 0, st>>>(Rt_dev, P, C1, C2);
+    RG_CUDA(cudaGetLastError());
+    const int launches = 4;
+    if (N) {
+        if ((rc = triangulate_dev(c, st, P, C1, C2, pair_off_host, (const double*)x1n, (const double*)x2n, TRI_OPTIMAL, X_dev)))
+            return rc;
+    }
+    c->last_stats[7] += launches;
+    return RG_OK;
+}
+
+int rg_two_view_init_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const double* F,
+                          const double* K9, const unsigned char* mask, double* Rt, int32_t* which, double* X) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_offsets(P, pair_off);
+    if (rc) return rc;
+    RG_CUDA(cudaSetDevice(c->device));
+    if (P == 0) return RG_OK;
+    const size_t N = (size_t)pair_off[P], p = (size_t)P;
+    RG_CHECK_ARG(F && K9 && Rt && which && (N == 0 || (pts64 && X)), "null buffers");
+    if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * std::max<size_t>(N, 1)))) return rc;
+    if ((rc = ensure(c->d_in_b, sizeof(double) * 9 * p))) return rc;
+    if ((rc = ensure(c->d_in_c, std::max<size_t>(N, 1)))) return rc;
+    if ((rc = ensure(c->d_out_b, sizeof(double) * (12 * p + 3 * std::max<size_t>(N, 1))))) return rc;
+    if ((rc = ensure(c->d_out_a, sizeof(int) * p))) return rc;
+    if (N) RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * N, cudaMemcpyHostToDevice, st));
+    RG_CUDA(cudaMemcpyAsync(c->d_in_b.ptr, F, sizeof(double) * 9 * p, cudaMemcpyHostToDevice, st));
+    if (mask && N) RG_CUDA(cudaMemcpyAsync(c->d_in_c.ptr, mask, N, cudaMemcpyHostToDevice, st));
+    double* dRt = (double*)c->d_out_b.ptr;
+    double* dX = dRt + 12 * p;
+    if ((rc = rg_two_view_init_dev(ctx, stream, P, (const double*)c->d_in_a.ptr, pair_off, (const double*)c->d_in_b.ptr, K9,
+                                   (mask && N) ? (const unsigned char*)c->d_in_c.ptr : nullptr, dRt, (int32_t*)c->d_out_a.ptr,
+                                   dX)))
+        return rc;
+    RG_CUDA(cudaMemcpyAsync(Rt, dRt, sizeof(double) * 12 * p, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(which, c->d_out_a.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost, st));
+    if (N) RG_CUDA(cudaMemcpyAsync(X, dX, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    return RG_OK;
+}
+
 int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C, double* K, double* R, double* t) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     RG_CHECK_ARG(V >= 0, "negative number of cameras");

@@ -474,6 +474,9 @@ __global__ void __launch_bounds__(kGeomThreads) triangulate_kernel(const PairGeo
         const double h1[3] = {a.x, a.y, 1.0}, h2[3] = {b.x, b.y, 1.0};
         triangulate_linear_h(g.C1, g.C2, h1, h2, out);
     }
+    if (!(isfinite(a.x) && isfinite(a.y) && isfinite(b.x) && isfinite(b.y))) {       // undefined input -> NaN, not Inf
+        out[0] = out[1] = out[2] = __longlong_as_double(0x7ff8000000000000ll);
+    }
     X[(size_t)i * 3] = out[0]; X[(size_t)i * 3 + 1] = out[1]; X[(size_t)i * 3 + 2] = out[2];
 }
 
@@ -585,6 +588,65 @@ __global__ void __launch_bounds__(kGeomThreads) relative_pose_kernel(const doubl
         which[p] = first;
         if (npass) npass[p] = __popc(grp);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-view initialisation of main.py:54-76 for P pairs at once: C-normalise (fun.MakeHomogenous, fun.py:48-55), pick the
+// correspondence for the cheirality test, build the cameras [I | 0], [R | t] for the batched triangulation.
+// ------------------------------------------------------------------------------------------------
+struct Mat3 { double m[9]; };
+
+// pts: (N, 4) pixels (x0, x1, y0, y1).  x1n / x2n: first two components of K^-1 (u, v, 1)^T (NOT divided by the third,
+// exactly what main.py passes on: y_hom[:, :2]).  Correspondences with mask == 0 become NaN (they are not triangulated).
+__global__ void __launch_bounds__(256) tv_normalise(const double4* __restrict__ pts, const unsigned char* __restrict__ mask,
+                                                    int N, Mat3 Kinv, double2* __restrict__ x1n, double2* __restrict__ x2n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double4 v = pts[i];
+    double2 a, b;
+    a.x = Kinv.m[0] * v.x + Kinv.m[1] * v.y + Kinv.m[2];
+    a.y = Kinv.m[3] * v.x + Kinv.m[4] * v.y + Kinv.m[5];
+    b.x = Kinv.m[0] * v.z + Kinv.m[1] * v.w + Kinv.m[2];
+    b.y = Kinv.m[3] * v.z + Kinv.m[4] * v.w + Kinv.m[5];
+    if (mask != nullptr && mask[i] == 0) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        a = make_double2(qnan, qnan); b = a;
+    }
+    x1n[i] = a; x2n[i] = b;
+}
+
+// one warp per pair: the first correspondence of the pair (main.py:62 uses index 0), or the first with mask != 0
+__global__ void __launch_bounds__(128) tv_pick(const double2* __restrict__ x1n, const double2* __restrict__ x2n,
+                                               const unsigned char* __restrict__ mask, const int* __restrict__ pair_off,
+                                               int P, double2* __restrict__ y1, double2* __restrict__ y2) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    const int lo = pair_off[p], hi = pair_off[p + 1];
+    int pick = -1;
+    if (mask == nullptr) {
+        pick = lo < hi ? lo : -1;
+    } else {
+        for (int base = lo; base < hi && pick < 0; base += 32) {
+            const int i = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < hi && mask[i] != 0);
+            if (m) pick = base + __ffs(m) - 1;
+        }
+    }
+    if (lane == 0) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        y1[p] = pick >= 0 ? x1n[pick] : make_double2(qnan, qnan);
+        y2[p] = pick >= 0 ? x2n[pick] : make_double2(qnan, qnan);
+    }
+}
+
+__global__ void __launch_bounds__(256) tv_cameras(const double* __restrict__ Rt, int P, double* __restrict__ C1,
+                                                  double* __restrict__ C2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * 12) return;
+    const int p = i / 12, k = i % 12, r = k >> 2, c = k & 3;
+    C1[i] = (r == c) ? 1.0 : 0.0;
+    C2[i] = (c < 3) ? Rt[(size_t)p * 12 + 3 * r + c] : Rt[(size_t)p * 12 + 9 + r];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -359,6 +359,38 @@ def relative_pose(M, y1, y2, K=None, device=None, stream=0) -> dict:
     return {"R": Rt[:, :9].reshape(P, 3, 3).copy(), "t": Rt[:, 9:].copy(), "which": which, "npass": npass}
 
 
+def two_view_init(pts_list, F, K, masks=None, device=None, stream=0) -> dict:
+    """main.py:54-76 (E = K^T F K, C-normalisation, relative pose, triangulation of every correspondence) for P image
+    pairs in ONE library call.  pts_list[p]: (N_p, 4) pixel rows (x0, x1, y0, y1); F: (P, 3, 3); K: (3, 3);
+    masks[p] (optional): (N_p,) uint8, zero = skip.  Returns dict(R (P,3,3), t (P,3), which (P,), X list of (N_p,3))."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    P = len(pts_list)
+    F = _f64(F).reshape(-1, 3, 3)
+    K = _f64(K)
+    if F.shape[0] != P or K.shape != (3, 3):
+        raise ValueError("F must be (P, 3, 3) and K (3, 3)")
+    pts = [_f64(p).reshape(-1, 4) for p in pts_list]
+    off = np.zeros(P + 1, dtype=np.int32)
+    for p in range(P):
+        off[p + 1] = off[p] + pts[p].shape[0]
+    N = int(off[-1])
+    allp = np.ascontiguousarray(np.concatenate(pts)) if P else np.zeros((0, 4))
+    mask = None
+    if masks is not None:
+        if len(masks) != P or any(len(m) != pts[p].shape[0] for p, m in enumerate(masks)):
+            raise ValueError("masks must match pts_list")
+        mask = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.uint8) for m in masks])) if P else None
+    Rt = np.full((P, 12), np.nan)
+    which = np.full(P, -1, dtype=np.int32)
+    X = np.full((N, 3), np.nan)
+    cabi.check(lib.rg_two_view_init_host(_vp(ctx), _vp(stream), P, _vp(cabi.ptr(allp)), off.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         _vp(cabi.ptr(F)), _vp(cabi.ptr(K)), _vp(cabi.ptr(mask)), _vp(cabi.ptr(Rt)),
+                                         _vp(cabi.ptr(which)), _vp(cabi.ptr(X))))
+    return {"R": Rt[:, :9].reshape(P, 3, 3).copy(), "t": Rt[:, 9:].copy(), "which": which,
+            "X": [X[off[p]:off[p + 1]] for p in range(P)]}
+
+
 def camera_resectioning(Cs, device=None, stream=0):
     """fun.camera_resectioning for V cameras: (V, 3, 4) -> K (V,3,3), R (V,3,3), t (V,3)."""
     lib = cabi.load_library()
