@@ -54,7 +54,7 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 int rg_microbench_run(double* out6, void* stream);
 
 /* out8 = {guard-band groups flagged by the FP32 scorer, band evaluations redone in FP64, decisions changed by that,
- *         0, 0, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
+ *         0, hypotheses with an out-of-range sample index, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
 int rg_get_last_stats(void* ctx, void* stream, long long* out8);
 
 /* ---- F-matrix RANSAC: replaces the loop of fun.getFFromLabCode (fun.py:303-328), which calls
@@ -69,7 +69,9 @@ int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, con
                     unsigned char* mask_dev /* may be NULL */);
 /* per-hypothesis results of the last rg_f_ransac_dev call on this context (device pointers, valid until the next call;
  * after rg_f_ransac_host they cover only its last sub-batch — use that function's counts / F_all / flags outputs):
- * counts (hyp_off[P] int32), F_all (hyp_off[P] x 9 doubles), flags (bit0: rank-deficient sample, bit1: non-finite F) */
+ * counts (hyp_off[P] int32), F_all (hyp_off[P] x 9 doubles), flags (bit0: rank-deficient sample, bit1: non-finite F,
+ * bit2: a sample index outside [0, N) of the pair — the solver clamps it; rg_f_ransac_host then returns -2 and
+ * rg_get_last_stats reports the number of such hypotheses in out8[4]) */
 int rg_f_last_hypotheses_dev(void* ctx, const int32_t** counts_dev, const double** F_all_dev,
                              const unsigned char** flags_dev);
 /* Same with host buffers; counts / F_all / flags / mask are optional (NULL = not copied back). */

@@ -308,3 +308,21 @@ def test_host_entry_sub_batches_do_not_change_results(rt, rg):
         rt.set_option(2, 0)
     with pytest.raises(ValueError):
         rt.set_option(2, 99)
+
+
+def test_out_of_range_sample_index_is_rejected_by_the_library(rt, rg):
+    """The batched call no longer scans the index arrays on the host: the solver flags indices outside [0, N_p) where it
+    reads them and the host entry point fails with ValueError (numpy indexing in the reference raises IndexError)."""
+    pts = [rg.synth.two_view(500, seed=k)[0] for k in range(3)]
+    idx = [rg.sampling.fast(500, 64, 8, seed=k) for k in range(3)]
+    rt.f_ransac_batched(pts, idx)                                   # fine
+    for bad in (500, -1, 2 ** 30):
+        idx2 = [i.copy() for i in idx]
+        idx2[1][17, 3] = bad
+        with pytest.raises(ValueError):
+            rt.f_ransac_batched(pts, idx2)
+        assert rt.last_stats()["bad_index_hyps"] == 1
+    out = rt.f_ransac_batched(pts, idx)                             # the context stays usable
+    assert (out["best_count"] > 0).all() and rt.last_stats()["bad_index_hyps"] == 0
+    with pytest.raises(ValueError):
+        rt.f8pt_solve(pts[0], np.full((4, 8), 500, dtype=np.int32))

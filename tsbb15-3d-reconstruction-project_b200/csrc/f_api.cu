@@ -98,7 +98,8 @@ static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const dou
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     int* counts = (int*)c->counts.ptr;
     int2* best = (int2*)c->best.ptr;
-    argmax_counts<<<plan.P, 256, 0, st>>>(counts, pi, best);
+    argmax_counts<<<plan.P, 256, 0, st>>>(counts, pi, best, (const unsigned char*)c->flags.ptr,
+                                          (unsigned long long*)c->stats.ptr);
     c->last_stats[7] += 1;
     if (tie_mode == TIE_REFERENCE && plan.Htot > 0) {
         const int nb = (int)std::min<long long>(plan.Htot, (long long)c->sm_count * 8);
@@ -291,6 +292,12 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     RG_CUDA(cudaMemcpyAsync(best_F, c->d_out_b.ptr, sizeof(double) * 9 * (size_t)P, cudaMemcpyDeviceToHost, st));
     if (mask && Ntot) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_c.ptr, Ntot, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
+    // sample indices are validated where they are read (the solver clamps them and sets flag bit 2): no host pass over idx
+    if (c->h_stats.ptr && ((const unsigned long long*)c->h_stats.ptr)[4] != 0) {
+        set_error("invalid argument: %llu hypotheses have a sample index outside [0, N) of their pair",
+                  ((const unsigned long long*)c->h_stats.ptr)[4]);
+        return RG_ERR_ARG;
+    }
     return RG_OK;
 }
 

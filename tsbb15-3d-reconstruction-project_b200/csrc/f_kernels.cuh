@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
     const PairInfo& info = pi[lo];
 
     double X[8], Y[8], x[8], y[8];
+    bool bad_index = false;
     {
         const int4 i0 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2];
         const int4 i1 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2 + 1];
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             int j = id[k];
+            bad_index = bad_index || j < 0 || j >= info.n;       // reported through flag bit 2 / the call's status
             j = j < 0 ? 0 : (j >= info.n ? info.n - 1 : j);     // never read out of the pair
             const double4 v = pts[info.pt_off + j];
             X[k] = v.x; Y[k] = v.y; x[k] = v.z; y[k] = v.w;
@@ -436,6 +438,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
     unsigned char fl = 0;
     if (!(rmin > 1e-9 * rmax)) fl |= 1;       // (nearly) rank-deficient sample: null direction not unique
     if (!finite) fl |= 2;
+    if (bad_index) fl |= 4;                   // a sample index outside [0, n): clamped, and the host call fails
     flags[h] = fl;
     make_hyp32<MODE>(F, info, hyp32 + h);
 }

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4*
     const PairInfo& info = pi[lo];
 
     double X[8], Y[8], x[8], y[8];
+    bool bad_index = false;
     {
         const int4 i0 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2];
         const int4 i1 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2 + 1];
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4*
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             int q = id[k];
+            bad_index = bad_index || q < 0 || q >= info.n;
             q = q < 0 ? 0 : (q >= info.n ? info.n - 1 : q);
             const double4 v = pts[info.pt_off + q];
             X[k] = v.x; Y[k] = v.y; x[k] = v.z; y[k] = v.w;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4*
         unsigned char fl = 0;
         if (!(s1 > 1e-18 * smax)) fl |= 1;        // sigma_8 / sigma_1 <= 1e-9: null direction not unique
         if (!finite) fl |= 2;
+        if (bad_index) fl |= 4;
         flags[h] = fl;
         make_hyp32<MODE>(F, info, hyp32 + h);
     }

@@ -125,7 +125,7 @@ static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const
     prof_mark(c, st, 4);
     int2* best = (int2*)c->best.ptr;
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
-    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts.ptr, pi, best);
+    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts.ptr, pi, best, nullptr, nullptr);
     const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
     pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
                                             best_count);

@@ -334,17 +334,22 @@ __global__ void __launch_bounds__(256) fixup_scan(typename Fix::Params prm, long
 }
 
 // best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
+// flags / stats (optional): hypotheses whose flag byte has bit 2 set (sample index out of range) are counted in stats[4]
 __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
-                                                      int2* __restrict__ best) {
+                                                      int2* __restrict__ best, const unsigned char* __restrict__ flags,
+                                                      unsigned long long* __restrict__ stats) {
     __shared__ unsigned long long sk[8];
     const int p = blockIdx.x;
     const PairInfo info = pi[p];
     unsigned long long key = 0ull;
+    unsigned bad = 0u;
     for (int h = threadIdx.x; h < info.H; h += blockDim.x) {
         const unsigned long long k =
             ((unsigned long long)(unsigned)counts[info.hyp_off + h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
         key = k > key ? k : key;
+        if (flags != nullptr) bad += (flags[info.hyp_off + h] >> 2) & 1u;
     }
+    if (stats != nullptr && bad) atomicAdd(&stats[4], (unsigned long long)bad);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);

@@ -23,6 +23,23 @@ def _f64(a, shape_tail=None):
     return arr
 
 
+_STAGE: dict = {}
+
+
+def _concat_into(key, arrays, tail, dtype) -> np.ndarray:
+    """np.concatenate into a cached grow-only buffer: the batched entry points are called in loops with the same shapes,
+    and a fresh 10 MB allocation per call costs more than the GPU work of a small batch."""
+    n = sum(a.shape[0] for a in arrays)
+    buf = _STAGE.get(key)
+    if buf is None or buf.shape[0] < n:
+        buf = np.empty((n + n // 4 + 16,) + tuple(tail), dtype=dtype)
+        _STAGE[key] = buf
+    out = buf[:n]
+    if arrays:
+        np.concatenate(arrays, axis=0, out=out)
+    return out
+
+
 def pack_pairs(p1, p2) -> np.ndarray:
     """(2, N) + (2, N) reference layout  ->  (N, 4) rows (x0, x1, y0, y1)."""
     p1 = np.asarray(p1, dtype=np.float64)
@@ -49,7 +66,8 @@ def last_stats(device=None, stream=0) -> dict:
     lib = cabi.load_library()
     out = (C.c_longlong * 8)()
     cabi.check(lib.rg_get_last_stats(_vp(cabi.context(device)), _vp(stream), out))
-    return {"recheck_groups": out[0], "band_evals": out[1], "flips": out[2], "overflow": out[3], "launches": out[7]}
+    return {"recheck_groups": out[0], "band_evals": out[1], "flips": out[2], "overflow": out[3], "bad_index_hyps": out[4],
+            "launches": out[7]}
 
 
 def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TIE_FIRST, solver=SOLVER_QR,
@@ -73,13 +91,11 @@ def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TI
     for p in range(P):
         pair_off[p + 1] = pair_off[p] + pts[p].shape[0]
         hyp_off[p + 1] = hyp_off[p] + idx[p].shape[0]
-        if idx[p].size and (idx[p].min() < 0 or idx[p].max() >= pts[p].shape[0]):
-            raise ValueError(f"pair {p}: sample index out of range")
+    # (sample indices are range-checked on the device where they are read: an index outside [0, N_p) makes the library
+    #  call fail with ValueError — no host pass over the index arrays)
     Ntot, Htot = int(pair_off[-1]), int(hyp_off[-1])
-    pts_all = np.concatenate(pts, axis=0) if P else np.zeros((0, 4))
-    idx_all = np.concatenate(idx, axis=0) if P else np.zeros((0, 8), dtype=np.int32)
-    pts_all = np.ascontiguousarray(pts_all)
-    idx_all = np.ascontiguousarray(idx_all)
+    pts_all = _concat_into("f_pts", pts, (4,), np.float64)
+    idx_all = _concat_into("f_idx", idx, (8,), np.int32)
     best_idx = np.full(P, -1, dtype=np.int32)
     best_count = np.zeros(P, dtype=np.int32)
     best_F = np.full((P, 3, 3), np.nan)
