@@ -533,6 +533,35 @@ def run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch) -> dict:
                                        "cpu_baseline": {"value": 32 / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
                                                         "sample": "32 pairs, numpy oracle port of fun.relative_camera_pose"}}
 
+    # main.py:54-76 for 512 pairs x 2000 correspondences in one call (E = K^T F K, relative pose, triangulation)
+    Pt, Nt = 512, 2000
+    it = rng.integers(0, 35, Pt)
+    tv_pts = np.empty((Pt * Nt, 4))
+    tv_F = np.empty((Pt, 3, 3))
+    for k, i in enumerate(it):
+        Xs = np.column_stack([rng.uniform(-0.04, 0.04, Nt), rng.uniform(-0.07, 0.02, Nt), rng.uniform(-0.7, -0.56, Nt),
+                              np.ones(Nt)])
+        a, b = Xs @ Ps[i].T, Xs @ Ps[i + 1].T
+        tv_pts[k * Nt:(k + 1) * Nt, :2] = a[:, :2] / a[:, 2:]
+        tv_pts[k * Nt:(k + 1) * Nt, 2:] = b[:, :2] / b[:, 2:]
+        tv_F[k] = Fs[i]
+    tv_pts += rng.normal(0, 0.3, tv_pts.shape)
+    d_tp, d_tF = torch.from_numpy(tv_pts).to(dev), torch.from_numpy(tv_F).to(dev)
+    d_tRt = torch.empty((Pt, 12), dtype=torch.float64, device=dev)
+    d_tw = torch.empty(Pt, dtype=torch.int32, device=dev)
+    d_tX = torch.empty((Pt * Nt, 3), dtype=torch.float64, device=dev)
+    toff = (np.arange(Pt + 1, dtype=np.int32) * Nt)
+    Kc = np.ascontiguousarray(Ks)
+
+    def tcall():
+        cabi.check(lib.rg_two_view_init_dev(vp(ctx), vp(stream), Pt, vp(d_tp.data_ptr()), toff.ctypes.data_as(pi32),
+                                            vp(d_tF.data_ptr()), vp(Kc.ctypes.data), None, vp(d_tRt.data_ptr()),
+                                            vp(d_tw.data_ptr()), vp(d_tX.data_ptr())))
+    ms = ev_time(tcall, 5)
+    out["two_view_init_512_pairs_x_2000"] = {"ms": ms, "pairs_per_s": Pt / (ms * 1e-3), "points_per_s": Pt * Nt / (ms * 1e-3),
+                                             "resolved": int((d_tw >= 0).sum().item()),
+                                             "finite_points": int(torch.isfinite(d_tX).all(dim=1).sum().item())}
+
     # 2D<->3D match loop of Tables.addNewView: 20 000 queries against 20 000 observations, 2/3 of them present
     M = Nq = 20000
     obs = np.column_stack([rng.uniform(-0.1, 0.1, (M, 2)), np.ones(M)])
