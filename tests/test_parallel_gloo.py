@@ -25,6 +25,43 @@ def _oracle_compute(pts_list, idx_list, thr=1.5, **kw):
     return out
 
 
+def _oracle_pnp(X, y, idx, thr2, **kw):
+    from oracle import pnp_path as opnp
+    X = np.asarray(X, dtype=np.float64)
+    yh = np.hstack([np.asarray(y, dtype=np.float64), np.ones((len(X), 1))])
+    r = opnp.pnp_ransac(X, yh, np.asarray(idx), thr2)
+    return {"best_idx": r["best"], "best_count": int(r["counts"].max()) if r["best"] >= 0 else 0,
+            "R": r["R"] if r["best"] >= 0 else np.full((3, 3), np.nan), "t": r["t"] if r["best"] >= 0 else np.full(3, np.nan),
+            "mask": r["mask"]}
+
+
+def _oracle_pnp_batched(X_list, y_list, idx_list, thr2, **kw):
+    rs = [_oracle_pnp(X, y, i, thr2) for X, y, i in zip(X_list, y_list, idx_list)]
+    return {"best_idx": np.array([r["best_idx"] for r in rs], np.int32), "best_count": np.array([r["best_count"] for r in rs], np.int32),
+            "R": np.stack([r["R"] for r in rs]), "t": np.stack([r["t"] for r in rs])}
+
+
+def _pnp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from tsbb15_b200 import parallel, sampling, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        thr2 = (1.5 / 3217.0) ** 2
+        X, y, _ = synth.pnp_scene(200, seed=3, sigma_px=0.02, outlier_frac=0.2)
+        idx = sampling.fast(200, 25, 6, seed=1)
+        one = parallel.pnp_ransac_split_hypotheses(X, y, idx, thr2, compute=_oracle_pnp)
+        views = [synth.pnp_scene(80 + 10 * v, seed=v, sigma_px=0.02, outlier_frac=0.1)[:2] for v in range(3)]
+        vidx = [sampling.fast(len(v[0]), 80, 6, seed=v_) for v_, v in enumerate(views)]
+        sh = parallel.pnp_ransac_views_sharded([v[0] for v in views], [v[1] for v in views], vidx, thr2,
+                                               compute=_oracle_pnp_batched)
+        q.put((rank, one["best_idx"], one["best_count"], one["R"].tolist(), one["t"].tolist(), one["mask"].tolist(),
+               one["owner"], sh["range"], sh["best_idx"].tolist(), sh["best_count"].tolist(), sh["R"].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -79,3 +116,34 @@ def test_world_size_2_gloo():
         assert np.allclose(np.array(o[7]), ref["F"][0])
         assert o[8] == ref["mask"][0].tolist()
     assert outs[0][9] == outs[1][9] in (0, 1)
+
+
+def test_world_size_2_gloo_pnp():
+    """PnP: hypotheses of one view split over two ranks (one 8-byte max-all-reduce) and views sharded over ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pnp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, ROOT)
+    from tsbb15_b200 import sampling, synth
+    thr2 = (1.5 / 3217.0) ** 2
+    X, y, _ = synth.pnp_scene(200, seed=3, sigma_px=0.02, outlier_frac=0.2)
+    ref = _oracle_pnp(X, y, sampling.fast(200, 25, 6, seed=1), thr2)
+    views = [synth.pnp_scene(80 + 10 * v, seed=v, sigma_px=0.02, outlier_frac=0.1)[:2] for v in range(3)]
+    vidx = [sampling.fast(len(v[0]), 80, 6, seed=v_) for v_, v in enumerate(views)]
+    refb = _oracle_pnp_batched([v[0] for v in views], [v[1] for v in views], vidx, thr2)
+    assert outs[0][7] == (0, 2) and outs[1][7] == (2, 3)
+    for o in outs:
+        assert o[1] == ref["best_idx"] >= 0 and o[2] == ref["best_count"]
+        assert np.allclose(np.array(o[3]), ref["R"]) and np.allclose(np.array(o[4]), ref["t"])
+        assert o[5] == ref["mask"].tolist()
+        assert o[8] == refb["best_idx"].tolist() and o[9] == refb["best_count"].tolist()
+        assert np.allclose(np.array(o[10]), refb["R"], equal_nan=True)
+    assert (refb["best_idx"] >= 0).any()
+    assert outs[0][6] == outs[1][6] in (0, 1)

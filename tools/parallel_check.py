@@ -32,6 +32,21 @@ def main():
     split = parallel.f_ransac_split_hypotheses(pts, idx, thr=1.5, device=local)
     ok2 = (split["best_idx"] == int(one["best_idx"][0]) and split["best_count"] == int(one["best_count"][0])
            and np.array_equal(split["mask"], one["mask"][0]) and np.array_equal(split["F"], one["F"][0]))
+    # PnP: hypotheses of one view split over the ranks; views sharded over the ranks
+    thr2 = (1.5 / 3217.0) ** 2
+    X, y, _ = synth.pnp_scene(30000, seed=4)
+    pidx = sampling.fast(30000, 2048, 6, seed=2)
+    pone = rt.pnp_ransac(X, y, pidx, thr2, device=local)
+    psplit = parallel.pnp_ransac_split_hypotheses(X, y, pidx, thr2, device=local)
+    ok3 = (psplit["best_idx"] == pone["best_idx"] and psplit["best_count"] == pone["best_count"]
+           and np.array_equal(psplit["mask"], pone["mask"]) and np.array_equal(psplit["R"], pone["R"]))
+    views = [synth.pnp_scene(500 + 37 * v, seed=v)[:2] for v in range(5)]
+    vidx = [sampling.fast(len(v[0]), 256, 6, seed=k) for k, v in enumerate(views)]
+    vref = rt.pnp_ransac_batched([v[0] for v in views], [v[1] for v in views], vidx, thr2, device=local)
+    vsh = parallel.pnp_ransac_views_sharded([v[0] for v in views], [v[1] for v in views], vidx, thr2, device=local)
+    ok4 = (np.array_equal(vsh["best_idx"], vref["best_idx"]) and np.array_equal(vsh["best_count"], vref["best_count"])
+           and np.array_equal(vsh["R"], vref["R"], equal_nan=True))
+    ok2 = ok2 and ok3 and ok4
     res = torch.tensor([int(ok1), int(ok2)], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:

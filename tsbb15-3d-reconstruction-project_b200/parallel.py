@@ -130,3 +130,94 @@ def f_ransac_split_hypotheses(pts, idx, thr=1.5, group=None, compute=None, **kw)
     payload = payload.cpu().numpy()
     return {"best_idx": gi, "best_count": cnt, "F": payload[:9].reshape(3, 3), "mask": payload[9:].astype(np.uint8),
             "owner": owner}
+
+
+def pnp_ransac_split_hypotheses(X, y, idx, thr2, group=None, compute=None, **kw) -> dict:
+    """PnP-RANSAC of ONE view (BASELINE config 4 at G > 1) with the pose hypotheses split across ranks: every rank holds
+    all N correspondences and scores its slice of the (H, n) samples; the same 8-byte max-all-reduce on
+    ``(count << 32) | ~index`` as the F path picks the winner (first maximum, ransac.py:108); its owner broadcasts
+    R, t and the consensus mask."""
+    import torch
+    rank, world = _world(group)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    H = idx.shape[0]
+    lo, hi = shard_range(H, rank, world)
+    compute = compute or _rt.pnp_ransac
+    kw = dict(kw)
+    kw["want_mask"] = True
+    n = np.asarray(X).reshape(-1, 3).shape[0]
+    if hi > lo:
+        local = compute(X, y, idx[lo:hi], thr2, **kw)
+    else:
+        local = {"best_idx": -1, "best_count": 0, "R": np.full((3, 3), np.nan), "t": np.full(3, np.nan),
+                 "mask": np.zeros(n, np.uint8)}
+    li = int(local["best_idx"])
+    key = argmax_key(int(local["best_count"]), lo + li) if li >= 0 else 0
+    if world == 1:
+        cnt, gi = key_decode(key) if key else (0, -1)
+        return {"best_idx": gi, "best_count": cnt, "R": local["R"], "t": local["t"], "mask": local["mask"], "owner": 0}
+    dist = _dist()
+    dev = _device_for_collectives(group)
+    k = torch.tensor([key], dtype=torch.int64, device=dev)
+    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+    gkey = int(k.item())
+    if gkey == 0:
+        return {"best_idx": -1, "best_count": 0, "R": np.full((3, 3), np.nan), "t": np.full(3, np.nan),
+                "mask": np.zeros(n, np.uint8), "owner": -1}
+    cnt, gi = key_decode(gkey)
+    owner = next(r for r in range(world) if shard_range(H, r, world)[0] <= gi < shard_range(H, r, world)[1])
+    payload = torch.zeros(12 + n, dtype=torch.float64)
+    if rank == owner:
+        payload[:9] = torch.from_numpy(np.asarray(local["R"], dtype=np.float64).reshape(9))
+        payload[9:12] = torch.from_numpy(np.asarray(local["t"], dtype=np.float64).reshape(3))
+        payload[12:] = torch.from_numpy(np.asarray(local["mask"], dtype=np.float64))
+    payload = payload.to(dev)
+    dist.broadcast(payload, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    payload = payload.cpu().numpy()
+    return {"best_idx": gi, "best_count": cnt, "R": payload[:9].reshape(3, 3), "t": payload[9:12].copy(),
+            "mask": payload[12:].astype(np.uint8), "owner": owner}
+
+
+def pnp_ransac_views_sharded(X_list, y_list, idx_list, thr2, group=None, compute=None, **kw) -> dict:
+    """View-sharded batched PnP-RANSAC (BASELINE config 2 at G > 1): views are independent, rank g takes a contiguous
+    block, no data-path collective; (best index, count, R, t) of all views are gathered on every rank."""
+    rank, world = _world(group)
+    V = len(X_list)
+    lo, hi = shard_range(V, rank, world)
+    compute = compute or _rt.pnp_ransac_batched
+    if hi > lo:
+        local = compute(X_list[lo:hi], y_list[lo:hi], idx_list[lo:hi], thr2, **kw)
+    else:
+        local = {"best_idx": np.zeros(0, np.int32), "best_count": np.zeros(0, np.int32), "R": np.zeros((0, 3, 3)),
+                 "t": np.zeros((0, 3))}
+    out = {"range": (lo, hi), "best_idx": np.asarray(local["best_idx"]), "best_count": np.asarray(local["best_count"]),
+           "R": np.asarray(local["R"]), "t": np.asarray(local["t"])}
+    if world == 1:
+        return out
+    import torch
+    dist = _dist()
+    dev = _device_for_collectives(group)
+    per = (V + world - 1) // world
+    buf = torch.full((per, 14), float("nan"), dtype=torch.float64)
+    n_loc = hi - lo
+    if n_loc:
+        buf[:n_loc, 0] = torch.from_numpy(out["best_idx"].astype(np.float64))
+        buf[:n_loc, 1] = torch.from_numpy(out["best_count"].astype(np.float64))
+        buf[:n_loc, 2:11] = torch.from_numpy(out["R"].reshape(n_loc, 9))
+        buf[:n_loc, 11:] = torch.from_numpy(out["t"].reshape(n_loc, 3))
+    buf = buf.to(dev)
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    best_idx = np.full(V, -1, dtype=np.int32)
+    best_count = np.zeros(V, dtype=np.int32)
+    R = np.full((V, 3, 3), np.nan)
+    t = np.full((V, 3), np.nan)
+    for r in range(world):
+        a, b = shard_range(V, r, world)
+        if b > a:
+            blk = gathered[r][:b - a].cpu().numpy()
+            best_idx[a:b] = blk[:, 0].astype(np.int32)
+            best_count[a:b] = blk[:, 1].astype(np.int32)
+            R[a:b] = blk[:, 2:11].reshape(-1, 3, 3)
+            t[a:b] = blk[:, 11:]
+    return {"range": (lo, hi), "best_idx": best_idx, "best_count": best_count, "R": R, "t": t}
