@@ -263,7 +263,9 @@ def run_ours(args) -> None:
         step_dev(s)
         step_host(s)
     torch.cuda.synchronize()
-    launches_per_call = rt.last_stats(device=local)["launches"]
+    launches_per_host_call = rt.last_stats(device=local)["launches"]      # last warm-up call was step_host
+    step_dev(0)
+    launches_per_call = rt.last_stats(device=local, stream=stream)["launches"]
 
     rt.set_option(1, 1, device=local)                                       # phase events on the launching stream
     ms_dev, win_dev = timed(step_dev, args.steps)
@@ -319,6 +321,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e, "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": P * (N * 32 + H * 32), "d2h_bytes_per_step": P * (4 + 4 + 72 + N)},
             "gpu_launches": int(launches_per_call) * args.steps,
+            "gpu_launches_e2e_region": int(launches_per_host_call) * args.steps,
             "roofline": {"bound": "fp32_ffma", "kernel": "score_packed<EpiPolicy>", "achieved": achieved_tflops,
                          "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": (achieved_tflops / fp32_peak_tflops) if achieved_tflops else None,
