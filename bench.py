@@ -565,6 +565,47 @@ def run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch) -> dict:
                                              "resolved": int((d_tw >= 0).sum().item()),
                                              "finite_points": int(torch.isfinite(d_tX).all(dim=1).sum().item())}
 
+    # gold-standard refinement (second half of fun.getFFromLabCode): the reference's own case (257 inliers of the noisy
+    # Dino pair (0,1); SciPy: 5482 residual evaluations, 267 s on this project's build box) and a config-5 sized batch
+    try:
+        gsg = np.load(os.path.join(ROOT, "tests", "golden", "gs_golden.npz"))
+        gpts = np.ascontiguousarray(np.hstack([gsg["in1"].T, gsg["in2"].T]))
+        rt.gold_standard([gpts], gsg["F0"][None])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            gres = rt.gold_standard([gpts], gsg["F0"][None])
+        dt = (time.perf_counter() - t0) / 5
+        Pg, Ng = 16, 50000
+        big = []
+        for k in range(Pg):
+            Xs = np.column_stack([rng.uniform(-0.04, 0.04, Ng), rng.uniform(-0.07, 0.02, Ng), rng.uniform(-0.7, -0.56, Ng),
+                                  np.ones(Ng)])
+            a, b = Xs @ Ps[k].T, Xs @ Ps[k + 1].T
+            big.append(np.hstack([a[:, :2] / a[:, 2:], b[:, :2] / b[:, 2:]]) + rng.normal(0, 0.5, (Ng, 4)))
+        d_gp = torch.from_numpy(np.concatenate(big)).to(dev)
+        d_gF = torch.from_numpy(np.stack([Fs[k] for k in range(Pg)])).to(dev)
+        d_gout = torch.empty((Pg, 9), dtype=torch.float64, device=dev)
+        d_gcost = torch.empty(Pg, dtype=torch.float64, device=dev)
+        d_git = torch.empty(2 * Pg, dtype=torch.int32, device=dev)
+        goff = (np.arange(Pg + 1, dtype=np.int32) * Ng)
+
+        def gcall():
+            cabi.check(lib.rg_gold_standard_dev(vp(ctx), vp(stream), Pg, vp(d_gp.data_ptr()), goff.ctypes.data_as(pi32),
+                                                vp(d_gF.data_ptr()), None, 50, 1e-12, vp(d_gout.data_ptr()),
+                                                vp(d_gcost.data_ptr()), vp(d_git.data_ptr()), vp(d_git[Pg:].data_ptr()), None))
+        msg = ev_time(gcall, 3)
+        out["gold_standard"] = {
+            "dino_noisy_pair_257_inliers": {"host_call_ms": dt * 1e3, "cost": float(gres["cost"][0]),
+                                            "iters": int(gres["iters"][0]), "status": int(gres["status"][0]),
+                                            "reference_scipy": {"cost": float(gsg["scipy_cost"]), "nfev": int(gsg["scipy_nfev"]),
+                                                                "seconds_on_build_box": 267}},
+            "batch_16_pairs_x_50000": {"ms": msg, "points_per_s": Pg * Ng / (msg * 1e-3),
+                                       "iters": [int(v) for v in d_git[:Pg].cpu().numpy()[:4]],
+                                       "status": [int(v) for v in d_git[Pg:].cpu().numpy()[:4]],
+                                       "cost_per_point": float(d_gcost.mean().item()) / Ng}}
+    except Exception as e:
+        out["gold_standard"] = {"error": repr(e)}
+
     # 2D<->3D match loop of Tables.addNewView: 20 000 queries against 20 000 observations, 2/3 of them present
     M = Nq = 20000
     obs = np.column_stack([rng.uniform(-0.1, 0.1, (M, 2)), np.ones(M)])

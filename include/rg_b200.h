@@ -161,6 +161,28 @@ int rg_two_view_init_host(void* ctx, void* stream, int P, const double* pts64, c
 int rg_two_view_init_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
                          const double* F_dev, const double* K9_host, const unsigned char* mask_dev, double* Rt_dev,
                          int32_t* which_dev, double* X_dev);
+/* ---- gold-standard refinement ------------------------------------------------------ */
+/* The second half of fun.getFFromLabCode (fun.py:342-369) for P image pairs in one call, entirely on the device:
+ * cameras from F (lab3.fmatrix_cameras, lab3.py:353-380), optimal triangulation of the inliers (fun.py:352), then the
+ * minimisation of the cost of lab3.fmatrix_residuals_gs (lab3.py:230-266) over C1 (3x4) and the 3-D points, and
+ * F_gold = lab3.fmatrix_from_cameras(C1, [I|0]) (fun.py:368).  The reference hands that cost to
+ * scipy.optimize.least_squares (trust-region reflective, finite-difference Jacobian: minutes, and it stops on ftol before
+ * the minimum); here it is Levenberg-Marquardt with the Schur complement of the point blocks and converges to the
+ * minimum of the SAME cost — F_gold therefore differs from the reference's by what its early stop leaves.
+ * pts64: (pair_off[P], 4) pixels; F0: (P, 3, 3) e.g. best_F of rg_f_ransac; mask (optional): 0 = not an inlier.
+ * Outputs: F_gold (P, 3, 3); cost (P, optional) = 0.5 * sum of squared residuals at the solution (SciPy's `cost`);
+ * iters (P, optional); status (P, optional): 1 = F0 not finite, 2 = converged (relative decrease <= ftol), 3 = no
+ * further descent, 4 = max_iter reached; X (pair_off[P], 3, optional) = refined points (NaN for masked-out ones). */
+int rg_gold_standard_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const double* F0,
+                          const unsigned char* mask, int max_iter, double ftol, double* F_gold, double* cost, int32_t* iters,
+                          int32_t* status, double* X);
+int rg_gold_standard_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                         const double* F0_dev, const unsigned char* mask_dev, int max_iter, double ftol, double* F_gold_dev,
+                         double* cost_dev, int32_t* iters_dev, int32_t* status_dev, double* X_dev);
+/* lab3.fmatrix_residuals_gs(params, pl, pr) (lab3.py:230-266): params = [C1.ravel() (12), X.T.ravel() (3N)], pl / pr (2, N)
+ * row-major; out (4N) = leftx, lefty, rightx, righty */
+int rg_fmatrix_residuals_gs_host(void* ctx, void* stream, int N, const double* params, const double* pl, const double* pr,
+                                 double* out);
 /* fun.camera_resectioning (fun.py:260-283, fun.specRQ fun.py:174-184) for V cameras: C (V,3,4) -> K (V,3,3) upper
  * triangular with positive diagonal and K[2][2] = 1, R (V,3,3), t (V,3); signs follow LAPACK's RQ as the reference's do */
 int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C, double* K, double* R, double* t);

@@ -10,6 +10,9 @@ What is recorded
   f_path_golden.npz  outputs of lab3.fmatrix_stls, lab3.fmatrix_residuals, the fun.py:303-328 loop replayed with the
                      real lab3 functions on seeded np.random.choice draws, and fun.getFFromLabCode itself (seeded)
   pnp_golden.npz     fun.camera_resectioning(newPs[i]) = ground-truth (K, R, t) of the exact synthetic Dino cameras
+  gs_golden.npz      the gold-standard stage of fun.getFFromLabCode (fun.py:342-369) replayed with the reference's functions
+                     on the RANSAC winner / inliers of the noisy pair (0,1): lab3.fmatrix_cameras, triangulate_optimal,
+                     scipy least_squares on lab3.fmatrix_residuals_gs (cost, nfev, status, F_gold), residual vectors
   geom_golden.npz    lab3.triangulate_optimal / triangulate_linear per correspondence (clean, noisy and gross-outlier
                      points of pair (0,1)) and fun.relative_camera_pose on all 35 consecutive clean pairs
 """
@@ -145,6 +148,21 @@ def main() -> None:
     for k, v in rel.items():
         gg["rel_" + k] = np.stack(v)
     np.savez_compressed(os.path.join(OUT, "geom_golden.npz"), **gg)
+    # ---- gold-standard stage: the reference's SciPy refinement, with its own stopping point ----
+    from scipy.optimize import least_squares
+    gs = {}
+    sel = np.flatnonzero(mask)
+    in1, in2 = p1[:, sel], p2[:, sel]
+    C1g, C2g = lab3.fmatrix_cameras(F_RANSAC)
+    Xg = np.vstack([lab3.triangulate_optimal(C1g, C2g, a_, b_) for a_, b_ in zip(in1.T, in2.T)]).T
+    par0 = np.hstack((C1g.ravel(), Xg.T.ravel()))
+    sol = least_squares(lab3.fmatrix_residuals_gs, par0, xtol=2.22e-14, tr_solver='lsmr', args=(in1, in2))
+    gs["F0"], gs["in1"], gs["in2"], gs["params0"] = F_RANSAC, in1, in2, par0
+    gs["resid0"] = lab3.fmatrix_residuals_gs(par0, in1, in2)
+    gs["scipy_cost"], gs["scipy_nfev"], gs["scipy_status"] = sol.cost, sol.nfev, sol.status
+    gs["scipy_params"] = sol.x
+    gs["F_gold"] = lab3.fmatrix_from_cameras(sol.x[:12].reshape(3, 4), C2g)
+    np.savez_compressed(os.path.join(OUT, "gs_golden.npz"), **gs)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

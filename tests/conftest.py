@@ -55,6 +55,11 @@ def pnp_golden():
 
 
 @pytest.fixture(scope="session")
+def gs_golden():
+    return _load("gs_golden.npz")
+
+
+@pytest.fixture(scope="session")
 def geom_golden():
     return _load("geom_golden.npz")
 

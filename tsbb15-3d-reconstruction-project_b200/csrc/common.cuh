@@ -160,6 +160,7 @@ struct Ctx {
     Buffer pose64, pose32, X32;                    // PnP path
     Buffer geom;                                   // two-view geometry: PairGeom table + CSR offsets
     Buffer geom_ws;                                // two-view initialisation: normalised points, cameras, picks
+    Buffer gs_ws;                                  // gold-standard refinement: per-pair state, sums, cameras, points
     // pinned host staging for the small per-call tables and the statistics read-back
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage

@@ -104,7 +104,7 @@ int rg_shutdown(void* ctx) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->bitmap,
-                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->d_out_a, &c->d_out_b,
+                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->d_out_a, &c->d_out_b,
                       &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
         release(*b);
     release_pinned(c->h_stage);

@@ -4,4 +4,5 @@
 #include "f_api.cu"
 #include "pnp_api.cu"
 #include "geom_api.cu"
+#include "gs_api.cu"
 #include "microbench.cu"

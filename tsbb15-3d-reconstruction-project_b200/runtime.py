@@ -407,6 +407,55 @@ def two_view_init(pts_list, F, K, masks=None, device=None, stream=0) -> dict:
             "X": [X[off[p]:off[p + 1]] for p in range(P)]}
 
 
+def gold_standard(pts_list, F0, masks=None, max_iter=50, ftol=1e-12, want_points=False, device=None, stream=0) -> dict:
+    """Gold-standard refinement (second half of fun.getFFromLabCode, fun.py:342-369) of P pairs in ONE library call.
+    pts_list[p]: (N_p, 4) pixel rows; F0: (P, 3, 3); masks[p] optional inlier masks.
+    Returns dict(F (P,3,3), cost (P,), iters (P,), status (P,), X list when want_points)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    P = len(pts_list)
+    F0 = _f64(F0).reshape(-1, 3, 3)
+    if F0.shape[0] != P:
+        raise ValueError("F0 must be (P, 3, 3)")
+    pts = [_f64(p).reshape(-1, 4) for p in pts_list]
+    off = np.zeros(P + 1, dtype=np.int32)
+    for p in range(P):
+        off[p + 1] = off[p] + pts[p].shape[0]
+    N = int(off[-1])
+    allp = np.ascontiguousarray(np.concatenate(pts)) if P else np.zeros((0, 4))
+    mask = None
+    if masks is not None:
+        if len(masks) != P or any(len(m) != pts[p].shape[0] for p, m in enumerate(masks)):
+            raise ValueError("masks must match pts_list")
+        mask = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.uint8) for m in masks])) if P else None
+    F = np.full((P, 3, 3), np.nan)
+    cost = np.full(P, np.nan)
+    iters = np.zeros(P, dtype=np.int32)
+    status = np.zeros(P, dtype=np.int32)
+    X = np.full((N, 3), np.nan) if want_points else None
+    cabi.check(lib.rg_gold_standard_host(_vp(ctx), _vp(stream), P, _vp(cabi.ptr(allp)), off.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         _vp(cabi.ptr(F0)), _vp(cabi.ptr(mask)), int(max_iter), float(ftol), _vp(cabi.ptr(F)),
+                                         _vp(cabi.ptr(cost)), _vp(cabi.ptr(iters)), _vp(cabi.ptr(status)), _vp(cabi.ptr(X))))
+    out = {"F": F, "cost": cost, "iters": iters, "status": status}
+    if want_points:
+        out["X"] = [X[off[p]:off[p + 1]] for p in range(P)]
+    return out
+
+
+def fmatrix_residuals_gs(params, pl, pr, device=None, stream=0):
+    """lab3.fmatrix_residuals_gs on the GPU: params (12 + 3N,), pl / pr (2, N) -> (4N,)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    params = _f64(params).ravel()
+    pl = _f64(pl)
+    pr = _f64(pr)
+    N = pl.shape[1]
+    out = np.empty(4 * N)
+    cabi.check(lib.rg_fmatrix_residuals_gs_host(_vp(ctx), _vp(stream), N, _vp(cabi.ptr(params)), _vp(cabi.ptr(pl)),
+                                                _vp(cabi.ptr(pr)), _vp(cabi.ptr(out))))
+    return out
+
+
 def camera_resectioning(Cs, device=None, stream=0):
     """fun.camera_resectioning for V cameras: (V, 3, 4) -> K (V,3,3), R (V,3,3), t (V,3)."""
     lib = cabi.load_library()
