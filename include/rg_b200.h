@@ -43,7 +43,11 @@ int rg_shutdown(void* ctx);
 int rg_device_sm_count(void* ctx);
 /* option 1 = phase profiling on/off: CUDA events on the launching stream around the phases of every RANSAC call
  * option 2 = number of sub-batches of rg_f_ransac_host (0 = automatic, 1 = monolithic, up to 8): the upload of sub-batch
- *            k+1 runs on a second stream while sub-batch k is scored; results do not depend on it */
+ *            k+1 runs on a second stream while sub-batch k is scored; results do not depend on it
+ * option 3 = CTAs in the thread-block cluster that factorises the bundle-adjustment camera system (0 = default 8; 1, 2, 4,
+ *            8); results do not depend on it
+ * option 4 = 1: factorise that system in global memory / L2 even when it fits in the cluster's distributed shared memory
+ *            (the default picks shared memory when it fits); results do not depend on it */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the calls since the last read
  * (at most 256 calls are remembered); synchronises `stream` */
@@ -183,6 +187,27 @@ int rg_gold_standard_dev(void* ctx, void* stream, int P, const double* pts64_dev
  * row-major; out (4N) = leftx, lefty, rightx, righty */
 int rg_fmatrix_residuals_gs_host(void* ctx, void* stream, int N, const double* params, const double* pl, const double* pr,
                                  double* out);
+/* ---- bundle adjustment (multi-view half) -------------------------------------------------- */
+/* The minimisation of tables.Tables.BundleAdjustment2 (tables.py:260-333): cost = 0.5 * sum over the observation table of
+ * (u - c1.x/c3.x)^2 + (v - c2.x/c3.x)^2 (EpsilonBA, tables.py:266-296) over all 12 entries of every view's 3x4 matrix except
+ * the first n_fixed views (the reference clears the first view's Jacobian columns, tables.py:376: n_fixed = 1) and all 3-D
+ * points.  The reference calls scipy.optimize.least_squares (trf, x_scale='jac', ftol=1e-4, finite differences); here it is
+ * Levenberg-Marquardt with the Schur complement of the point blocks and a dense Cholesky of the reduced camera system on
+ * one thread-block cluster, converging on the relative cost decrease ftol — same cost function, not the same iterates
+ * (DESIGN.md section 4.6).  cams (n_views, 3, 4) and pts (n_points, 3) are refined IN PLACE; uv (n_obs, 2) observed
+ * C-normalised image points; cam_idx / pt_idx (n_obs) HOST arrays in both variants.  n_views - n_fixed <= 170.
+ * Outputs (optional scalars): cost at the solution, iterations, status: 2 = converged, 3 = no further descent,
+ * 4 = max_iter reached. */
+int rg_bundle_adjust_host(void* ctx, void* stream, int n_views, int n_points, int n_obs, double* cams, double* pts,
+                          const double* uv, const int32_t* cam_idx, const int32_t* pt_idx, int n_fixed, int max_iter, double ftol,
+                          double* cost, int32_t* iters, int32_t* status);
+int rg_bundle_adjust_dev(void* ctx, void* stream, int n_views, int n_points, int n_obs, double* cams_dev, double* pts_dev,
+                         const double* uv_dev, const int32_t* cam_idx_host, const int32_t* pt_idx_host, int n_fixed, int max_iter,
+                         double ftol, double* cost_dev, int32_t* iters_dev, int32_t* status_dev);
+/* EpsilonBA(x0, u, v, table) (tables.py:266-296): x = [all camera matrices raveled (n_views x 12), all points (n_points x 3)]
+ * (tables.py:315, fun.reshapeToCamera3DPoints2 fun.py:282-289); out (2 * n_obs) = interleaved u / v residuals */
+int rg_ba_residuals_host(void* ctx, void* stream, int n_views, int n_points, int n_obs, const double* x, const double* u,
+                         const double* v, const int32_t* cam_idx, const int32_t* pt_idx, double* out);
 /* fun.camera_resectioning (fun.py:260-283, fun.specRQ fun.py:174-184) for V cameras: C (V,3,4) -> K (V,3,3) upper
  * triangular with positive diagonal and K[2][2] = 1, R (V,3,3), t (V,3); signs follow LAPACK's RQ as the reference's do */
 int rg_camera_resectioning_host(void* ctx, void* stream, int V, const double* C, double* K, double* R, double* t);

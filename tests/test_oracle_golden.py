@@ -161,3 +161,56 @@ def test_gs_dense_lm_beats_the_reference_stopping_point(gs_golden):
     assert c < float(g["scipy_cost"]) and it < 40
     assert abs(c - ogs.cost(C1, X, g["in1"], g["in2"])) < 1e-12 * c
     assert _nerr(F, g["F_gold"]) < 2e-3
+
+
+# ---- bundle adjustment (multi-view half) -------------------------------------------------
+@pytest.fixture(scope="module")
+def ba_golden():
+    from conftest import _load
+    return _load("ba_golden.npz")
+
+
+@pytest.mark.parametrize("nv", [3, 8, 36])
+def test_ba_oracle_residuals_and_mask_match_reference_golden(ba_golden, dino, nv):
+    from oracle import ba_path as oba
+    g, p = ba_golden, f"v{nv}_"
+    cams, pts, uv, ci, pi = g[p + "cams0"], g[p + "pts0"], g[p + "uv"], g[p + "cam_idx"], g[p + "pt_idx"]
+    # the scene builder is deterministic: the committed problem is what dino_scene makes from the Dino data
+    c2, p2, uv2, ci2, pi2 = oba.dino_scene(dino["Ps"], dino["x2d"], dino["X3d"], nv)
+    assert np.abs(c2 - cams).max() < 1e-9 and np.abs(p2 - pts).max() < 1e-12 and np.abs(uv2 - uv).max() < 1e-12
+    assert np.array_equal(ci2, ci) and np.array_equal(pi2, pi)
+    # EpsilonBA (tables.py:266-296) at the start and at SciPy's solution
+    r0 = oba.residuals(oba.pack(cams, pts), uv[:, 0], uv[:, 1], ci, pi, len(cams), len(pts))
+    assert r0.shape == g[p + "resid0"].shape and np.abs(r0 - g[p + "resid0"]).max() < 1e-13
+    r1 = oba.residuals(g[p + "scipy_x"], uv[:, 0], uv[:, 1], ci, pi, len(cams), len(pts))
+    assert abs(0.5 * r1 @ r1 - float(g[p + "scipy_cost"])) < 1e-12 * float(g[p + "scipy_cost"])
+    # what the reference wrote back into its tables is SciPy's solution (updateCameras3Dpoints2, tables.py:384-390)
+    C1, X1 = oba.unpack(g[p + "scipy_x"], len(cams), len(pts))
+    assert np.array_equal(C1, g[p + "cams1"]) and np.array_equal(X1, g[p + "pts1"])
+    assert np.array_equal(C1[0], cams[0])                      # first view fixed by the sparsity mask
+    # sparsity_mask (tables.py:346-380)
+    m = oba.sparsity_mask(ci, pi, len(cams), len(pts)).tocsr()
+    assert m.nnz == int(g[p + "mask_nnz"])
+    assert np.array_equal(np.asarray(m.sum(axis=1)).ravel(), g[p + "mask_rowsum"])
+    assert np.array_equal(np.asarray(m.sum(axis=0)).ravel(), g[p + "mask_colsum"])
+
+
+def test_ba_oracle_scipy_call_reproduces_the_reference_run(ba_golden):
+    """Same SciPy call on the vectorised residual function: same stopping point as the reference's Python-loop residuals
+    up to what the rounding of the residuals does to SciPy's finite-difference path (6e-5 of the cost, measured)."""
+    from oracle import ba_path as oba
+    g, p = ba_golden, "v3_"
+    C, X, sol = oba.bundle_adjust_scipy(g[p + "cams0"], g[p + "pts0"], g[p + "uv"], g[p + "cam_idx"], g[p + "pt_idx"])
+    assert sol.status == int(g[p + "scipy_status"])
+    assert sol.nfev == int(g[p + "scipy_nfev"])
+    assert abs(sol.cost - float(g[p + "scipy_cost"])) < 1e-3 * float(g[p + "scipy_cost"])
+
+
+@pytest.mark.parametrize("nv", [3, 8])
+def test_ba_lm_iteration_not_above_the_reference_stopping_point(ba_golden, nv):
+    from oracle import ba_path as oba
+    g, p = ba_golden, f"v{nv}_"
+    cams, pts, uv, ci, pi = g[p + "cams0"], g[p + "pts0"], g[p + "uv"], g[p + "cam_idx"], g[p + "pt_idx"]
+    C, X, c, it, st = oba.bundle_adjust_lm(cams, pts, uv, ci, pi, ftol=1e-4)
+    assert st == 2 and c <= float(g[p + "scipy_cost"]) and np.array_equal(C[0], cams[0])
+    assert abs(oba.cost(C, X, uv, ci, pi) - c) < 1e-12 * c

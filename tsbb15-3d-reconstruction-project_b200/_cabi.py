@@ -61,6 +61,9 @@ SIGNATURES = {
     "rg_gold_standard_host": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "rg_gold_standard_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "rg_fmatrix_residuals_gs_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rg_bundle_adjust_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _pi, _pi, _i, _i, _d, _vp, _vp, _vp]),
+    "rg_bundle_adjust_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _pi, _pi, _i, _i, _d, _vp, _vp, _vp]),
+    "rg_ba_residuals_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _pi, _pi, _vp]),
     "rg_two_view_init_host": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_two_view_init_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_match_first_within_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp]),

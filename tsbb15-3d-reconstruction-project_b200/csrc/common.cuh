@@ -161,6 +161,10 @@ struct Ctx {
     Buffer geom;                                   // two-view geometry: PairGeom table + CSR offsets
     Buffer geom_ws;                                // two-view initialisation: normalised points, cameras, picks
     Buffer gs_ws;                                  // gold-standard refinement: per-pair state, sums, cameras, points
+    Buffer ba_ws;                                  // bundle adjustment: state, step, trial points, point blocks, camera system
+    int opt_ba_cluster = 0;                        // option 3: CTAs in the cluster of the camera-system factorisation (0 = 8)
+    int opt_ba_l2 = 0;                             // option 4: 1 = keep the camera system in L2 (ba_solve) even when it fits in DSMEM
+    bool ba_attr_set = false;                      // dynamic shared memory limit of ba_solve raised on this device
     // pinned host staging for the small per-call tables and the statistics read-back
     Buffer h_stage, h_stats;
     cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage

@@ -104,7 +104,7 @@ int rg_shutdown(void* ctx) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->bitmap,
-                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->d_out_a, &c->d_out_b,
+                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->ba_ws, &c->d_out_a, &c->d_out_b,
                       &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
         release(*b);
     release_pinned(c->h_stage);
@@ -126,6 +126,8 @@ int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 
 // option 1: phase profiling (CUDA events on the launching stream around the phases of every RANSAC call)
 // option 2: number of sub-batches of rg_f_ransac_host (0 = automatic): uploads overlap the previous sub-batch's kernels
+// option 3: thread-block cluster size of the bundle-adjustment Cholesky (0 = default 8; 1, 2, 4, 8)
+// option 4: 1 = factorise the bundle-adjustment camera system in L2 even when it fits in distributed shared memory
 int rg_set_option(void* ctx, int option, long long value) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
@@ -145,6 +147,18 @@ int rg_set_option(void* ctx, int option, long long value) {
             return RG_ERR_ARG;
         }
         c->opt_host_slices = (int)value;
+        return RG_OK;
+    }
+    if (option == 3) {
+        if (!(value == 0 || value == 1 || value == 2 || value == 4 || value == 8)) {
+            set_error("invalid argument: option 3 (cluster size of the bundle-adjustment factorisation) must be 0, 1, 2, 4 or 8");
+            return RG_ERR_ARG;
+        }
+        c->opt_ba_cluster = (int)value;
+        return RG_OK;
+    }
+    if (option == 4) {
+        c->opt_ba_l2 = value != 0;
         return RG_OK;
     }
     set_error("invalid argument: unknown option %d", option);

@@ -5,4 +5,5 @@
 #include "pnp_api.cu"
 #include "geom_api.cu"
 #include "gs_api.cu"
+#include "ba_api.cu"
 #include "microbench.cu"

@@ -49,6 +49,12 @@ def camera_resectioning(C):
     return K[0], R[0], t[0]
 
 
+def reshapeToCamera3DPoints2(x0, n_C, n_P):
+    """fun.py:282-289: the bundle-adjustment parameter vector back to (n_C, 3, 4) cameras and (n_P, 3) points."""
+    x0 = np.asarray(x0)
+    return np.reshape(x0[:n_C * 12], [n_C, 3, 4]), np.reshape(x0[n_C * 12:], [n_P, 3])
+
+
 def getEAndK(C, F):
     """E = K^T F K with K taken from the LAST camera of C (1, n, 3, 4), as the reference does (fun.py:91-102)."""
     C = np.asarray(C, dtype=np.float64)

@@ -456,6 +456,48 @@ def fmatrix_residuals_gs(params, pl, pr, device=None, stream=0):
     return out
 
 
+def bundle_adjust(cams, pts, uv, cam_idx, pt_idx, n_fixed=1, max_iter=50, ftol=1e-4, device=None, stream=0) -> dict:
+    """Bundle adjustment (the minimisation of tables.Tables.BundleAdjustment2, tables.py:260-333) in ONE library call.
+    cams (V, 3, 4) camera matrices, pts (P, 3), uv (O, 2) observed C-normalised image points, cam_idx / pt_idx (O,) the
+    view and point of every observation; the first n_fixed views are held fixed (the reference fixes view 0).
+    Returns dict(cams, pts, cost = 0.5 * sum r^2, iters, status: 2 converged, 3 no further descent, 4 max_iter)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    cams = np.array(cams, dtype=np.float64).reshape(-1, 3, 4)
+    pts = np.array(pts, dtype=np.float64).reshape(-1, 3)
+    uv = _f64(uv).reshape(-1, 2)
+    ci, ci_p = cabi.as_i32(np.asarray(cam_idx).ravel())
+    pi, pi_p = cabi.as_i32(np.asarray(pt_idx).ravel())
+    if not (ci.shape[0] == pi.shape[0] == uv.shape[0]):
+        raise ValueError("uv, cam_idx and pt_idx must have one row per observation")
+    cost = np.full(1, np.nan)
+    it_st = np.zeros(2, dtype=np.int32)
+    cabi.check(lib.rg_bundle_adjust_host(_vp(ctx), _vp(stream), cams.shape[0], pts.shape[0], uv.shape[0], _vp(cabi.ptr(cams)),
+                                         _vp(cabi.ptr(pts)), _vp(cabi.ptr(uv)), ci_p, pi_p, int(n_fixed), int(max_iter), float(ftol),
+                                         _vp(cabi.ptr(cost)), _vp(it_st.ctypes.data), _vp(it_st.ctypes.data + 4)))
+    return {"cams": cams, "pts": pts, "cost": float(cost[0]), "iters": int(it_st[0]), "status": int(it_st[1])}
+
+
+def ba_residuals(x, u, v, cam_idx, pt_idx, n_C, n_P, device=None, stream=0) -> np.ndarray:
+    """EpsilonBA of tables.Tables.BundleAdjustment2 (tables.py:266-296) on the GPU: x = [cameras (n_C x 12), points (n_P x 3)]
+    -> interleaved residuals (2 * n_obs,)."""
+    lib = cabi.load_library()
+    ctx = cabi.context(device)
+    x = _f64(x).ravel()
+    if x.shape[0] != 12 * n_C + 3 * n_P:
+        raise ValueError("parameter vector must hold n_C * 12 + n_P * 3 values")
+    u = _f64(u).ravel()
+    v = _f64(v).ravel()
+    ci, ci_p = cabi.as_i32(np.asarray(cam_idx).ravel())
+    pi, pi_p = cabi.as_i32(np.asarray(pt_idx).ravel())
+    if not (u.shape[0] == v.shape[0] == ci.shape[0] == pi.shape[0]):
+        raise ValueError("u, v, cam_idx and pt_idx must have one entry per observation")
+    out = np.empty(2 * u.shape[0])
+    cabi.check(lib.rg_ba_residuals_host(_vp(ctx), _vp(stream), int(n_C), int(n_P), u.shape[0], _vp(cabi.ptr(x)), _vp(cabi.ptr(u)),
+                                        _vp(cabi.ptr(v)), ci_p, pi_p, _vp(cabi.ptr(out))))
+    return out
+
+
 def camera_resectioning(Cs, device=None, stream=0):
     """fun.camera_resectioning for V cameras: (V, 3, 4) -> K (V,3,3), R (V,3,3), t (V,3)."""
     lib = cabi.load_library()

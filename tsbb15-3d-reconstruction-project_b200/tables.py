@@ -14,7 +14,14 @@ What runs on the GPU
     (DESIGN.md, "parity unpinned at the OpenCV boundary");
   * triangulation of the new points: one batched ``lab3.triangulate_optimal_batch`` call instead of a Python loop.
 
-Out of scope: bundle adjustment (tables.py:75-102, 260-380), plotting, colours/normals export.
+  * bundle adjustment: ``BundleAdjustment2`` (tables.py:260-333) gathers the tables into
+    arrays as the reference does and minimises the same cost (EpsilonBA, tables.py:266-296, first view fixed as in
+    sparsity_mask tables.py:376) in one ``runtime.bundle_adjust`` call — Levenberg-Marquardt with the Schur complement
+    on the device instead of SciPy's finite-difference trust-region solver (same cost, not the same iterates);
+    ``updateCameras3Dpoints2`` (tables.py:384-390) and ``sparsity_mask`` (tables.py:346-380) keep their behaviour.
+
+Out of scope: the dead first version ``BundleAdjustment`` (tables.py:75-102, never called, its cost
+is a scalar that least_squares cannot use), plotting, colours/normals export.
 The reference's constructor loads ``../images/*.ppm`` (fun.getImages, absent from the repository); here ``images`` is an
 optional constructor argument and observation colours are ``None`` without it.
 """
@@ -66,6 +73,51 @@ class Tables:
         Rs = np.stack([v.camera_pose.R for v in self.T_views]) if self.T_views.size else np.zeros([0, 3, 3])
         ts = np.stack([v.camera_pose.t for v in self.T_views]) if self.T_views.size else np.zeros([0, 3])
         return Rs, ts
+
+    # ---- BA (tables.py:260-390) -------------------------------------------------------------------------------
+    def observationArrays(self):
+        """The observation table as arrays, in table order: uv (O, 2), view index (O,), point index (O,)."""
+        uv = np.array([o.image_coordinates[:2] for o in self.T_obs], dtype=np.float64).reshape(-1, 2)
+        cam_idx = np.array([o.view_index for o in self.T_obs], dtype=np.int32)
+        pt_idx = np.array([o.point_3D_index for o in self.T_obs], dtype=np.int32)
+        return uv, cam_idx, pt_idx
+
+    def BundleAdjustment2(self, max_iter=50, ftol=1e-4):
+        """tables.py:298-333: all camera matrices (first view fixed) and all points refined against every observation.
+        ftol is the reference's (tables.py:317); here it bounds the relative cost decrease of an accepted LM step.
+        Returns the solver record (cost, iters, status) — the reference returns None."""
+        Rktk = np.empty((len(self.T_views), 3, 4))
+        xj = np.empty((len(self.T_points), 3))
+        for i, o in enumerate(self.T_views):
+            Rktk[i] = o.camera_pose.GetCameraMatrix()
+        for i, o in enumerate(self.T_points):
+            xj[i] = o.point
+        uv, cam_idx, pt_idx = self.observationArrays()
+        res = _rt.bundle_adjust(Rktk, xj, uv, cam_idx, pt_idx, n_fixed=1, max_iter=max_iter, ftol=ftol)
+        self.updateCameras3Dpoints2(res["cams"], res["pts"])
+        return {k: res[k] for k in ("cost", "iters", "status")}
+
+    def sparsity_mask(self):
+        """tables.py:346-380: the Jacobian sparsity pattern the reference gives SciPy (first view's columns cleared)."""
+        from scipy.sparse import lil_matrix
+        _, camera_idx, point_idx = self.observationArrays()
+        n_obs = len(self.T_obs)
+        A = lil_matrix((n_obs * 2, len(self.T_views) * 12 + len(self.T_points) * 3), dtype='int')
+        i = np.arange(n_obs)
+        for s in range(12):
+            A[2 * i, camera_idx * 12 + s] = 1
+            A[2 * i + 1, camera_idx * 12 + s] = 1
+        for s in range(3):
+            A[2 * i, len(self.T_views) * 12 + point_idx * 3 + s] = 1
+            A[2 * i + 1, len(self.T_views) * 12 + point_idx * 3 + s] = 1
+        A[:, 0:12] = 0
+        return A
+
+    def updateCameras3Dpoints2(self, new_pose, new_points):
+        for i, o in enumerate(self.T_views):
+            o.camera_pose = CameraPose(new_pose[i, :3, :3], new_pose[i, :, 3])
+        for i, o in enumerate(self.T_points):
+            o.point = new_points[i]
 
     # ---- EXT2 + EXT3 (tables.py:104-159) ----------------------------------------------------------------------
     def matchLastView(self, y1_hom):
