@@ -606,6 +606,59 @@ def run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch) -> dict:
     except Exception as e:
         out["gold_standard"] = {"error": repr(e)}
 
+    # bundle adjustment (Tables.BundleAdjustment2): the 36-view Dino scene the golden file holds (reference: SciPy trf with
+    # a finite-difference Jacobian, 14 residual sweeps, ~8 s) and the oracle's SciPy call timed here on the 8-view scene
+    try:
+        from oracle import ba_path as oba
+        bag = np.load(os.path.join(ROOT, "tests", "golden", "ba_golden.npz"))
+        bsc = lambda nv: tuple(bag[f"v{nv}_" + k] for k in ("cams0", "pts0", "uv", "cam_idx", "pt_idx"))
+        b36 = bsc(36)
+        rt.bundle_adjust(*b36, ftol=1e-4)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            bres = rt.bundle_adjust(*b36, ftol=1e-4)
+        dt = (time.perf_counter() - t0) / 5
+        d_bc = torch.from_numpy(b36[0].copy()).to(dev)
+        d_bp = torch.from_numpy(b36[1].copy()).to(dev)
+        d_buv = torch.from_numpy(b36[2].copy()).to(dev)
+        d_bout = torch.empty(1, dtype=torch.float64, device=dev)
+        d_bit = torch.empty(2, dtype=torch.int32, device=dev)
+        bci = np.ascontiguousarray(b36[3], dtype=np.int32)
+        bpi = np.ascontiguousarray(b36[4], dtype=np.int32)
+        n_it = 8                                     # fixed number of LM iterations from the same start: per-iteration device time
+
+        def bcall():
+            d_bc.copy_(torch.from_numpy(b36[0]), non_blocking=False)
+            d_bp.copy_(torch.from_numpy(b36[1]), non_blocking=False)
+            cabi.check(lib.rg_bundle_adjust_dev(vp(ctx), vp(stream), 36, b36[1].shape[0], b36[2].shape[0], vp(d_bc.data_ptr()),
+                                                vp(d_bp.data_ptr()), vp(d_buv.data_ptr()), bci.ctypes.data_as(pi32),
+                                                bpi.ctypes.data_as(pi32), 1, n_it, 0.0, vp(d_bout.data_ptr()),
+                                                vp(d_bit.data_ptr()), vp(d_bit[1:].data_ptr())))
+        msb = ev_time(bcall, 3)
+        b8 = bsc(8)
+        t0 = time.perf_counter()
+        _, _, sol8 = oba.bundle_adjust_scipy(*b8)
+        dt8 = time.perf_counter() - t0
+        r8 = rt.bundle_adjust(*b8, ftol=1e-4)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            r8 = rt.bundle_adjust(*b8, ftol=1e-4)
+        dt8g = (time.perf_counter() - t0) / 5
+        out["bundle_adjust"] = {
+            "dino_36_views_676_points_4165_obs": {
+                "host_call_ms": dt * 1e3, "cost": bres["cost"], "iters": bres["iters"], "status": bres["status"],
+                "device_ms_per_lm_iteration": msb / n_it,
+                "reference_scipy": {"cost": float(bag["v36_scipy_cost"]), "nfev": int(bag["v36_scipy_nfev"]),
+                                    "seconds_on_build_box": 8.1}},
+            "dino_8_views_113_points_560_obs": {
+                "host_call_ms": dt8g * 1e3, "cost": r8["cost"], "iters": r8["iters"],
+                "cpu_baseline": {"value": dt8 * 1e3, "unit": "ms per bundle adjustment", "cores": 1, "kind": "port",
+                                 "cost": float(sol8.cost), "nfev": int(sol8.nfev),
+                                 "sample": "the reference's SciPy call (tables.py:317) on the oracle's vectorised EpsilonBA, "
+                                           "whole problem"}}}
+    except Exception as e:
+        out["bundle_adjust"] = {"error": repr(e)}
+
     # 2D<->3D match loop of Tables.addNewView: 20 000 queries against 20 000 observations, 2/3 of them present
     M = Nq = 20000
     obs = np.column_stack([rng.uniform(-0.1, 0.1, (M, 2)), np.ones(M)])

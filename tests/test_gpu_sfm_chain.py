@@ -1,4 +1,4 @@
-"""The reference's incremental pipeline (main.py:34-128: INIT1-3, EXT1-5, without bundle adjustment) replayed on the
+"""The reference's incremental pipeline (main.py:34-128: INIT1-3, EXT1-5; the second test adds the BA step) replayed on the
 exact synthetic Dino tracks through the drop-in modules: F-RANSAC -> E -> relative pose -> triangulation -> for every
 further view the 2D<->3D match loop + PnP-RANSAC of Tables.addNewView + triangulation of the new points.  Everything
 numeric runs on the GPU; the data are exact, so every recovered pose must equal the ground-truth camera (expressed in
@@ -67,6 +67,51 @@ def test_main_py_chain_on_clean_dino(rg, dino, pnp_golden):
     assert d.max() < 1e-5 * np.abs(Xgt).max()
     Rs, ts = T.getCamerasForEvaluation()
     assert Rs.shape == (7, 3, 3) and ts.shape == (7, 3)
+
+
+def test_main_py_chain_with_bundle_adjustment(rg, dino, pnp_golden):
+    """main.py:95-128 in the reference's order — BundleAdjustment2, then addNewView / addNewPoints — on the exact Dino
+    tracks.  Without BA the chain drifts (1e-5, test above); with BA after every view the total reprojection cost of the
+    tables goes back to rounding level each time, and a perturbed reconstruction is pulled back onto the observations."""
+    from oracle import ba_path as oba
+    fun = rg.fun
+    Tables, CameraPose = rg.tables.Tables, rg.help_classes.CameraPose
+    y1, y2, _ = _pair(dino, 0, 1)
+    F = fun.getFFromLabCode(y1.T, y2.T, r=2000, seed=0, refine=False)
+    E, K = fun.getEAndK(dino["Ps"][None], F)
+    T = Tables()
+    T.K = K
+    y1h, y2h = fun.MakeHomogenous(K, y1), fun.MakeHomogenous(K, y2)
+    R, t = fun.relative_camera_pose(E, y1h[0, :2].T, y2h[0, :2].T)
+    C1, C2 = CameraPose(), CameraPose(R, t)
+    v1, v2 = T.addView(0, C1), T.addView(1, C2)
+    T.triangulateAndAddPoints(v1, v2, C1, C2, y1h, y2h)
+
+    def table_cost():
+        cams = np.stack([v.camera_pose.GetCameraMatrix() for v in T.T_views])
+        pts = np.stack([p.point for p in T.T_points])
+        uv, ci, pi = T.observationArrays()
+        return oba.cost(cams, pts, uv, ci, pi)
+
+    for i in range(1, 5):
+        before = table_cost()
+        info = T.BundleAdjustment2()                          # main.py:100
+        after = table_cost()
+        assert abs(after - info["cost"]) <= 1e-9 * max(after, 1e-30) + 1e-24
+        assert after <= before and after < 1e-18              # exact observations: the drift of the chain is removed
+        assert np.array_equal(T.T_views[0].camera_pose.GetCameraMatrix(), np.hstack([np.eye(3), np.zeros((3, 1))]))
+        a, b, _ = _pair(dino, i, i + 1)
+        ah, bh = fun.MakeHomogenous(K, a), fun.MakeHomogenous(K, b)
+        A1, A2 = T.addNewView(K, i + 1, ah, bh, a, b, r=256, reproj_px=1.5, seed=i)
+        T.addNewPoints(fun.MakeHomogenous(K, A1), fun.MakeHomogenous(K, A2), i, i + 1)
+    # a perturbed reconstruction (3-D points off by 1 % of the scene depth) is pulled back onto the exact observations
+    rng = np.random.default_rng(5)
+    scale = np.abs(np.stack([p.point for p in T.T_points])).max()
+    for p in T.T_points:
+        p.point = p.point + 0.01 * scale * rng.standard_normal(3)
+    c0 = table_cost()
+    info = T.BundleAdjustment2(max_iter=100, ftol=1e-12)
+    assert info["cost"] < 1e-10 * c0 and info["status"] in (2, 3)
 
 
 def test_match_last_view_equals_reference_loop(rg, dino, pnp_golden):
