@@ -84,7 +84,8 @@ def _inv_sym3(V):
 def bundle_adjust_lm(cams, pts, uv, cam_idx, pt_idx, n_fixed=1, max_iter=50, ftol=1e-12, lam=1e-3, trace=None):
     """Numpy version of the device algorithm (csrc/ba_kernels.cuh): Levenberg-Marquardt with Marquardt scaling over all
     12 entries of every non-fixed camera and all points; the 3x3 point blocks are eliminated (Schur complement), the
-    reduced camera system is solved by Cholesky; accept / reject with lambda /10, x10.
+    reduced camera system is solved by Cholesky; accept / reject with lambda /10, x10; converged when an accepted step
+    lowers the cost by no more than ftol * cost, or brings it to the rounding level of the observations.
     Returns cameras, points, cost, iterations, status (2 converged, 3 lambda overflow, 4 max_iter)."""
     C = np.array(cams, dtype=np.float64).reshape(-1, 3, 4)
     X = np.array(pts, dtype=np.float64).reshape(-1, 3)
@@ -94,6 +95,7 @@ def bundle_adjust_lm(cams, pts, uv, cam_idx, pt_idx, n_fixed=1, max_iter=50, fto
     n_C, n_P, n_O = len(C), len(X), len(uv)
     n_free = n_C - n_fixed
     c = cost(C, X, uv, cam_idx, pt_idx)
+    floor = 0.5 * float(np.sum(uv * uv)) * (64.0 * np.finfo(np.float64).eps) ** 2      # residuals = rounding noise of uv
     status, it = 4, 0
     if n_free <= 0 and n_P == 0:
         return C, X, c, 0, 2
@@ -160,7 +162,7 @@ def bundle_adjust_lm(cams, pts, uv, cam_idx, pt_idx, n_fixed=1, max_iter=50, fto
             trace.append(dict(it=it, lam=lam, cost=c, cost_trial=cn if ok else np.nan, ok=ok))
         if ok and cn < c:
             gain = c - cn
-            conv = gain <= ftol * c
+            conv = gain <= ftol * c or cn <= floor
             C, X, c = Cn, Xn, cn
             lam = max(lam * 0.1, 1e-15)
             if conv:

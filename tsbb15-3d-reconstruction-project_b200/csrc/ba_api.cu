@@ -70,7 +70,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     const int nparts = std::max(1, std::min(1024, ceil_div(std::max(nP, 1), kBaPointThreads)));
     const size_t s_elems = (size_t)(n + 1) * (size_t)std::max(n, 1);
     const size_t bytes = sizeof(BaState) + 64 + sizeof(double) * ((size_t)12 * std::max(nC, 1) + (size_t)3 * nP + (size_t)2 * nO +
-                                                                  (size_t)12 * nP + s_elems + (size_t)24 * (n + 1) + (size_t)n + (size_t)2 * nparts + 8) +
+                                                                  (size_t)12 * nP + s_elems + (size_t)24 * (n + 1) + (size_t)n + (size_t)3 * nparts + 8) +
                          sizeof(int) * (n_int + nparts + 8);
     if ((rc = ensure(c->ba_ws, bytes))) return rc;
     char* w = (char*)c->ba_ws.ptr;
@@ -84,6 +84,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     double* dinv = (double*)w;                     w += sizeof(double) * n;                 // reciprocal diagonal (L2 variant)
     double* cost_part = (double*)w;                w += sizeof(double) * nparts;
     double* trial_part = (double*)w;               w += sizeof(double) * nparts;
+    double* obs2_part = (double*)w;                w += sizeof(double) * nparts;
     int* d_int = (int*)w;                          w += sizeof(int) * n_int;
     int* bad_part = (int*)w;
     int* d_perm = d_int;
@@ -126,7 +127,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
 
     const dim3 bgrid(std::max(nF, 1), std::max(nF, 1));
     for (int it = 0; it < max_iter; ++it) {
-        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part);
+        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
         if (nF > 0) {
             ba_blocks<<<bgrid, kBaBlockThreads, 0, st>>>(bs, cams, pts, uvS, d_ocam, d_opt, d_pt_off, d_cam_off, d_cam_obs, pblk,
                                                          n_fixed, nF, S);
@@ -136,11 +137,11 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
             ba_solve_none<<<1, 1, 0, st>>>(bs);
         }
         ba_trial<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, dC, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, trial_part);
-        ba_accept<<<1, 256, 0, st>>>(bs, cams, dC, nC, cost_part, trial_part, bad_part, nparts, ftol, max_iter);
+        ba_accept<<<1, 256, 0, st>>>(bs, cams, dC, nC, cost_part, trial_part, bad_part, obs2_part, nparts, ftol, max_iter);
         launches += nF > 0 ? 5 : 4;
     }
     if (max_iter == 0) {
-        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part);
+        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
         ba_cost_only<<<1, 1, 0, st>>>(bs, cost_part, nparts);
         launches += 2;
     }

@@ -32,6 +32,7 @@ struct BaState {                // one per problem, device resident
     double lambda, cost, cost_trial;
     int iters, done, accepted, have_cost;
     int n_bad, pad;             // observations skipped (non-finite projection) at the last linearisation
+    double floor;               // cost at which the residuals are rounding noise of the observations: (64 eps)^2 sum |uv|^2 / 2
 };
 
 // one observation at (C, X): prediction, residual, the derivative factors
@@ -92,12 +93,14 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
                                                              double* __restrict__ X, const double* __restrict__ Xtrial,
                                                              const double2* __restrict__ uv, const int* __restrict__ ocam,
                                                              const int* __restrict__ pt_off, int nP, double* __restrict__ pblk,
-                                                             double* __restrict__ cost_part, int* __restrict__ bad_part) {
+                                                             double* __restrict__ cost_part, int* __restrict__ bad_part,
+                                                             double* __restrict__ obs2_part) {
     __shared__ double sh[kBaPointThreads / 32];
     if (st->done) return;
     const double lambda = st->lambda;
     const bool commit = st->accepted > 0;
-    double cost = 0.0;
+    const bool first = st->have_cost == 0;                  // first linearisation: also sum |uv|^2 for the rounding floor
+    double cost = 0.0, obs2 = 0.0;
     int bad = 0;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nP; j += gridDim.x * blockDim.x) {
         double X0, X1, X2;
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
                 g[a] += b.Q[0][a] * b.r0 + b.Q[1][a] * b.r1;
             }
             cost += b.r0 * b.r0 + b.r1 * b.r1;
+            obs2 += m.x * m.x + m.y * m.y;
         }
         V[0] += lambda * V[0]; V[3] += lambda * V[3]; V[5] += lambda * V[5];        // Marquardt scaling
         double Vi[6];
@@ -137,6 +141,10 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
         }
     }
     const double s = ba_block_sum(cost, sh);
+    if (first) {
+        const double s2 = ba_block_sum(obs2, sh);
+        if (threadIdx.x == 0) obs2_part[blockIdx.x] = s2;
+    }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if (threadIdx.x == 0) { cost_part[blockIdx.x] = s; bad_part[blockIdx.x] = 0; }
     __syncthreads();
@@ -726,14 +734,16 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ba_accept(BaState* __restrict__ st, double* __restrict__ cams, const double* __restrict__ dC,
                                                  int nC, const double* __restrict__ cost_part, const double* __restrict__ trial_part,
-                                                 const int* __restrict__ bad_part, int nparts, double ftol, int max_iter) {
+                                                 const int* __restrict__ bad_part, const double* __restrict__ obs2_part,
+                                                 int nparts, double ftol, int max_iter) {
     __shared__ int better_s;
     if (st->done) return;
     if (threadIdx.x == 0) {
         if (!st->have_cost) {
-            double s = 0.0;
-            for (int i = 0; i < nparts; ++i) s += cost_part[i];
+            double s = 0.0, s2 = 0.0;
+            for (int i = 0; i < nparts; ++i) { s += cost_part[i]; s2 += obs2_part[i]; }
             st->cost = 0.5 * s;
+            st->floor = 0.5 * s2 * (64.0 * 2.220446049250313e-16) * (64.0 * 2.220446049250313e-16);
             st->have_cost = 1;
         }
         int nb = 0;
@@ -748,7 +758,7 @@ __global__ void __launch_bounds__(256) ba_accept(BaState* __restrict__ st, doubl
         better_s = better ? 1 : 0;
         if (better) {
             const double gain = st->cost - st->cost_trial;
-            const bool conv = gain <= ftol * st->cost;
+            const bool conv = gain <= ftol * st->cost || st->cost_trial <= st->floor;   // relative decrease, or rounding level
             st->cost = st->cost_trial;
             st->lambda = fmax(st->lambda * 0.1, 1e-15);
             st->accepted = 1;                      // ba_points / ba_finish commit X_trial
@@ -776,7 +786,7 @@ __global__ void ba_cost_only(BaState* __restrict__ st, const double* __restrict_
 
 __global__ void ba_init(BaState* __restrict__ st, double lambda0) {
     st->lambda = lambda0; st->cost = 0.0; st->cost_trial = 0.0;
-    st->iters = 0; st->done = 0; st->accepted = 0; st->have_cost = 0; st->n_bad = 0; st->pad = 0;
+    st->iters = 0; st->done = 0; st->accepted = 0; st->have_cost = 0; st->n_bad = 0; st->pad = 0; st->floor = 0.0;
 }
 
 // after the loop: commit a last accepted trial; points back in the caller's order; scalars
