@@ -368,8 +368,29 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict_
     const int rank = (int)cluster.block_rank(), nr = (int)cluster.num_blocks();
     if (tid == 0) fail = 0;
     __syncthreads();
+    // Every CTA reads block column kb of S (diagonal block + panel) at the start of step kb, so the factor of that block
+    // column may only be written back once ALL CTAs are past those reads: it is written at the start of step kb + 1
+    // (after the cluster barrier), from the copies every CTA still holds in shared memory (Ld, Li, Pn).
+    auto write_back = [&](const int kb) {
+        const int j0 = 12 * kb;
+        int pass = 0;
+        for (int i = j0 + 12 + tid; i < rows; i += blockDim.x, ++pass)
+            if (pass % nr == rank) {
+#pragma unroll
+                for (int c = 0; c < 12; ++c) __stcg(&S[(size_t)i + (size_t)(j0 + c) * ld], Pn[c * rows + i]);
+            }
+        if (rank == nr - 1 && tid < 144) {
+            const int r = tid / 12, c = tid % 12;
+            if (r >= c) __stcg(&S[(size_t)(j0 + r) + (size_t)(j0 + c) * ld], Ld[tid]);
+            if (r == c) __stcg(&dinv[j0 + r], Li[r]);
+        }
+    };
     for (int kb = 0; kb < nF; ++kb) {
         const int j0 = 12 * kb;
+        if (kb > 0) {
+            write_back(kb - 1);
+            __syncthreads();                                // Ld / Li / Pn are overwritten below
+        }
         if (tid < 144) {
             const int r = tid / 12, c = tid % 12;
             Ld[tid] = r >= c ? __ldcg(&S[(size_t)(j0 + r) + (size_t)(j0 + c) * ld]) : 0.0;
@@ -378,23 +399,13 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict_
         if (warp == 0 && !ba_chol12(Ld, Li, cb, lane) && lane == 0) fail = 1;
         __syncthreads();
         if (fail) break;                                    // identical arithmetic in every CTA: uniform decision
-        int pass = 0;
-        for (int i = j0 + 12 + tid; i < rows; i += blockDim.x, ++pass) {
+        for (int i = j0 + 12 + tid; i < rows; i += blockDim.x) {
             double x[12];
 #pragma unroll
             for (int c = 0; c < 12; ++c) x[c] = __ldcg(&S[(size_t)i + (size_t)(j0 + c) * ld]);
             ba_panel_row(x, Ld, Li);
 #pragma unroll
             for (int c = 0; c < 12; ++c) Pn[c * rows + i] = x[c];
-            if (pass % nr == rank) {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) __stcg(&S[(size_t)i + (size_t)(j0 + c) * ld], x[c]);
-            }
-        }
-        if (rank == 0 && tid < 144) {
-            const int r = tid / 12, c = tid % 12;
-            if (r >= c) __stcg(&S[(size_t)(j0 + r) + (size_t)(j0 + c) * ld], Ld[tid]);
-            if (r == c) __stcg(&dinv[j0 + r], Li[r]);
         }
         __syncthreads();
         const int ncol = n - j0 - 12;
@@ -413,6 +424,8 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict_
         }
         cluster.sync();
     }
+    if (!fail && nF > 0) write_back(nF - 1);
+    cluster.sync();                                         // the factor is complete in global memory
     const bool bad = fail != 0;
     if (rank != 0) return;
     // backward substitution  L^T x = y,  y = row n of the factor

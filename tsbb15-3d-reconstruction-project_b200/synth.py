@@ -118,3 +118,41 @@ def pnp_scene(n: int, seed: int = 4, cam: int = 17, outlier_frac: float = 0.3, s
     lo, hi = y[n_out:].min(axis=0), y[n_out:].max(axis=0)
     y[:n_out] = rng.uniform(lo, hi, size=(n_out, 2))
     return np.ascontiguousarray(X), np.ascontiguousarray(y), (Rt[:, :3], Rt[:, 3])
+
+
+def ba_scene(n_views: int, n_points: int, seed: int = 7, track: int = 8, sigma: float = 0.5 / 3217.0, start_pt: float = 2e-3,
+             start_cam: float = 1e-3):
+    """A bundle-adjustment problem in the layout Tables.BundleAdjustment2 works on (tables.py:298-315): n_views cameras
+    [R | t] on a ring around a point cloud (first view = [I | 0]), every point seen by `track` consecutive views
+    (wrapping), C-normalised observations with noise sigma, start values off the truth by start_pt / start_cam.
+    Returns cams (V,3,4), pts (P,3), uv (O,2), cam_idx (O,), pt_idx (O,), and the noise-free truth (cams, pts)."""
+    rng = np.random.default_rng(seed)
+    track = min(track, n_views)
+    X = rng.uniform(-1.0, 1.0, (n_points, 3)) * np.array([1.0, 0.6, 1.0])
+    cams_w = np.zeros((n_views, 3, 4))
+    for k in range(n_views):
+        a = 2.0 * np.pi * k / n_views
+        c = np.array([6.0 * np.sin(a), 0.3 * np.sin(3 * a), -6.0 * np.cos(a)])        # camera centre on a ring of radius 6
+        z = -c / np.linalg.norm(c)
+        x = np.cross([0.0, 1.0, 0.0], z)
+        x /= np.linalg.norm(x)
+        R = np.stack([x, np.cross(z, x), z])
+        cams_w[k, :, :3] = R
+        cams_w[k, :, 3] = -R @ c
+    R0, t0 = cams_w[0, :, :3], cams_w[0, :, 3]
+    Xc = X @ R0.T + t0                                                               # frame of view 0
+    true_cams = np.zeros_like(cams_w)
+    for k in range(n_views):
+        Rk = cams_w[k, :, :3] @ R0.T
+        true_cams[k, :, :3] = Rk
+        true_cams[k, :, 3] = cams_w[k, :, 3] - Rk @ t0
+    first = rng.integers(0, n_views, n_points)
+    cam_idx = ((first[:, None] + np.arange(track)[None, :]) % n_views).ravel()
+    pt_idx = np.repeat(np.arange(n_points), track)
+    Xh = np.hstack([Xc, np.ones((n_points, 1))])
+    y = np.einsum("oab,ob->oa", true_cams[cam_idx], Xh[pt_idx])
+    uv = y[:, :2] / y[:, 2:] + sigma * rng.standard_normal((len(cam_idx), 2))
+    cams0 = true_cams.copy()
+    cams0[1:] += start_cam * rng.standard_normal((n_views - 1, 3, 4)) * np.array([1, 1, 1, 0.1])
+    pts0 = Xc + start_pt * rng.standard_normal(Xc.shape)
+    return cams0, pts0, uv, cam_idx.astype(np.int32), pt_idx.astype(np.int32), (true_cams, Xc)
