@@ -20,7 +20,7 @@ static inline char* align16(char* w) { return (char*)(((uintptr_t)w + 15) & ~(ui
 // cam_idx / pt_idx are HOST arrays (table bookkeeping lives on the host in the reference too).
 static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, double* cams, double* pts, const double* uv,
                              const int* cam_idx, const int* pt_idx, int n_fixed, int max_iter, double ftol, double* cost,
-                             int* iters, int* status) {
+                             int* iters, int* status, bool host_paced) {
     RG_CHECK_ARG(nC >= 0 && nP >= 0 && nO >= 0, "negative size");
     RG_CHECK_ARG(n_fixed >= 0, "n_fixed must be >= 0");
     RG_CHECK_ARG(max_iter >= 0 && max_iter <= 10000, "max_iter must be in [0, 10000]");
@@ -125,8 +125,22 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(kBaSolveThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
 
+    // host_paced (the host-buffer entry point, which ends with a synchronisation anyway): the solver's `done` flag is
+    // copied to pinned memory after every iteration and the enqueue loop stays at most two iterations ahead of the
+    // device, so that it stops two iterations after convergence instead of enqueueing max_iter x 5 empty launches.
+    volatile int* h_flags = nullptr;
+    if (host_paced && max_iter > 2) {
+        if ((rc = ensure_pinned(c->h_ba_flags, sizeof(int) * (size_t)max_iter))) return rc;
+        h_flags = (volatile int*)c->h_ba_flags.ptr;
+        for (int i = 0; i < 2; ++i)
+            if (!c->ba_iter_ev[i]) RG_CUDA(cudaEventCreateWithFlags(&c->ba_iter_ev[i], cudaEventDisableTiming));
+    }
     const dim3 bgrid(std::max(nF, 1), std::max(nF, 1));
     for (int it = 0; it < max_iter; ++it) {
+        if (h_flags && it >= 2) {
+            RG_CUDA(cudaEventSynchronize(c->ba_iter_ev[it & 1]));          // iteration it - 2 has finished
+            if (h_flags[it - 2]) break;
+        }
         ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
         if (nF > 0) {
             ba_blocks<<<bgrid, kBaBlockThreads, 0, st>>>(bs, cams, pts, uvS, d_ocam, d_opt, d_pt_off, d_cam_off, d_cam_obs, pblk,
@@ -139,6 +153,10 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
         ba_trial<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, dC, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, trial_part);
         ba_accept<<<1, 256, 0, st>>>(bs, cams, dC, nC, cost_part, trial_part, bad_part, obs2_part, nparts, ftol, max_iter);
         launches += nF > 0 ? 5 : 4;
+        if (h_flags) {
+            RG_CUDA(cudaMemcpyAsync((void*)&h_flags[it], &bs->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            RG_CUDA(cudaEventRecord(c->ba_iter_ev[it & 1], st));
+        }
     }
     if (max_iter == 0) {
         ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
@@ -164,7 +182,7 @@ int rg_bundle_adjust_dev(void* ctx, void* stream, int n_views, int n_points, int
                          double ftol, double* cost_dev, int32_t* iters_dev, int32_t* status_dev) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     return bundle_adjust_dev((Ctx*)ctx, (cudaStream_t)stream, n_views, n_points, n_obs, cams_dev, pts_dev, uv_dev, cam_idx_host,
-                             pt_idx_host, n_fixed, max_iter, ftol, cost_dev, iters_dev, status_dev);
+                             pt_idx_host, n_fixed, max_iter, ftol, cost_dev, iters_dev, status_dev, false);
 }
 
 int rg_bundle_adjust_host(void* ctx, void* stream, int n_views, int n_points, int n_obs, double* cams, double* pts,
@@ -188,7 +206,7 @@ int rg_bundle_adjust_host(void* ctx, void* stream, int n_views, int n_points, in
     if (np) RG_CUDA(cudaMemcpyAsync(dpts, pts, sizeof(double) * 3 * np, cudaMemcpyHostToDevice, st));
     if (no) RG_CUDA(cudaMemcpyAsync(duv, uv, sizeof(double) * 2 * no, cudaMemcpyHostToDevice, st));
     rc = bundle_adjust_dev(c, st, n_views, n_points, n_obs, dcam, dpts, duv, cam_idx, pt_idx, n_fixed, max_iter, ftol, dcost, dit,
-                           dit + 1);
+                           dit + 1, true);
     if (rc) return rc;
     if (nc) RG_CUDA(cudaMemcpyAsync(cams, dcam, sizeof(double) * 12 * nc, cudaMemcpyDeviceToHost, st));
     if (np) RG_CUDA(cudaMemcpyAsync(pts, dpts, sizeof(double) * 3 * np, cudaMemcpyDeviceToHost, st));

@@ -109,6 +109,9 @@ int rg_shutdown(void* ctx) {
         release(*b);
     release_pinned(c->h_stage);
     release_pinned(c->h_stats);
+    release_pinned(c->h_ba_flags);
+    for (int i = 0; i < 2; ++i)
+        if (c->ba_iter_ev[i]) cudaEventDestroy(c->ba_iter_ev[i]);
     if (c->prof_ev) {
         for (int i = 0; i < Ctx::kProfRing * (Ctx::kProfPhases + 1); ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
