@@ -3,6 +3,10 @@ modules on the clean Dino tracks, timed.  main.py itself cannot run here or on t
 plots); this script follows it statement by statement without the image / plot calls.
 
     python tools/run_main_dropin.py [last_view=34] [--no-ba]
+
+Data: the exact BAdino2.mat projections, i.e. the branch of correspondences.py that the reference ships active (its
+tracked points.txt branch is commented out: those tracks contain gross mismatches, INIT3 triangulates every putative
+correspondence and BundleAdjustment2 has no robust loss, so the pipeline is not meant to run on them).
 """
 import os
 import sys
@@ -20,8 +24,9 @@ def run(last_view=34, bundle_adjust=True, r_f=10000, verbose=True):
     Tables, CameraPose = rg.tables.Tables, rg.help_classes.CameraPose
     d = np.load(os.path.join(ROOT, "tests", "golden", "dino_data.npz"))
     x2d, Ps = d["x2d"], d["Ps"]
+    pnp_kw = dict(r=256, reproj_px=1.5)
 
-    def corr(i1, i2):                                         # correspondences.getCorrByIndices, clean branch
+    def corr(i1, i2):                                         # correspondences.getCorrByIndices (clean branch)
         y1, y2 = x2d[i1].T, x2d[i2].T
         ok = np.logical_and(np.any(y1 != -1, axis=1), np.any(y2 != -1, axis=1))
         return np.array(y1[ok]), np.array(y2[ok])
@@ -53,7 +58,7 @@ def run(last_view=34, bundle_adjust=True, r_f=10000, verbose=True):
         a, b = corr(i, i + 1)                                                     # main.py:113
         ah, bh = fun.MakeHomogenous(K, a), fun.MakeHomogenous(K, b)
         t0 = time.perf_counter()
-        A1, A2 = T.addNewView(K, i + 1, ah, bh, a, b, r=256, reproj_px=1.5, seed=i)  # main.py:127
+        A1, A2 = T.addNewView(K, i + 1, ah, bh, a, b, seed=i, **pnp_kw)          # main.py:127
         times["add_view"] += time.perf_counter() - t0
         t0 = time.perf_counter()
         T.addNewPoints(fun.MakeHomogenous(K, A1), fun.MakeHomogenous(K, A2), i, i + 1)  # main.py:137
@@ -68,6 +73,22 @@ def run(last_view=34, bundle_adjust=True, r_f=10000, verbose=True):
     return T, Rs, ts, times, total, ba_log
 
 
+def rotation_errors_deg(Rs):
+    """Angle between every recovered rotation (nearest rotation of the possibly non-orthonormal 3x3 block BA leaves) and
+    the ground-truth rotation of that view relative to view 0 (fun.camera_resectioning of BAdino2.mat's cameras)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pnp_golden.npz"))
+    out = []
+    for k, R in enumerate(Rs):
+        U, _, Vt = np.linalg.svd(R)
+        Rn = U @ np.diag([1.0, 1.0, np.linalg.det(U @ Vt)]) @ Vt
+        Rg = g["R"][k] @ g["R"][0].T
+        c = (np.trace(Rn @ Rg.T) - 1.0) / 2.0
+        out.append(np.degrees(np.arccos(np.clip(c, -1.0, 1.0))))
+    return np.array(out)
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    run(int(args[0]) if args else 34, bundle_adjust="--no-ba" not in sys.argv)
+    T, Rs, ts, times, total, ba_log = run(int(args[0]) if args else 34, bundle_adjust="--no-ba" not in sys.argv)
+    err = rotation_errors_deg(Rs)
+    print("rotation error vs ground truth (deg): median %.2e max %.2e" % (np.median(err), err.max()))
