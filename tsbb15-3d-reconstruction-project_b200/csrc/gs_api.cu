@@ -6,7 +6,7 @@ namespace rg {
 
 static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64, const int* pair_off, const double* F0,
                              const unsigned char* mask, int max_iter, double ftol, double* F_gold, double* cost, int* iters,
-                             int* status, double* X_out) {
+                             int* status, double* X_out, bool host_paced) {
     RG_CHECK_ARG(P >= 0 && pair_off != nullptr, "bad pair table");
     RG_CHECK_ARG(pair_off[0] == 0, "pair_off must start at 0");
     for (int p = 0; p < P; ++p) RG_CHECK_ARG(pair_off[p + 1] >= pair_off[p], "pair_off must be non-decreasing");
@@ -21,7 +21,7 @@ static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64
     for (int q = 0; q < P; ++q) maxN = std::max(maxN, pair_off[q + 1] - pair_off[q]);
     // workspace: GsPair[P] | sums[P x kGsSums] | C1, C2 (P x 12) | x1n, x2n (N double2) | Xcur, Xtrial (3N) | pair_off
     const size_t bytes = sizeof(GsPair) * p + sizeof(double) * (kGsSums * p + 24 * p + 4 * N + 6 * N + 2) +
-                         sizeof(int) * (p + 1) + 64;
+                         sizeof(int) * (p + 1 + (size_t)max_iter) + 64;
     int rc;
     if ((rc = ensure(c->gs_ws, bytes))) return rc;
     char* w = (char*)c->gs_ws.ptr;
@@ -34,7 +34,8 @@ static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64
     double* C2 = (double*)w;                       w += sizeof(double) * 12 * p;
     double* Xws = (double*)w;                      w += sizeof(double) * 3 * N;
     double* Xtrial = (double*)w;                   w += sizeof(double) * 3 * N;
-    int* doff = (int*)w;
+    int* doff = (int*)w;                           w += sizeof(int) * (p + 1);
+    int* active = (int*)w;                         // pairs still running after iteration it (host-paced loop)
     double* Xcur = X_out ? X_out : Xws;
 
     gs_init<<<ceil_div(P, 64), 64, 0, st>>>(F0, P, 1e-3, gp, C1, C2);
@@ -56,12 +57,32 @@ static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64
         RG_CUDA(cudaEventRecord(c->staging_free, st));
         const int nbx = std::max(1, std::min(32, ceil_div(maxN, kGsThreads * 4)));
         const dim3 grid(nbx, P);
+        // host_paced (the host-buffer entry point, which ends with a synchronisation anyway): the number of pairs still
+        // running is copied to pinned memory after every iteration and the enqueue loop stays at most two iterations
+        // ahead of the device: it stops two iterations after the last pair converged instead of enqueueing 4 x max_iter
+        // launches that return at once.
+        volatile int* h_act = nullptr;
+        if (host_paced && max_iter > 2) {
+            if ((rc = ensure_pinned(c->h_ba_flags, sizeof(int) * (size_t)max_iter))) return rc;
+            h_act = (volatile int*)c->h_ba_flags.ptr;
+            for (int i = 0; i < 2; ++i)
+                if (!c->ba_iter_ev[i]) RG_CUDA(cudaEventCreateWithFlags(&c->ba_iter_ev[i], cudaEventDisableTiming));
+            RG_CUDA(cudaMemsetAsync(active, 0, sizeof(int) * (size_t)max_iter, st));
+        }
         for (int it = 0; it < max_iter; ++it) {
+            if (h_act && it >= 2) {
+                RG_CUDA(cudaEventSynchronize(c->ba_iter_ev[it & 1]));      // iteration it - 2 has finished
+                if (h_act[it - 2] == 0) break;
+            }
             gs_accumulate<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial, sums);
             gs_solve<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P);
             gs_trial<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial);
-            gs_accept<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P, ftol, max_iter);
+            gs_accept<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P, ftol, max_iter, h_act ? active + it : nullptr);
             launches += 4;
+            if (h_act) {
+                RG_CUDA(cudaMemcpyAsync((void*)&h_act[it], active + it, sizeof(int), cudaMemcpyDeviceToHost, st));
+                RG_CUDA(cudaEventRecord(c->ba_iter_ev[it & 1], st));
+            }
         }
         RG_CUDA(cudaGetLastError());
         gs_finish<<<grid, kGsThreads, 0, st>>>(doff, gp, Xcur, Xtrial, C1);
@@ -94,7 +115,7 @@ int rg_gold_standard_dev(void* ctx, void* stream, int P, const double* pts64_dev
                          double* cost_dev, int32_t* iters_dev, int32_t* status_dev, double* X_dev) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     return gold_standard_dev((Ctx*)ctx, (cudaStream_t)stream, P, pts64_dev, pair_off_host, F0_dev, mask_dev, max_iter, ftol,
-                             F_gold_dev, cost_dev, iters_dev, status_dev, X_dev);
+                             F_gold_dev, cost_dev, iters_dev, status_dev, X_dev, false);
 }
 
 int rg_gold_standard_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const double* F0,
@@ -123,7 +144,8 @@ int rg_gold_standard_host(void* ctx, void* stream, int P, const double* pts64, c
     int* dit = (int*)(dX + 3 * std::max<size_t>(N, 1));
     int* dst = dit + p;
     rc = gold_standard_dev(c, st, P, (const double*)c->d_in_a.ptr, pair_off, (const double*)c->d_in_b.ptr,
-                           (mask && N) ? (const unsigned char*)c->d_in_c.ptr : nullptr, max_iter, ftol, dF, dcost, dit, dst, dX);
+                           (mask && N) ? (const unsigned char*)c->d_in_c.ptr : nullptr, max_iter, ftol, dF, dcost, dit, dst, dX,
+                           true);
     if (rc) return rc;
     RG_CUDA(cudaMemcpyAsync(F_gold, dF, sizeof(double) * 9 * p, cudaMemcpyDeviceToHost, st));
     if (cost) RG_CUDA(cudaMemcpyAsync(cost, dcost, sizeof(double) * p, cudaMemcpyDeviceToHost, st));

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kGsThreads) gs_trial(const double4* __restrict
 
 // step 4 (one thread per pair): accept / reject, damping schedule, convergence, clear the sums
 __global__ void __launch_bounds__(32) gs_accept(GsPair* __restrict__ gpair, double* __restrict__ sums, int P, double ftol,
-                                                int max_iter) {
+                                                int max_iter, int* __restrict__ n_active) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     GsPair& G = gpair[p];
@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(32) gs_accept(GsPair* __restrict__ gpair, doub
         if (G.lambda > 1e12) G.done = 3;         // no descent direction found any more: current point is kept
     }
     if (!G.done && G.iters >= max_iter) G.done = 4;
+    if (n_active != nullptr && !G.done) atomicAdd(n_active, 1);      // host-paced loop: pairs still running after this iteration
 }
 
 // after the loop: commit a last accepted trial, export the camera
