@@ -218,6 +218,19 @@ int rg_match_first_within_host(void* ctx, void* stream, int dim, int M, const do
 int rg_match_first_within_dev(void* ctx, void* stream, int dim, int M, const double* obs_dev, int N, const double* y_dev,
                               double tol, int32_t* idx_dev);
 
+/* ---- cross-GPU argmax when ONE pair's / view's hypotheses are split over several GPUs ------- */
+/* Every rank runs rg_f_ransac_dev / rg_pnp_ransac_dev on its hypothesis block [index_offset, ...).  rg_argmax_pack_dev
+ * turns the per-pair (best_idx, best_count) into the monotone key (count << 32) | (0xFFFFFFFF - (best_idx + index_offset)),
+ * 0 if the block has no hypothesis with an inlier; rg_argmax_allreduce is ONE in-place ncclAllReduce(ncclMax, ncclUint64)
+ * over `count` keys on `stream` (nccl_comm: the caller's ncclComm_t; libnccl.so.2 is dlopen'ed at the first call, or
+ * the library named by RG_NCCL_LIB); rg_argmax_unpack_dev gives the winner's GLOBAL hypothesis index and count: larger
+ * count first, then the lower index = the first maximum of the single-GPU selection (fun.py:320-323, ransac.py:108).
+ * The rank that owns the winning index then publishes its F / pose and mask. */
+int rg_argmax_pack_dev(void* stream, int P, const int32_t* best_idx_dev, const int32_t* best_count_dev, int index_offset,
+                       unsigned long long* key_dev);
+int rg_argmax_allreduce(void* nccl_comm, void* stream, unsigned long long* key_dev, int count);
+int rg_argmax_unpack_dev(void* stream, int P, const unsigned long long* key_dev, int32_t* best_idx_dev, int32_t* best_count_dev);
+
 #ifdef __cplusplus
 }
 #endif

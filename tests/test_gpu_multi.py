@@ -33,4 +33,4 @@ def test_two_gpus_nccl_if_available():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
-    assert d["world"] == 2 and d["pairs_sharded_ok"] and d["hyp_split_ok"]
+    assert d["world"] == 2 and d["pairs_sharded_ok"] and d["hyp_split_ok"] and d["c_abi_allreduce_ok"]

@@ -32,6 +32,29 @@ def main():
     split = parallel.f_ransac_split_hypotheses(pts, idx, thr=1.5, device=local)
     ok2 = (split["best_idx"] == int(one["best_idx"][0]) and split["best_count"] == int(one["best_count"][0])
            and np.array_equal(split["mask"], one["mask"][0]) and np.array_equal(split["F"], one["F"][0]))
+    # the same split with the key reduced by the library's own C entry point (rg_argmax_pack_dev / rg_argmax_allreduce /
+    # rg_argmax_unpack_dev on a raw ncclComm_t) instead of torch.distributed
+    comm = parallel.NcclComm(rank, world)
+    split_c = parallel.f_ransac_split_hypotheses(pts, idx, thr=1.5, device=local, nccl_comm=comm)
+    ok_c = (split_c["best_idx"] == split["best_idx"] and split_c["best_count"] == split["best_count"]
+            and np.array_equal(split_c["mask"], split["mask"]) and np.array_equal(split_c["F"], split["F"]))
+    # many keys in one reduction: every rank contributes its own (index, count) per pair
+    rs = np.random.default_rng(100 + rank)
+    bi = rs.integers(-1, 500, 64).astype(np.int32)
+    bc = np.where(bi >= 0, rs.integers(1, 1000, 64), 0).astype(np.int32)
+    gi, gc = parallel.argmax_allreduce_c(bi, bc, 1000 * rank, comm)
+    allb = [torch.zeros(128, dtype=torch.int32, device="cuda") for _ in range(world)]
+    dist.all_gather(allb, torch.from_numpy(np.concatenate([bi, bc])).cuda())
+    keys = np.zeros(64, dtype=np.uint64)
+    for r, t_ in enumerate(allb):
+        a = t_.cpu().numpy()
+        k_ = np.array([parallel.argmax_key(int(c_), int(i_) + 1000 * r) if i_ >= 0 and c_ > 0 else 0
+                       for i_, c_ in zip(a[:64], a[64:])], dtype=np.uint64)
+        keys = np.maximum(keys, k_)
+    exp = [parallel.key_decode(int(k_)) if k_ else (0, -1) for k_ in keys]
+    ok_c = ok_c and all(int(gc[p]) == e[0] and int(gi[p]) == e[1] for p, e in enumerate(exp))
+    comm.close()
+    ok2 = ok2 and ok_c
     # PnP: hypotheses of one view split over the ranks; views sharded over the ranks
     thr2 = (1.5 / 3217.0) ** 2
     X, y, _ = synth.pnp_scene(30000, seed=4)
@@ -51,7 +74,7 @@ def main():
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "pairs_sharded_ok": bool(res[0].item()), "hyp_split_ok": bool(res[1].item()),
-                          "split_owner": split["owner"], "best": split["best_idx"], "count": split["best_count"]}))
+                          "c_abi_allreduce_ok": bool(ok_c), "split_owner": split["owner"], "best": split["best_idx"], "count": split["best_count"]}))
     dist.destroy_process_group()
     sys.exit(0 if int(res.min().item()) == 1 else 1)
 

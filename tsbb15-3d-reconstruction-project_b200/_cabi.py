@@ -67,6 +67,9 @@ SIGNATURES = {
     "rg_two_view_init_host": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_two_view_init_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_match_first_within_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp]),
+    "rg_argmax_pack_dev": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "rg_argmax_allreduce": (_i, [_vp, _vp, _vp, _i]),
+    "rg_argmax_unpack_dev": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rg_match_first_within_dev": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp]),
 }
 

@@ -6,4 +6,5 @@
 #include "geom_api.cu"
 #include "gs_api.cu"
 #include "ba_api.cu"
+#include "nccl_api.cu"
 #include "microbench.cu"

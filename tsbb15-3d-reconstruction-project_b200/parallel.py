@@ -55,6 +55,66 @@ def _device_for_collectives(group=None):
     return torch.device("cpu")
 
 
+class NcclComm:
+    """A raw ``ncclComm_t`` for the C-ABI reduction ``rg_argmax_allreduce`` (include/rg_b200.h) — what a host that does
+    not use torch would create itself.  The unique id is made on rank 0 and handed to the other ranks through
+    ``exchange`` (default: ``torch.distributed.broadcast_object_list`` on whatever backend is initialised)."""
+
+    def __init__(self, rank: int, world: int, exchange=None, lib_name: str | None = None):
+        import ctypes as C
+        import os
+        self._C = C
+        self.lib = C.CDLL(lib_name or os.environ.get("RG_NCCL_LIB") or "libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+
+        self.lib.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+        uid = UniqueId()
+        if rank == 0 and self.lib.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+        raw = bytes(C.string_at(C.byref(uid), 128))
+        if exchange is None:
+            def exchange(b):
+                box = [b]
+                _dist().broadcast_object_list(box, src=0)
+                return box[0]
+        raw = exchange(raw)
+        C.memmove(C.byref(uid), raw, 128)
+        self.handle = C.c_void_p()
+        rc = self.lib.ncclCommInitRank(C.byref(self.handle), int(world), uid, int(rank))
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.handle:
+            self.lib.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
+def argmax_allreduce_c(best_idx, best_count, index_offset, comm: NcclComm, stream=0):
+    """(best_idx, best_count) of this rank's hypothesis block -> global winner, entirely through the C ABI on the device:
+    rg_argmax_pack_dev -> rg_argmax_allreduce (ONE ncclAllReduce(max) of 8 bytes per pair) -> rg_argmax_unpack_dev."""
+    import ctypes as C
+    import torch
+    from . import _cabi as cabi
+    lib = cabi.load_library()
+    vp = C.c_void_p
+    bi = torch.as_tensor(np.atleast_1d(np.asarray(best_idx, dtype=np.int32))).cuda()
+    bc = torch.as_tensor(np.atleast_1d(np.asarray(best_count, dtype=np.int32))).cuda()
+    P = bi.numel()
+    key = torch.empty(P, dtype=torch.int64, device=bi.device)
+    st = stream or torch.cuda.current_stream().cuda_stream
+    cabi.check(lib.rg_argmax_pack_dev(vp(st), P, vp(bi.data_ptr()), vp(bc.data_ptr()), int(index_offset), vp(key.data_ptr())))
+    cabi.check(lib.rg_argmax_allreduce(comm.handle, vp(st), vp(key.data_ptr()), P))
+    cabi.check(lib.rg_argmax_unpack_dev(vp(st), P, vp(key.data_ptr()), vp(bi.data_ptr()), vp(bc.data_ptr())))
+    torch.cuda.current_stream().synchronize()
+    return bi.cpu().numpy(), bc.cpu().numpy()
+
+
 def f_ransac_pairs_sharded(pts_list, idx_list, thr=1.5, group=None, gather=True, compute=None, **kw) -> dict:
     """Pair-sharded batched F-RANSAC.  Every rank passes the SAME full lists (or at least its own shard filled in);
     returns, on every rank, arrays over all pairs when ``gather`` is True, else only the local shard's results."""
@@ -94,8 +154,10 @@ def f_ransac_pairs_sharded(pts_list, idx_list, thr=1.5, group=None, gather=True,
     return {"range": (lo, hi), "best_idx": best_idx, "best_count": best_count, "F": F}
 
 
-def f_ransac_split_hypotheses(pts, idx, thr=1.5, group=None, compute=None, **kw) -> dict:
-    """One pair, hypotheses split across ranks, one max-all-reduce of an int64 key (first-maximum selection)."""
+def f_ransac_split_hypotheses(pts, idx, thr=1.5, group=None, compute=None, nccl_comm: NcclComm | None = None, **kw) -> dict:
+    """One pair, hypotheses split across ranks, one max-all-reduce of an int64 key (first-maximum selection).
+    nccl_comm: reduce through the library's own C entry point ``rg_argmax_allreduce`` on that communicator instead of
+    ``torch.distributed.all_reduce`` (same key, same result)."""
     import torch
     rank, world = _world(group)
     idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -112,9 +174,13 @@ def f_ransac_split_hypotheses(pts, idx, thr=1.5, group=None, compute=None, **kw)
         return {"best_idx": gi, "best_count": cnt, "F": local["F"][0], "mask": local["mask"][0], "owner": 0}
     dist = _dist()
     dev = _device_for_collectives(group)
-    k = torch.tensor([key], dtype=torch.int64, device=dev)
-    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
-    gkey = int(k.item())
+    if nccl_comm is not None:
+        gi_a, cnt_a = argmax_allreduce_c(local["best_idx"][:1], local["best_count"][:1], lo, nccl_comm)
+        gkey = argmax_key(int(cnt_a[0]), int(gi_a[0])) if gi_a[0] >= 0 else 0
+    else:
+        k = torch.tensor([key], dtype=torch.int64, device=dev)
+        dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+        gkey = int(k.item())
     if gkey == 0:
         n = np.asarray(pts).reshape(-1, 4).shape[0]
         return {"best_idx": -1, "best_count": 0, "F": np.full((3, 3), np.nan), "mask": np.zeros(n, np.uint8), "owner": -1}
