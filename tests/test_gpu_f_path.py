@@ -280,6 +280,30 @@ def test_config3_shape_fp32_equals_fp64_and_invariances(rt, rg):
         assert np.array_equal(e32["counts"][0], e64["counts"][0])
 
 
+def test_config5_shape_batch_vs_oracle_and_fp64(rt, rg):
+    """BASELINE config 5 (pairs of 50 000 correspondences x 8 192 hypotheses; bench.py scores 16 of them per step): the
+    first two pairs against the oracle on a slice of 160 hypotheses ('check the first pairs against the
+    oracle'), every pair of the batch against the all-FP64 path, and the batch against pair-by-pair calls."""
+    P, N, H = 16, 50000, 8192
+    pairs = rg.synth.multi_pair(P, N)
+    idxs = [rg.sampling.fast(N, H, 8, seed=1000 + p) for p in range(P)]
+    a = rt.f_ransac_batched(pairs, idxs, thr=1.5, want_counts=True)
+    b = rt.f_ransac_batched(pairs, idxs, thr=1.5, want_counts=True, score_path=rg.SCORE_FP64)
+    for p in range(P):
+        assert np.array_equal(a["counts"][p], b["counts"][p]), p
+        assert int(a["best_idx"][p]) == int(b["best_idx"][p]) and np.array_equal(a["mask"][p], b["mask"][p])
+        assert int(a["best_count"][p]) == int(a["mask"][p].sum()) == int(a["counts"][p].max()) > 0.55 * N
+    for p in (0, 1):
+        p1, p2 = pairs[p][:, :2].T.copy(), pairs[p][:, 2:].T.copy()
+        sub = idxs[p][:160]
+        o = orc.f_ransac(p1, p2, sub, 1.5, tie="first")
+        good = orc.sample_condition(p1, p2, sub) > 1e-6
+        assert good.sum() > 150 and np.array_equal(a["counts"][p][:160][good], o["counts"][good])
+    for p in (3, 15):
+        one = rt.f_ransac_batched([pairs[p]], [idxs[p]], thr=1.5, want_counts=True)
+        assert np.array_equal(one["counts"][0], a["counts"][p]) and np.array_equal(one["F"][0], a["F"][p])
+
+
 def test_host_entry_sub_batches_do_not_change_results(rt, rg):
     """rg_f_ransac_host uploads its inputs in sub-batches on a second stream (option 2); pairs are independent, so every
     output — winners, masks, per-hypothesis counts / F / flags, guard-band statistics — must be identical for any split."""
