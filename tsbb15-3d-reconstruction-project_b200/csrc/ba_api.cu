@@ -38,7 +38,8 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     c->last_stats[7] = 0;
 
     // ---- host: observations sorted by point (stable), CSR by point and by view -------------------------------------
-    const size_t n_int = (size_t)4 * nO + (size_t)nP + 1 + (size_t)nC + 1;
+    const size_t n_int_base = (size_t)4 * nO + (size_t)nP + 1 + (size_t)nC + 1;
+    const size_t n_int = n_int_base;
     RG_CUDA(cudaEventSynchronize(c->staging_free));
     int rc;
     if ((rc = ensure_pinned(c->h_stage, sizeof(int) * n_int))) return rc;
@@ -65,13 +66,63 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
         for (int s = 0; s < nO; ++s) h_cam_obs[fill[h_ocam[s]]++] = s;
     }
 
+    // blocks (kf, lf <= kf) of the reduced camera system with at least one common point (all diagonal blocks included)
+    const int nFh = std::max(0, nC - n_fixed);
+    std::vector<int2> blist;
+    {
+        const int words = (nC + 63) / 64;
+        std::vector<unsigned long long> cov((size_t)nC * words, 0ull), tm(words);
+        for (int j = 0; j < nP; ++j) {
+            const int a = h_pt_off[j], b = h_pt_off[j + 1];
+            if (b - a < 2) continue;
+            std::fill(tm.begin(), tm.end(), 0ull);
+            for (int s = a; s < b; ++s) tm[h_ocam[s] >> 6] |= 1ull << (h_ocam[s] & 63);
+            for (int s = a; s < b; ++s) {
+                unsigned long long* row = &cov[(size_t)h_ocam[s] * words];
+                for (int w = 0; w < words; ++w) row[w] |= tm[w];
+            }
+        }
+        for (int kf = 0; kf < nFh; ++kf)
+            for (int lf = 0; lf <= kf; ++lf) {
+                const int k = n_fixed + kf, l = n_fixed + lf;
+                if (kf == lf || ((cov[(size_t)k * words + (l >> 6)] >> (l & 63)) & 1ull)) blist.push_back(make_int2(kf, lf));
+            }
+    }
+    const size_t n_blocks = blist.size();
+    // work items of ba_blocks: a block whose view has many observations is split into segments of kBaSegChunks chunks
+    const int seg_len = kBaSegChunks * kBaBlockThreads;
+    size_t n_items = 0;
+    bool any_split = false;
+    for (size_t i = 0; i < n_blocks; ++i) {
+        const int k = n_fixed + blist[i].x;
+        const int nseg = std::max(1, ceil_div(h_cam_off[k + 1] - h_cam_off[k], seg_len));
+        n_items += (size_t)nseg;
+        any_split = any_split || nseg > 1;
+    }
+    const size_t item_ints = 4 * n_items + n_blocks + 8;
+    if ((rc = ensure_pinned(c->h_ba_items, sizeof(int) * item_ints))) return rc;
+    int* h_items = (int*)c->h_ba_items.ptr;                        // int4 per item, then first item of every block
+    int* h_first = h_items + 4 * n_items;
+    {
+        size_t it = 0;
+        for (size_t i = 0; i < n_blocks; ++i) {
+            const int k = n_fixed + blist[i].x;
+            const int nseg = std::max(1, ceil_div(h_cam_off[k + 1] - h_cam_off[k], seg_len));
+            h_first[i] = (int)it;
+            for (int sgm = 0; sgm < nseg; ++sgm, ++it) {
+                h_items[4 * it] = blist[i].x; h_items[4 * it + 1] = blist[i].y; h_items[4 * it + 2] = sgm; h_items[4 * it + 3] = nseg;
+            }
+        }
+    }
+    const bool sparse_blocks = n_blocks < (size_t)nFh * (nFh + 1) / 2;
+
     // ---- workspace ---------------------------------------------------------------------------------------------------
     const int n = 12 * nF;
     const int nparts = std::max(1, std::min(1024, ceil_div(std::max(nP, 1), kBaPointThreads)));
     const size_t s_elems = (size_t)(n + 1) * (size_t)std::max(n, 1);
     const size_t bytes = sizeof(BaState) + 64 + sizeof(double) * ((size_t)12 * std::max(nC, 1) + (size_t)3 * nP + (size_t)2 * nO +
-                                                                  (size_t)12 * nP + s_elems + (size_t)24 * (n + 1) + (size_t)n + (size_t)3 * nparts + 8) +
-                         sizeof(int) * (n_int + nparts + 8);
+                                                                  (size_t)12 * nP + (size_t)kBaLin * nO + (any_split ? (size_t)kBaPart * n_items : 0) + s_elems + (size_t)24 * (n + 1) + (size_t)n + (size_t)3 * nparts + 8) +
+                         sizeof(int) * (n_int + nparts + 8 + item_ints) + 256;
     if ((rc = ensure(c->ba_ws, bytes))) return rc;
     char* w = (char*)c->ba_ws.ptr;
     BaState* bs = (BaState*)w;                     w = align16(w + sizeof(BaState));
@@ -79,6 +130,9 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     double* dC = (double*)w;                       w += sizeof(double) * 12 * std::max(nC, 1);
     double* Xtrial = (double*)w;                   w += sizeof(double) * 3 * nP;
     double* pblk = (double*)w;                     w += sizeof(double) * 12 * nP;
+    w = align16(w) + 16;                           w = (char*)(((uintptr_t)w + 31) & ~(uintptr_t)31);
+    double* lin = (double*)w;                      w += sizeof(double) * kBaLin * nO;       // per-observation linearisation
+    double* part = (double*)w;                     w += sizeof(double) * (any_split ? (size_t)kBaPart * n_items : 0);
     double* S = (double*)w;                        w += sizeof(double) * s_elems;
     double* Pg = (double*)w;                       w += sizeof(double) * 24 * (n + 1);      // published panels (double buffer)
     double* dinv = (double*)w;                     w += sizeof(double) * n;                 // reciprocal diagonal (L2 variant)
@@ -86,7 +140,11 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     double* trial_part = (double*)w;               w += sizeof(double) * nparts;
     double* obs2_part = (double*)w;                w += sizeof(double) * nparts;
     int* d_int = (int*)w;                          w += sizeof(int) * n_int;
+    w = align16(w);
+    int* d_items_raw = (int*)w;                    w += sizeof(int) * item_ints;
     int* bad_part = (int*)w;
+    const int4* d_items = (const int4*)d_items_raw;
+    const int* d_first = d_items_raw + 4 * n_items;
     int* d_perm = d_int;
     int* d_ocam = d_perm + nO;
     int* d_opt = d_ocam + nO;
@@ -95,6 +153,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     int* d_cam_off = d_pt_off + nP + 1;
 
     RG_CUDA(cudaMemcpyAsync(d_int, h, sizeof(int) * n_int, cudaMemcpyHostToDevice, st));
+    if (n_items) RG_CUDA(cudaMemcpyAsync(d_items_raw, h_items, sizeof(int) * item_ints, cudaMemcpyHostToDevice, st));
     RG_CUDA(cudaEventRecord(c->staging_free, st));
     RG_CUDA(cudaMemsetAsync(dC, 0, sizeof(double) * 12 * std::max(nC, 1), st));
     int launches = 0;
@@ -135,22 +194,26 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
         for (int i = 0; i < 2; ++i)
             if (!c->ba_iter_ev[i]) RG_CUDA(cudaEventCreateWithFlags(&c->ba_iter_ev[i], cudaEventDisableTiming));
     }
-    const dim3 bgrid(std::max(nF, 1), std::max(nF, 1));
     for (int it = 0; it < max_iter; ++it) {
         if (h_flags && it >= 2) {
             RG_CUDA(cudaEventSynchronize(c->ba_iter_ev[it & 1]));          // iteration it - 2 has finished
             if (h_flags[it - 2]) break;
         }
-        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
+        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part, lin);
         if (nF > 0) {
-            ba_blocks<<<bgrid, kBaBlockThreads, 0, st>>>(bs, cams, pts, uvS, d_ocam, d_opt, d_pt_off, d_cam_off, d_cam_obs, pblk,
-                                                         n_fixed, nF, S);
+            if (sparse_blocks) RG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * s_elems, st));   // blocks without a common point
+            ba_blocks<<<(unsigned)n_items, kBaBlockThreads, 0, st>>>(bs, d_items, part, pts, lin, d_ocam, d_opt, d_pt_off, d_cam_off,
+                                                                    d_cam_obs, pblk, n_fixed, nF, S);
+            if (any_split) {
+                ba_blocks_reduce<<<(unsigned)n_blocks, kBaBlockThreads, 0, st>>>(bs, d_items, d_first, (int)n_blocks, part, nF, S);
+                ++launches;
+            }
             if (dsmem) RG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_dsmem, bs, (const double*)S, Pg, n_fixed, nF, dC));
             else RG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve, bs, S, dinv, n_fixed, nF, dC));
         } else {
             ba_solve_none<<<1, 1, 0, st>>>(bs);
         }
-        ba_trial<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, dC, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, trial_part);
+        ba_trial<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, dC, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, lin, trial_part);
         ba_accept<<<1, 256, 0, st>>>(bs, cams, dC, nC, cost_part, trial_part, bad_part, obs2_part, nparts, ftol, max_iter);
         launches += nF > 0 ? 5 : 4;
         if (h_flags) {
@@ -159,7 +222,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
         }
     }
     if (max_iter == 0) {
-        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part);
+        ba_points<<<nparts, kBaPointThreads, 0, st>>>(bs, cams, pts, Xtrial, uvS, d_ocam, d_pt_off, nP, pblk, cost_part, bad_part, obs2_part, lin);
         ba_cost_only<<<1, 1, 0, st>>>(bs, cost_part, nparts);
         launches += 2;
     }

@@ -24,6 +24,9 @@ namespace cg = cooperative_groups;
 constexpr int kBaPointThreads = 128;
 constexpr int kBaBlockThreads = 192;      // chunk of observations per pass; threads 0..143 own the 12x12 entries
 constexpr int kBaRec = 17;                // doubles per staged observation: A (9) | X (3) | z (3) | M00, M22
+constexpr int kBaSegChunks = 2;            // chunks of kBaBlockThreads observations per work item of ba_blocks
+constexpr int kBaPart = 168;              // doubles per partial block: 144 entries | 12 rhs | 12 diagonal damping sums
+constexpr int kBaLin = 16;                // doubles per observation written by ba_points: T (9) | iy^2, u, v | P2^T r (3) | pad
 constexpr int kBaSolveThreads = 512;
 constexpr int kBaSolveFixed = 192;        // doubles at the start of ba_solve*'s dynamic shared memory: Ld (144) | Li (16) | scratch (32)
 constexpr int kBaMaxFree = 170;           // free views: the 12 x (n + 1) Cholesky panel must fit in shared memory
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
                                                              const double2* __restrict__ uv, const int* __restrict__ ocam,
                                                              const int* __restrict__ pt_off, int nP, double* __restrict__ pblk,
                                                              double* __restrict__ cost_part, int* __restrict__ bad_part,
-                                                             double* __restrict__ obs2_part) {
+                                                             double* __restrict__ obs2_part, double* __restrict__ lin) {
     __shared__ double sh[kBaPointThreads / 32];
     if (st->done) return;
     const double lambda = st->lambda;
@@ -115,7 +118,21 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
             BaObs b;
             const double2 m = uv[o];
             ba_obs(cams + 12 * (size_t)ocam[o], X0, X1, X2, m.x, m.y, b);
-            if (!b.ok) { ++bad; continue; }
+            double4* lo = reinterpret_cast<double4*>(lin + kBaLin * (size_t)o);
+            if (!b.ok) {                                                            // skipped everywhere: an all-zero record
+                ++bad;
+                const double4 z4 = make_double4(0.0, 0.0, 0.0, 0.0);
+                lo[0] = z4; lo[1] = z4; lo[2] = z4; lo[3] = z4;
+                continue;
+            }
+            {
+                double T[3][3];
+                ba_T(b, T);
+                lo[0] = make_double4(T[0][0], T[0][1], T[0][2], T[1][0]);
+                lo[1] = make_double4(T[1][1], T[1][2], T[2][0], T[2][1]);
+                lo[2] = make_double4(T[2][2], b.iy * b.iy, b.u, b.v);
+                lo[3] = make_double4(b.iy * b.r0, b.iy * b.r1, -(b.u * b.r0 + b.v * b.r1) * b.iy, 0.0);   // P2^T r
+            }
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -152,20 +169,23 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// step 2 (CTA per 12x12 block (kf, lf <= kf) of the reduced camera system; grid = (nF, nF)):
-// observations of view k in chunks; each thread linearises one observation, looks through the point's track for
-// observations in view l, stages A = [k == l] M - T V'^-1 T'^T and Xh in shared memory; then thread (r, c) adds
+// step 2 (CTA per 12x12 block (kf, lf <= kf) of the reduced camera system that has at least one common point; the list
+// of such blocks comes from the host, the others stay zero): observations of view k in chunks; each thread takes one
+// observation's linearisation (written by ba_points), looks through the point's track for observations in view l,
+// stages A = [k == l] M - T V'^-1 T'^T and Xh in shared memory (ordered ballot compaction); then thread (r, c) adds
 // A[a][a2] Xh[b] Xh[b2] over the chunk.  Row n of the matrix (leading dimension n + 1) receives the right-hand side,
 // so that the factorisation performs the forward substitution as it goes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBaBlockThreads) ba_blocks(const BaState* __restrict__ st, const double* __restrict__ cams,
-                                                             const double* __restrict__ X, const double2* __restrict__ uv,
-                                                             const int* __restrict__ ocam, const int* __restrict__ opt,
-                                                             const int* __restrict__ pt_off, const int* __restrict__ cam_off,
-                                                             const int* __restrict__ cam_obs, const double* __restrict__ pblk,
-                                                             int n_fixed, int nF, double* __restrict__ S) {
-    const int kf = blockIdx.x, lf = blockIdx.y;
-    if (lf > kf || st->done) return;
+__global__ void __launch_bounds__(kBaBlockThreads, 3) ba_blocks(const BaState* __restrict__ st, const int4* __restrict__ items,
+                                                                double* __restrict__ part,
+                                                                const double* __restrict__ X, const double* __restrict__ lin,
+                                                                const int* __restrict__ ocam, const int* __restrict__ opt,
+                                                                const int* __restrict__ pt_off, const int* __restrict__ cam_off,
+                                                                const int* __restrict__ cam_obs, const double* __restrict__ pblk,
+                                                                int n_fixed, int nF, double* __restrict__ S) {
+    if (st->done) return;
+    const int4 item = items[blockIdx.x];                    // (kf, lf, segment, segments of this block)
+    const int kf = item.x, lf = item.y;
     __shared__ double rec[kBaBlockThreads * kBaRec];
     __shared__ int wcount[kBaBlockThreads / 32 + 1];
     const int k = n_fixed + kf, l = n_fixed + lf;
@@ -175,71 +195,56 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks(const BaState* __re
     const int er = tid / 12, ec = tid % 12;                 // entry of the block owned by threads 0..143
     const int ea = er >> 2, eb = er & 3, ea2 = ec >> 2, eb2 = ec & 3;
     const int rz = tid - 144;                               // threads 144..155: right-hand side entry (a, b) = (rz/4, rz%4)
-    double acc = 0.0, accd = 0.0;
-    double Ck[12], Cl[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) { Ck[q] = cams[12 * (size_t)k + q]; Cl[q] = cams[12 * (size_t)l + q]; }
-    const int lo = cam_off[k], hi = cam_off[k + 1];
+    double acc = 0.0, accd = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const int lo = cam_off[k] + item.z * (kBaSegChunks * kBaBlockThreads);
+    const int hi = min(cam_off[k + 1], lo + kBaSegChunks * kBaBlockThreads);
     for (int base = lo; base < hi; base += kBaBlockThreads) {
         const int oi = base + tid;
         bool valid = false;
         double A[9], Xh[3], z[3], m00 = 0.0, m22 = 0.0;
         if (oi < hi) {
             const int o = cam_obs[oi], j = opt[o];
-            Xh[0] = X[3 * (size_t)j]; Xh[1] = X[3 * (size_t)j + 1]; Xh[2] = X[3 * (size_t)j + 2];
-            const double2 m = uv[o];
-            BaObs b;
-            ba_obs(Ck, Xh[0], Xh[1], Xh[2], m.x, m.y, b);
-            if (b.ok) {
-                double T[3][3], TV[3][3];
-                ba_T(b, T);
-                const double* pb = pblk + 12 * (size_t)j;
-                double Vi[6];
+            const int t0 = pt_off[j], t1 = pt_off[j + 1];
+            const double4* L = reinterpret_cast<const double4*>(lin + kBaLin * (size_t)o);
+            const double4 l0 = L[0], l1 = L[1], l2 = L[2];
+            const double T[3][3] = {{l0.x, l0.y, l0.z}, {l0.w, l1.x, l1.y}, {l1.z, l1.w, l2.x}};
+            const double* pb = pblk + 12 * (size_t)j;
+            double Vi[6], TV[3][3];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) Vi[q] = pb[q];
+            for (int q = 0; q < 6; ++q) Vi[q] = pb[q];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    TV[a][c] = T[a][0] * Vi[sym3(0, c)] + T[a][1] * Vi[sym3(1, c)] + T[a][2] * Vi[sym3(2, c)];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) A[q] = 0.0;
+            if (diag) {
+                const double i2 = l2.y, u = l2.z, v = l2.w;
+                const double4 l3 = L[3];
+                m00 = i2; m22 = (u * u + v * v) * i2;
+                A[0] = i2; A[4] = i2; A[8] = m22;
+                A[2] = A[6] = -u * i2;
+                A[5] = A[7] = -v * i2;
+                const double e0 = pb[6], e1 = pb[7], e2 = pb[8];        // z = P2^T r - T e_j
+                z[0] = l3.x - (T[0][0] * e0 + T[0][1] * e1 + T[0][2] * e2);
+                z[1] = l3.y - (T[1][0] * e0 + T[1][1] * e1 + T[1][2] * e2);
+                z[2] = l3.z - (T[2][0] * e0 + T[2][1] * e1 + T[2][2] * e2);
+                valid = true;
+            }
+            for (int o2 = t0; o2 < t1; ++o2) {
+                if (ocam[o2] != l) continue;
+                const double4* L2 = reinterpret_cast<const double4*>(lin + kBaLin * (size_t)o2);
+                const double4 p0 = L2[0], p1 = L2[1], p2 = L2[2];
+                const double T2[3][3] = {{p0.x, p0.y, p0.z}, {p0.w, p1.x, p1.y}, {p1.z, p1.w, p2.x}};
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        TV[a][c] = T[a][0] * Vi[sym3(0, c)] + T[a][1] * Vi[sym3(1, c)] + T[a][2] * Vi[sym3(2, c)];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) A[q] = 0.0;
-                if (diag) {
-                    const double i2 = b.iy * b.iy;
-                    m00 = i2; m22 = (b.u * b.u + b.v * b.v) * i2;
-                    A[0] = i2; A[4] = i2; A[8] = m22;
-                    A[2] = A[6] = -b.u * i2;
-                    A[5] = A[7] = -b.v * i2;
-                    // z = P2^T r - T e_j
-                    const double e0 = pb[6], e1 = pb[7], e2 = pb[8];
-                    z[0] = b.iy * b.r0 - (T[0][0] * e0 + T[0][1] * e1 + T[0][2] * e2);
-                    z[1] = b.iy * b.r1 - (T[1][0] * e0 + T[1][1] * e1 + T[1][2] * e2);
-                    z[2] = -(b.u * b.r0 + b.v * b.r1) * b.iy - (T[2][0] * e0 + T[2][1] * e1 + T[2][2] * e2);
-                    valid = true;
-                }
-                for (int o2 = pt_off[j]; o2 < pt_off[j + 1]; ++o2) {
-                    if (ocam[o2] != l) continue;
-                    double T2[3][3];
-                    if (o2 == o) {
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) T2[a][c] = T[a][c];
-                    } else {
-                        const double2 m2 = uv[o2];
-                        BaObs b2;
-                        ba_obs(Cl, Xh[0], Xh[1], Xh[2], m2.x, m2.y, b2);
-                        if (!b2.ok) continue;
-                        ba_T(b2, T2);
-                    }
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int a2 = 0; a2 < 3; ++a2)
-                            A[a * 3 + a2] -= TV[a][0] * T2[a2][0] + TV[a][1] * T2[a2][1] + TV[a][2] * T2[a2][2];
-                    valid = true;
-                }
+                    for (int a2 = 0; a2 < 3; ++a2)
+                        A[a * 3 + a2] -= TV[a][0] * T2[a2][0] + TV[a][1] * T2[a2][1] + TV[a][2] * T2[a2][2];
+                valid = true;
             }
+            if (valid) { Xh[0] = X[3 * (size_t)j]; Xh[1] = X[3 * (size_t)j + 1]; Xh[2] = X[3 * (size_t)j + 2]; }
         }
         // ordered compaction of the valid observations of this chunk
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -260,10 +265,30 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks(const BaState* __re
         __syncthreads();
         if (tid < 144) {
             const bool dd = diag && er == ec;
-            for (int i = 0; i < total; ++i) {
+            const int ia = ea * 3 + ea2, ib = eb < 3 ? 9 + eb : -1, ib2 = eb2 < 3 ? 9 + eb2 : -1;
+            int i = 0;
+            for (; i + 4 <= total; i += 4) {                 // four independent chains (fixed order: still reproducible)
                 const double* r = rec + i * kBaRec;
-                const double xb = eb < 3 ? r[9 + eb] : 1.0, xb2 = eb2 < 3 ? r[9 + eb2] : 1.0;
-                acc = fma(r[ea * 3 + ea2] * xb, xb2, acc);
+                const double xa0 = ib >= 0 ? r[ib] : 1.0, xa1 = ib >= 0 ? r[kBaRec + ib] : 1.0;
+                const double xa2 = ib >= 0 ? r[2 * kBaRec + ib] : 1.0, xa3 = ib >= 0 ? r[3 * kBaRec + ib] : 1.0;
+                const double xc0 = ib2 >= 0 ? r[ib2] : 1.0, xc1 = ib2 >= 0 ? r[kBaRec + ib2] : 1.0;
+                const double xc2 = ib2 >= 0 ? r[2 * kBaRec + ib2] : 1.0, xc3 = ib2 >= 0 ? r[3 * kBaRec + ib2] : 1.0;
+                acc = fma(r[ia] * xa0, xc0, acc);
+                acc1 = fma(r[kBaRec + ia] * xa1, xc1, acc1);
+                acc2 = fma(r[2 * kBaRec + ia] * xa2, xc2, acc2);
+                acc3 = fma(r[3 * kBaRec + ia] * xa3, xc3, acc3);
+                if (dd) {
+                    const int im = ea < 2 ? 15 : 16;
+                    accd = fma(r[im] * xa0, xa0, accd);
+                    accd = fma(r[kBaRec + im] * xa1, xa1, accd);
+                    accd = fma(r[2 * kBaRec + im] * xa2, xa2, accd);
+                    accd = fma(r[3 * kBaRec + im] * xa3, xa3, accd);
+                }
+            }
+            for (; i < total; ++i) {
+                const double* r = rec + i * kBaRec;
+                const double xb = ib >= 0 ? r[ib] : 1.0, xb2 = ib2 >= 0 ? r[ib2] : 1.0;
+                acc = fma(r[ia] * xb, xb2, acc);
                 if (dd) accd = fma((ea < 2 ? r[15] : r[16]) * xb, xb, accd);
             }
         } else if (diag && rz < 12) {
@@ -275,12 +300,51 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks(const BaState* __re
         }
         __syncthreads();
     }
+    acc = (acc + acc1) + (acc2 + acc3);
+    if (item.w > 1) {                                       // the block is split over several work items: partial sums
+        double* p = part + (size_t)blockIdx.x * kBaPart;
+        if (tid < 144) {
+            p[tid] = acc;
+            if (diag && er == ec) p[156 + er] = accd;
+        } else if (rz < 12) {
+            p[144 + rz] = diag ? acc : 0.0;
+        }
+        return;
+    }
     const size_t ld = (size_t)12 * nF + 1;
     if (tid < 144) {
         if (diag && er == ec) acc += lambda * accd;
         S[(size_t)(12 * kf + er) + (size_t)(12 * lf + ec) * ld] = acc;
     } else if (diag && rz < 12) {
         S[(size_t)12 * nF + (size_t)(12 * kf + rz) * ld] = acc;
+    }
+}
+
+// blocks that were split over several work items: sum the partials in segment order (reproducible), write the block
+__global__ void __launch_bounds__(kBaBlockThreads) ba_blocks_reduce(const BaState* __restrict__ st, const int4* __restrict__ items,
+                                                                    const int* __restrict__ first_item, int n_blocks,
+                                                                    const double* __restrict__ part, int nF,
+                                                                    double* __restrict__ S) {
+    if (st->done) return;
+    const int f = first_item[blockIdx.x];
+    const int4 item = items[f];
+    if (item.w <= 1) return;                                // written directly by ba_blocks
+    const int kf = item.x, lf = item.y, tid = threadIdx.x;
+    const bool diag = kf == lf;
+    const size_t ld = (size_t)12 * nF + 1;
+    if (tid < 144) {
+        const int er = tid / 12, ec = tid % 12;
+        double a = 0.0, d = 0.0;
+        for (int s = 0; s < item.w; ++s) {
+            a += part[(size_t)(f + s) * kBaPart + tid];
+            if (diag && er == ec) d += part[(size_t)(f + s) * kBaPart + 156 + er];
+        }
+        if (diag && er == ec) a += st->lambda * d;
+        S[(size_t)(12 * kf + er) + (size_t)(12 * lf + ec) * ld] = a;
+    } else if (diag && tid < 156) {
+        double a = 0.0;
+        for (int s = 0; s < item.w; ++s) a += part[(size_t)(f + s) * kBaPart + tid];
+        S[(size_t)12 * nF + (size_t)(12 * kf + (tid - 144)) * ld] = a;
     }
 }
 
@@ -695,7 +759,8 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
                                                             const double* __restrict__ dC, const double* __restrict__ X,
                                                             double* __restrict__ Xtrial, const double2* __restrict__ uv,
                                                             const int* __restrict__ ocam, const int* __restrict__ pt_off, int nP,
-                                                            const double* __restrict__ pblk, double* __restrict__ trial_part) {
+                                                            const double* __restrict__ pblk, const double* __restrict__ lin,
+                                                            double* __restrict__ trial_part) {
     __shared__ double sh[kBaPointThreads / 32];
     if (st->done || st->accepted < 0) return;
     double cost = 0.0;
@@ -705,20 +770,17 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
         double back[3] = {0, 0, 0};
         const int lo = pt_off[j], hi = pt_off[j + 1];
         for (int o = lo; o < hi; ++o) {
-            const size_t k = (size_t)ocam[o];
-            const double* d = dC + 12 * k;
+            const double* d = dC + 12 * (size_t)ocam[o];
             double q[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) q[a] = d[4 * a] * X0 + d[4 * a + 1] * X1 + d[4 * a + 2] * X2 + d[4 * a + 3];
             if (q[0] == 0.0 && q[1] == 0.0 && q[2] == 0.0) continue;             // fixed view
-            BaObs b;
-            const double2 m = uv[o];
-            ba_obs(cams + 12 * k, X0, X1, X2, m.x, m.y, b);
-            if (!b.ok) continue;
-            double T[3][3];
-            ba_T(b, T);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) back[c] += T[0][c] * q[0] + T[1][c] * q[1] + T[2][c] * q[2];
+            const double4* L = reinterpret_cast<const double4*>(lin + kBaLin * (size_t)o);   // T of ba_points (zero if skipped)
+            const double4 l0 = L[0], l1 = L[1];
+            const double t22 = L[2].x;
+            back[0] += l0.x * q[0] + l0.w * q[1] + l1.z * q[2];
+            back[1] += l0.y * q[0] + l1.x * q[1] + l1.w * q[2];
+            back[2] += l0.z * q[0] + l1.y * q[1] + t22 * q[2];
         }
         const double r0 = pb[9] - back[0], r1 = pb[10] - back[1], r2 = pb[11] - back[2];
         const double n0 = X0 + pb[0] * r0 + pb[1] * r1 + pb[2] * r2;
@@ -726,14 +788,13 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
         const double n2 = X2 + pb[2] * r0 + pb[4] * r1 + pb[5] * r2;
         Xtrial[3 * (size_t)j] = n0; Xtrial[3 * (size_t)j + 1] = n1; Xtrial[3 * (size_t)j + 2] = n2;
         for (int o = lo; o < hi; ++o) {
+            if (lin[kBaLin * (size_t)o + 9] == 0.0) continue;                  // skipped in the linearisation: skipped here
             const size_t k = (size_t)ocam[o];
             double Cn[12];
 #pragma unroll
             for (int q = 0; q < 12; ++q) Cn[q] = cams[12 * k + q] + dC[12 * k + q];
             const double2 m = uv[o];
-            BaObs b, t;
-            ba_obs(cams + 12 * k, X0, X1, X2, m.x, m.y, b);
-            if (!b.ok) continue;                                               // skipped in the linearisation: skipped here
+            BaObs t;
             ba_obs(Cn, n0, n1, n2, m.x, m.y, t);
             cost += t.ok ? t.r0 * t.r0 + t.r1 * t.r1 : INFINITY;
         }

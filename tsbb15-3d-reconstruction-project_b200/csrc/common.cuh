@@ -164,6 +164,7 @@ struct Ctx {
     Buffer ba_ws;                                  // bundle adjustment: state, step, trial points, point blocks, camera system
     int opt_ba_cluster = 0;                        // option 3: CTAs in the cluster of the camera-system factorisation (0 = 8)
     int opt_ba_l2 = 0;                             // option 4: 1 = keep the camera system in L2 (ba_solve) even when it fits in DSMEM
+    Buffer h_ba_items;                             // pinned: work items of ba_blocks (blocks with a common point x segments)
     Buffer h_ba_flags;                             // pinned: the solver's `done` flag after every iteration (host entry point)
     cudaEvent_t ba_iter_ev[2] = {nullptr, nullptr};
     bool ba_attr_set = false;                      // dynamic shared memory limit of ba_solve raised on this device

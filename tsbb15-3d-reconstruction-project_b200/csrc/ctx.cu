@@ -110,6 +110,7 @@ int rg_shutdown(void* ctx) {
     release_pinned(c->h_stage);
     release_pinned(c->h_stats);
     release_pinned(c->h_ba_flags);
+    release_pinned(c->h_ba_items);
     for (int i = 0; i < 2; ++i)
         if (c->ba_iter_ev[i]) cudaEventDestroy(c->ba_iter_ev[i]);
     if (c->prof_ev) {
