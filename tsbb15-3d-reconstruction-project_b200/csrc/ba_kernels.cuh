@@ -356,13 +356,16 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks_reduce(const BaStat
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool ba_chol12(double* __restrict__ Ld, double* __restrict__ Li, double* __restrict__ cb,
                                           const int lane) {
-    double a[12];
+    double a[12], dg[12];                                       // own row; every lane's copy of the remaining diagonal
 #pragma unroll
-    for (int c = 0; c < 12; ++c) a[c] = (lane < 12 && c <= lane) ? Ld[lane * 12 + c] : 0.0;
+    for (int c = 0; c < 12; ++c) {
+        a[c] = (lane < 12 && c <= lane) ? Ld[lane * 12 + c] : 0.0;
+        dg[c] = Ld[c * 12 + c];
+    }
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        const double d = dg[j];                                 // kept up to date below: no shuffle on the critical chain
         ok = ok && d > 0.0 && isfinite(d);                      // no early exit: the loop stays fully unrolled
         const double inv = rsqrt(d);
         if (lane == j) { a[j] = d * inv; Li[j] = inv; }
@@ -371,8 +374,12 @@ __device__ __forceinline__ bool ba_chol12(double* __restrict__ Ld, double* __res
         if (lane > j && lane < 12) col[lane] = a[j];
         __syncwarp();
 #pragma unroll
-        for (int c = j + 1; c < 12; ++c)
-            if (lane >= c) a[c] = fma(-a[j], col[c], a[c]);     // L[lane][c] -= L[lane][j] L[c][j]
+        for (int c = j + 1; c < 12; ++c) {
+            const double t = col[c];                            // L[c][j]
+            if (lane > c) a[c] = fma(-a[j], t, a[c]);           // L[lane][c] -= L[lane][j] L[c][j]
+            dg[c] = fma(-t, t, dg[c]);
+            if (lane == c) a[c] = dg[c];                        // the diagonal entry of the own row: same value in every lane
+        }
     }
     if (ok && lane < 12) {
 #pragma unroll
