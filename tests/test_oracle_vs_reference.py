@@ -113,3 +113,24 @@ def test_geom_oracle_matches_reference_functions(ref_lab3, dino):
         K, R, t = fun.camera_resectioning(Ps[k])
         Ko, Ro, to = og.camera_resectioning(Ps[k])
         assert np.allclose(K, Ko) and np.allclose(R, Ro) and np.allclose(t, to)
+
+
+def test_package_data_loaders_match_reference(rg, dino):
+    """fun.getCameraMatrices / correspondences.Correspondences (main.py:24-30): same arrays as the reference's loaders."""
+    import os
+    from oracle import _refimport as ri
+    if not ri.reference_available():
+        pytest.skip("reference tree not mounted")
+    path = os.path.join(ri.REFERENCE_DIR, "BAdino2.mat")
+    C = rg.fun.getCameraMatrices(path)
+    assert C.shape == (1, 36, 3, 4) and np.array_equal(C[0], dino["Ps"])
+    c = rg.correspondences.Correspondences(path)
+    ref_fun = ri.import_reference("fun")
+    with ri.reference_cwd():
+        rc = ref_fun.Correspondences()
+        assert np.array_equal(ref_fun.getCameraMatrices(), C)
+    for i1, i2 in ((0, 1), (7, 8), (34, 35), (3, 10)):
+        a, b = c.getCorrByIndices(i1, i2)
+        ra, rb = rc.getCorrByIndices(i1, i2)
+        assert np.array_equal(a, ra) and np.array_equal(b, rb)
+    assert rg.fun.Correspondences is rg.correspondences.Correspondences

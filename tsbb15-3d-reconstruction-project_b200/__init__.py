@@ -8,11 +8,12 @@ from . import _cabi, runtime, sampling  # noqa: F401
 from ._cabi import (MODE_EPI_MAX, MODE_SAMPSON, RGError, SCORE_FP32_GUARDED, SCORE_FP64, SOLVER_JACOBI, SOLVER_QR,  # noqa: F401
                     TIE_FIRST, TIE_REFERENCE, TRI_LINEAR, TRI_OPTIMAL)
 
-__all__ = ["runtime", "sampling", "lab3", "fun", "ransac", "pnp", "tables", "help_classes", "batched", "parallel", "synth"]
+__all__ = ["runtime", "sampling", "lab3", "fun", "ransac", "pnp", "tables", "help_classes", "correspondences", "batched",
+           "parallel", "synth"]
 
 
 def __getattr__(name):
-    if name in ("lab3", "fun", "ransac", "pnp", "tables", "help_classes", "batched", "parallel", "synth"):
+    if name in ("lab3", "fun", "ransac", "pnp", "tables", "help_classes", "correspondences", "batched", "parallel", "synth"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -14,6 +14,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import lab3
+from .correspondences import Correspondences  # noqa: F401  (fun.Correspondences, main.py:28)
 from . import runtime as _rt
 from . import sampling as _sampling
 from ._cabi import MODE_EPI_MAX, SCORE_FP32_GUARDED, SOLVER_QR, TIE_FIRST, TIE_REFERENCE
@@ -47,6 +48,12 @@ def camera_resectioning(C):
         raise ValueError('C must be a (3, 4) camera matrix')
     K, R, t = _rt.camera_resectioning(C)
     return K[0], R[0], t[0]
+
+
+def getCameraMatrices(path='BAdino2.mat'):
+    """fun.py:75-89: the (1, 36, 3, 4) camera array of BAdino2.mat (read from the working directory like the reference)."""
+    import scipy.io as sio
+    return np.asarray(sio.loadmat(path)['newPs'].tolist())
 
 
 def reshapeToCamera3DPoints2(x0, n_C, n_P):
