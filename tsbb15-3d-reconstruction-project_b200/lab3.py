@@ -10,7 +10,8 @@ Next to the hot path — CUDA as well, one thread 
     fmatrix_from_cameras(C1, C2)          reference lab3.py:331-351
 
 Host-side helpers kept in numpy because they run once per image pair inside SciPy's Levenberg-Marquardt callback of
-the gold-standard refinement (fun.py:342-369; SURVEY.md section 8f row N4, not built): homog, project, cross_matrix,
+the gold-standard refinement when it runs on the host as in the reference (fun.py:342-369, `refine=True`; the device
+version of that stage is fun.gold_standard_device): homog, project, cross_matrix,
 fmatrix_cameras, fmatrix_epipoles, fmatrix_residuals_gs.  Same names, argument layouts, return shapes and errors.
 """
 from __future__ import annotations
