@@ -545,7 +545,9 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict_
 // panel in place and publishes the solved panel (<= 39 KB) through a double-buffered global array (L2; pushing it with
 // st.shared::cluster was measured no faster than the L2 variant: DSMEM moves ~20 B/clk per SM); one cluster barrier;
 // every CTA copies the panel into its shared memory and updates the block columns it owns there, 4 x 6 elements per
-// thread in registers (the update is shared-memory-bandwidth bound otherwise: 2 loads per FMA).  The backward
+// thread in registers (the update is shared-memory-bandwidth bound otherwise: 2 loads per FMA).  Look-ahead: the owner of
+// the NEXT block column updates that column first, factorises it, publishes its panel and arrives at the barrier before
+// it updates the rest of its columns (barrier.cluster.arrive / .wait split).  The backward
 // substitution walks the owners in reverse: dot products with the local block column, 12x12 back-solve by one thread,
 // the 12 new unknowns pushed to every CTA's copy of x through distributed shared memory, one barrier per block.
 // Same operations in the same order as ba_solve: bit-identical results.
@@ -606,51 +608,109 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve_dsmem(BaState* __res
     BA_T(0);
     size_t own_off = 0;                                     // first own block column that is not factorised yet
     int own_kb = rank;
-    for (int kb = 0; kb < nF; ++kb) {
+
+    // the owner's part of step kb: factorise the diagonal block, solve the panel in place, publish it through L2
+    auto factor_and_publish = [&](const int kb) {
         const int j0 = 12 * kb, h = rows - j0;
         double* Pgb = Pg + (size_t)(kb & 1) * 12 * rows;
-        if (rank == kb % nr) {
-            double* B = cols + own_off;
+        double* B = cols + own_off;
+        if (tid < 144) {
+            const int r = tid / 12, c = tid % 12;
+            Ld[tid] = r >= c ? B[c * h + r] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0 && !ba_chol12(Ld, Li, cb, lane) && lane < nr) *cluster.map_shared_rank(&fail, lane) = 1;
+        __syncthreads();
+        if (!fail) {
             if (tid < 144) {
                 const int r = tid / 12, c = tid % 12;
-                Ld[tid] = r >= c ? B[c * h + r] : 0.0;
+                if (r >= c) B[c * h + r] = Ld[tid];
+                if (r == c) linv[12 * (kb / nr) + r] = Li[r];
             }
-            __syncthreads();
-            if (warp == 0 && !ba_chol12(Ld, Li, cb, lane) && lane < nr) *cluster.map_shared_rank(&fail, lane) = 1;
-            __syncthreads();
-            BA_T(1);
-            if (!fail) {
-                if (tid < 144) {
-                    const int r = tid / 12, c = tid % 12;
-                    if (r >= c) B[c * h + r] = Ld[tid];
-                    if (r == c) linv[12 * (kb / nr) + r] = Li[r];
+            for (int r = 12 + tid; r < h; r += blockDim.x) {
+                double x[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) x[c] = B[c * h + r];
+                ba_panel_row(x, Ld, Li);
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    B[c * h + r] = x[c];
+                    __stcg(&Pgb[c * rows + j0 + r], x[c]);
                 }
-                for (int r = 12 + tid; r < h; r += blockDim.x) {
-                    double x[12];
+                if (r == h - 1) {                           // the right-hand-side row: y = L^-1 rhs, final for these 12 entries
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) x[c] = B[c * h + r];
-                    ba_panel_row(x, Ld, Li);
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        B[c * h + r] = x[c];
-                        __stcg(&Pgb[c * rows + j0 + r], x[c]);
-                    }
-                    if (r == h - 1) {                       // the right-hand-side row: y = L^-1 rhs, final for these 12 entries
-#pragma unroll
-                        for (int c = 0; c < 12; ++c) y[j0 + c] = x[c];
-                    }
+                    for (int c = 0; c < 12; ++c) y[j0 + c] = x[c];
                 }
             }
-            own_off += (size_t)12 * h;
-            own_kb += nr;
-#ifdef RG_BA_PROF
-            __syncthreads();
-#endif
-            BA_T(2);
         }
-        cluster.sync();
+        own_off += (size_t)12 * h;
+        own_kb += nr;
+    };
+
+    // trailing update of the own block columns kb_first, kb_first + nr, ... (at most n_cols of them) with the panel in Pn:
+    // tiles of 4 rows x 6 columns, numbered across the block columns so that every warp has work
+    auto update_columns = [&](const int kb_first, const size_t off_first, const int n_cols) {
+        int total = 0, ncol = 0;
+        for (int kb2 = kb_first; kb2 < nF && ncol < n_cols; kb2 += nr, ++ncol) total += 2 * ((rows - 12 * kb2 + 3) >> 2);
+        for (int t0 = tid; t0 < total; t0 += blockDim.x) {
+            int t = t0, kb2 = kb_first;
+            size_t off2 = off_first;
+            for (;;) {
+                const int nt = 2 * ((rows - 12 * kb2 + 3) >> 2);
+                if (t < nt) break;
+                t -= nt;
+                off2 += (size_t)12 * (rows - 12 * kb2);
+                kb2 += nr;
+            }
+            const int j2 = 12 * kb2, h2 = rows - j2;
+            double* B2 = cols + off2;
+            const int ntr = (h2 + 3) >> 2;                  // row groups: thread rows tr, tr + ntr, tr + 2 ntr, tr + 3 ntr
+            const int cgp = t >= ntr ? 1 : 0, tr = t - cgp * ntr, c0 = 6 * cgp;
+            int rq[4];
+            bool vq[4];
+            double acc[4][6];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rq[q] = tr + q * ntr;
+                vq[q] = rq[q] < h2;
+                if (!vq[q]) rq[q] = h2 - 1;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc[q][k] = B2[(c0 + k) * h2 + rq[q]];
+            }
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const double* Pc = Pn + c * rows + j2;
+                double pi[4], pj[6];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pi[q] = Pc[rq[q]];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) pj[k] = Pc[c0 + k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc[q][k] = fma(-pi[q], pj[k], acc[q][k]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (vq[q]) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) B2[(c0 + k) * h2 + rq[q]] = acc[q][k];
+                }
+        }
+    };
+
+    // Look-ahead: in step kb the owner of block column kb + 1 updates that column first, factorises it and publishes
+    // panel kb + 1, ARRIVES at the cluster barrier and only then updates the rest of its columns; the other CTAs arrive
+    // after their own update.  The pivot chain (copy, column update, factor, panel, barrier) no longer waits for anybody's
+    // bulk update.
+    if (rank == 0 && nF > 0) factor_and_publish(0);
+    BA_T(1);
+    cluster.sync();
+    for (int kb = 0; kb < nF; ++kb) {
+        if (fail) break;                                    // set by the owner before its arrive: uniform after the wait
         BA_T(3);
-        if (fail) break;
+        const int j0 = 12 * kb;
+        const double* Pgb = Pg + (size_t)(kb & 1) * 12 * rows;
         if (own_kb < nF) {                                  // something left to update in this CTA
             for (int i = j0 + 12 + tid; i < rows; i += blockDim.x) {        // 12 independent L2 loads per thread
                 double v[12];
@@ -660,57 +720,24 @@ __global__ void __launch_bounds__(kBaSolveThreads) ba_solve_dsmem(BaState* __res
                 for (int c = 0; c < 12; ++c) Pn[c * rows + i] = v[c];
             }
             __syncthreads();
-            BA_T(4);
-            // tiles of 4 rows x 6 columns, numbered across all own block columns so that every warp has work
-            int total = 0;
-            for (int kb2 = own_kb; kb2 < nF; kb2 += nr) total += 2 * ((rows - 12 * kb2 + 3) >> 2);
-            for (int t0 = tid; t0 < total; t0 += blockDim.x) {
-                int t = t0, kb2 = own_kb;
-                size_t off2 = own_off;
-                for (;;) {
-                    const int nt = 2 * ((rows - 12 * kb2 + 3) >> 2);
-                    if (t < nt) break;
-                    t -= nt;
-                    off2 += (size_t)12 * (rows - 12 * kb2);
-                    kb2 += nr;
-                }
-                const int j2 = 12 * kb2, h2 = rows - j2;
-                double* B2 = cols + off2;
-                const int ntr = (h2 + 3) >> 2;              // row groups: thread rows tr, tr + ntr, tr + 2 ntr, tr + 3 ntr
-                const int cgp = t >= ntr ? 1 : 0, tr = t - cgp * ntr, c0 = 6 * cgp;
-                int rq[4];
-                bool vq[4];
-                double acc[4][6];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    rq[q] = tr + q * ntr;
-                    vq[q] = rq[q] < h2;
-                    if (!vq[q]) rq[q] = h2 - 1;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) acc[q][k] = B2[(c0 + k) * h2 + rq[q]];
-                }
-#pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    const double* Pc = Pn + c * rows + j2;
-                    double pi[4], pj[6];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pi[q] = Pc[rq[q]];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) pj[k] = Pc[c0 + k];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) acc[q][k] = fma(-pi[q], pj[k], acc[q][k]);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (vq[q]) {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) B2[(c0 + k) * h2 + rq[q]] = acc[q][k];
-                    }
-            }
+        }
+        BA_T(4);
+        if (kb + 1 < nF && rank == (kb + 1) % nr) {         // own_kb == kb + 1
+            update_columns(own_kb, own_off, 1);
+            __syncthreads();
+            factor_and_publish(kb + 1);
+            BA_T(2);
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            update_columns(own_kb, own_off, 1 << 30);
             __syncthreads();
             BA_T(5);
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            update_columns(own_kb, own_off, 1 << 30);
+            __syncthreads();
+            BA_T(5);
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         }
     }
     const bool bad = fail != 0;
