@@ -30,7 +30,7 @@ static int f_workspace(Ctx* c, const FPlan& plan) {
     if ((rc = ensure(c->F64, sizeof(double) * 9 * H))) return rc;
     if ((rc = ensure(c->hyp32, sizeof(Hyp32) * H))) return rc;
     if ((rc = ensure(c->flags, H))) return rc;
-    if ((rc = ensure(c->counts, sizeof(int) * H))) return rc;
+    if ((rc = ensure(c->counts, sizeof(int) * (H + 1)))) return rc;      // + the scorer's work counter
     if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
     if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure(c->tie_stats, sizeof(double2) * H))) return rc;
@@ -63,7 +63,7 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     int* counts = (int*)c->counts.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)std::max<long long>(plan.Htot, 1), st));
+    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)std::max<long long>(plan.Htot, 1) + 1), st));   // counts + work counter
     if (!c->accumulate_stats) RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
     if (plan.Htot == 0 || plan.Ntot == 0) return RG_OK;
     if (score_path == SCORE_FP32_GUARDED) {
@@ -72,7 +72,7 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
             const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<EpiPolicy<MODE>>());
             score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>(
                 (const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr, pi, plan.P, plan.n_items, counts,
-                (unsigned*)c->bitmap.ptr);
+                (unsigned*)c->bitmap.ptr, counts + std::max<long long>(plan.Htot, 1));
             prof_mark(c, st, 3);
             const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
                                                                               (plan.total_words + 255) / 256));

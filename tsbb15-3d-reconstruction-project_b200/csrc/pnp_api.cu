@@ -55,7 +55,7 @@ static int pnp_workspace(Ctx* c, const FPlan& plan) {
     if ((rc = ensure(c->pose64, sizeof(double) * 12 * H))) return rc;
     if ((rc = ensure(c->pose32, sizeof(Pose32) * H))) return rc;
     if ((rc = ensure(c->flags, H))) return rc;
-    if ((rc = ensure(c->counts, sizeof(int) * H))) return rc;
+    if ((rc = ensure(c->counts, sizeof(int) * (H + 1)))) return rc;      // + the scorer's work counter
     if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
     if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
@@ -67,7 +67,7 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
                             int score_path) {
     int* counts = (int*)c->counts.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)std::max<long long>(plan.Htot, 1), st));
+    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)std::max<long long>(plan.Htot, 1) + 1), st));   // counts + work counter
     RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
     if (plan.Htot == 0) return RG_OK;
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
@@ -77,7 +77,8 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
             const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<PnpPolicy>());
             score_packed<PnpPolicy><<<grid, kScoreThreads, smem, st>>>((const float4*)c->X32.ptr, (const Pose32*)c->pose32.ptr,
                                                                       pi, plan.P, plan.n_items, counts,
-                                                                      (unsigned*)c->bitmap.ptr);
+                                                                      (unsigned*)c->bitmap.ptr,
+                                                                      counts + std::max<long long>(plan.Htot, 1));
             prof_mark(c, st, 3);
             const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
                                                                               (plan.total_words + 255) / 256));

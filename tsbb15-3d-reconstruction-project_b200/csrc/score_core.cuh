@@ -90,15 +90,18 @@ struct __align__(128) ScoreStage {
 template <class Pol>
 constexpr size_t score_smem_bytes() { return kStages * sizeof(ScoreStage<Pol>) + 64; }
 
-// persistent block: items blockIdx.x, blockIdx.x + gridDim.x, ...; every item = 512 hypotheses x a contiguous
-// range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1 hypothesis.
+// persistent block: first item blockIdx.x, then items claimed from a global counter (dynamic: with static round-robin a
+// batch whose item count is not a multiple of the grid leaves most SMs idle during the last round); every item = 512
+// hypotheses x a contiguous range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1
+// hypothesis; *work_counter is 0 at launch.
 // Points and (at the first chunk of an item) hypothesis records arrive by 1-D bulk TMA on one mbarrier per stage;
 // the next chunk / next item is always in flight while the current one is being scored.
 template <class Pol>
 __global__ void __launch_bounds__(kScoreThreads, kScoreBlocksPerSM)
 score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restrict__ hyp32,
              const PairInfo* __restrict__ pi, int P, int n_items, int* __restrict__ counts,
-             unsigned* __restrict__ bitmap) {
+             unsigned* __restrict__ bitmap, int* __restrict__ work_counter) {
+    __shared__ int s_next;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScoreStage<Pol>* st = reinterpret_cast<ScoreStage<Pol>*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(ScoreStage<Pol>));
@@ -131,7 +134,10 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
     }
 
     while (true) {
-        const int next_item = item + gridDim.x;
+        // claim the following item now: its first chunk and hypotheses are prefetched during the last chunk of this one
+        if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work_counter, 1);
+        __syncthreads();                  // (the previous value was read by everybody before the last chunk's barrier)
+        const int next_item = s_next;
         const bool has_next = next_item < n_items;
         ScoreItem nxt = cur;
         const float4* nxt_src = cur_src;
