@@ -224,10 +224,30 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     if ((rc = ensure(c->d_out_b, sizeof(double) * 9 * (size_t)P))) return rc;
     if (mask && (rc = ensure(c->d_out_c, std::max<size_t>(Ntot, 1)))) return rc;
 
-    // sub-batches: automatic = two once the input is worth hiding (>= 8 MB): every sub-batch pays the small prepare / solve /
-    // select kernels again (~0.14 ms), so more than two only costs (measured: 1 -> 5.11, 2 -> 4.85, 3 -> 4.93, 4 -> 4.99 ms)
-    const size_t in_bytes = Ntot * 32 + Htot * 32;
-    int S = c->opt_host_slices > 0 ? c->opt_host_slices : (in_bytes >= (8u << 20) ? 2 : 1);
+    // sub-batches.  Every sub-batch pays the small prepare / solve / select kernels again (~0.15 ms), so the automatic choice
+    // is two — the first one the smallest whose scoring time covers the upload of everything after it (model: 1.5e12
+    // evaluations/s against a 50 GB/s host link), at most half of the pairs — and only when the upload time it hides
+    // exceeds that fixed cost (measured on the config-5 batch: 1 -> 5.11, 2 -> 4.80, 3 -> 4.90, 4 -> 4.99 ms; the Dino
+    // sequence, 35 small pairs, stays monolithic).
+    int first = 1;
+    double hidden_s = 0.0;
+    {
+        double score_s = 0.0;
+        for (first = 1; first < P; ++first) {
+            const double n = pair_off[first] - pair_off[first - 1], h = hyp_off[first] - hyp_off[first - 1];
+            score_s += n * h / 1.5e12;
+            const double rest_bytes = 32.0 * ((double)(pair_off[P] - pair_off[first]) + (double)(hyp_off[P] - hyp_off[first]));
+            if (score_s >= rest_bytes / 5.0e10) break;
+        }
+        first = std::max(1, std::min(first, std::max(1, P / 2)));
+        double sc = 0.0;
+        for (int q = 0; q < first && q < P; ++q)
+            sc += (double)(pair_off[q + 1] - pair_off[q]) * (double)(hyp_off[q + 1] - hyp_off[q]) / 1.5e12;
+        const double rest_bytes = P > 0 ? 32.0 * ((double)(pair_off[P] - pair_off[std::min(first, P)]) +
+                                                  (double)(hyp_off[P] - hyp_off[std::min(first, P)])) : 0.0;
+        hidden_s = std::min(sc, rest_bytes / 5.0e10);
+    }
+    int S = c->opt_host_slices > 0 ? c->opt_host_slices : (hidden_s > 1.5e-4 ? 2 : 1);
     S = std::max(1, std::min(std::min(S, P), (int)Ctx::kMaxSlices));
     if (c->opt_profile) S = 1;                       // phase events describe one monolithic call
     if (S > 1) {
@@ -242,19 +262,6 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     if (S == 1) {
         bounds[1] = P;
     } else {
-        // smallest first sub-batch whose scoring time covers the upload of everything after it (model: 1.5e12 evaluations/s,
-        // 50 GB/s host link), at most half of the pairs
-        int first = 1;
-        {
-            double score_s = 0.0;
-            for (first = 1; first < P; ++first) {
-                const double n = pair_off[first] - pair_off[first - 1], h = hyp_off[first] - hyp_off[first - 1];
-                score_s += n * h / 1.5e12;
-                const double rest_bytes = 32.0 * ((double)(pair_off[P] - pair_off[first]) + (double)(hyp_off[P] - hyp_off[first]));
-                if (score_s >= rest_bytes / 5.0e10) break;
-            }
-            first = std::max(1, std::min(first, std::max(1, P / 2)));
-        }
         for (int k = 1; k <= S; ++k) bounds[k] = first + (int)((long long)(P - first) * (k - 1) / (S - 1));
     }
     double* d_pts = (double*)c->d_in_a.ptr;
