@@ -118,7 +118,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
 
     // ---- workspace ---------------------------------------------------------------------------------------------------
     const int n = 12 * nF;
-    const int nparts = std::max(1, std::min(1024, ceil_div(std::max(nP, 1), kBaPointThreads)));
+    const int nparts = std::max(1, std::min(1024, ceil_div(std::max(nP, 1), kBaPointThreads / kBaPointLanes)));
     const size_t s_elems = (size_t)(n + 1) * (size_t)std::max(n, 1);
     const size_t bytes = sizeof(BaState) + 64 + sizeof(double) * ((size_t)12 * std::max(nC, 1) + (size_t)3 * nP + (size_t)2 * nO +
                                                                   (size_t)12 * nP + (size_t)kBaLin * nO + (any_split ? (size_t)kBaPart * n_items : 0) + s_elems + (size_t)24 * (n + 1) + (size_t)n + (size_t)3 * nparts + 8) +

@@ -22,6 +22,7 @@ namespace rg {
 namespace cg = cooperative_groups;
 
 constexpr int kBaPointThreads = 128;
+constexpr int kBaPointLanes = 8;          // lanes that share one point in ba_points / ba_trial (one observation of the track each)
 constexpr int kBaBlockThreads = 192;      // chunk of observations per pass; threads 0..143 own the 12x12 entries
 constexpr int kBaRec = 17;                // doubles per staged observation: A (9) | X (3) | z (3) | M00, M22
 constexpr int kBaSegChunks = 2;            // chunks of kBaBlockThreads observations per work item of ba_blocks
@@ -89,7 +90,8 @@ __device__ __forceinline__ double ba_block_sum(double v, double* sh) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// step 1 (thread per point): commit an accepted trial, V_j, g_j, damped inverse, e_j = V'^-1 g_j, cost partials
+// step 1 (kBaPointLanes lanes per point): commit an accepted trial, linearise the track, V_j, g_j, damped inverse,
+// e_j = V'^-1 g_j, cost partials
 // observations are stored sorted by point: the track of point j is [pt_off[j], pt_off[j+1])
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict__ st, const double* __restrict__ cams,
@@ -105,16 +107,25 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
     const bool first = st->have_cost == 0;                  // first linearisation: also sum |uv|^2 for the rounding floor
     double cost = 0.0, obs2 = 0.0;
     int bad = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nP; j += gridDim.x * blockDim.x) {
-        double X0, X1, X2;
-        if (commit) {
-            X0 = Xtrial[3 * (size_t)j]; X1 = Xtrial[3 * (size_t)j + 1]; X2 = Xtrial[3 * (size_t)j + 2];
-            X[3 * (size_t)j] = X0; X[3 * (size_t)j + 1] = X1; X[3 * (size_t)j + 2] = X2;
-        } else {
-            X0 = X[3 * (size_t)j]; X1 = X[3 * (size_t)j + 1]; X2 = X[3 * (size_t)j + 2];
+    // kBaPointLanes lanes per point: lane t of the group takes observations t, t + kBaPointLanes, ... of the track; the
+    // 3x3 block and the gradient are reduced inside the group by a fixed xor-shuffle tree (reproducible)
+    const int sub = threadIdx.x & (kBaPointLanes - 1);
+    const int gpb = blockDim.x / kBaPointLanes;                               // groups per block
+    const int npad = ((nP + gpb - 1) / gpb) * gpb;                            // whole warps stay together in the shuffles
+    for (int j = blockIdx.x * gpb + threadIdx.x / kBaPointLanes; j < npad; j += gridDim.x * gpb) {
+        const bool real = j < nP;
+        double X0 = 0.0, X1 = 0.0, X2 = 1.0;
+        if (real) {
+            if (commit) {
+                X0 = Xtrial[3 * (size_t)j]; X1 = Xtrial[3 * (size_t)j + 1]; X2 = Xtrial[3 * (size_t)j + 2];
+                if (sub == 0) { X[3 * (size_t)j] = X0; X[3 * (size_t)j + 1] = X1; X[3 * (size_t)j + 2] = X2; }
+            } else {
+                X0 = X[3 * (size_t)j]; X1 = X[3 * (size_t)j + 1]; X2 = X[3 * (size_t)j + 2];
+            }
         }
         double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-        for (int o = pt_off[j]; o < pt_off[j + 1]; ++o) {
+        const int t0 = real ? pt_off[j] : 0, t1 = real ? pt_off[j + 1] : 0;
+        for (int o = t0 + sub; o < t1; o += kBaPointLanes) {
             BaObs b;
             const double2 m = uv[o];
             ba_obs(cams + 12 * (size_t)ocam[o], X0, X1, X2, m.x, m.y, b);
@@ -142,19 +153,28 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_points(BaState* __restrict
             cost += b.r0 * b.r0 + b.r1 * b.r1;
             obs2 += m.x * m.x + m.y * m.y;
         }
-        V[0] += lambda * V[0]; V[3] += lambda * V[3]; V[5] += lambda * V[5];        // Marquardt scaling
-        double Vi[6];
-        if (!inv_sym3(V, Vi)) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) Vi[k] = 0.0;                                  // unobserved / degenerate point: not moved
+        for (int o = kBaPointLanes / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) V[k] += __shfl_xor_sync(0xffffffffu, V[k], o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
         }
-        double* pb = pblk + 12 * (size_t)j;
+        if (real && sub == 0) {
+            V[0] += lambda * V[0]; V[3] += lambda * V[3]; V[5] += lambda * V[5];        // Marquardt scaling
+            double Vi[6];
+            if (!inv_sym3(V, Vi)) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) pb[k] = Vi[k];
+                for (int k = 0; k < 6; ++k) Vi[k] = 0.0;                              // unobserved / degenerate point: not moved
+            }
+            double* pb = pblk + 12 * (size_t)j;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            pb[6 + a] = Vi[sym3(a, 0)] * g[0] + Vi[sym3(a, 1)] * g[1] + Vi[sym3(a, 2)] * g[2];
-            pb[9 + a] = g[a];
+            for (int k = 0; k < 6; ++k) pb[k] = Vi[k];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pb[6 + a] = Vi[sym3(a, 0)] * g[0] + Vi[sym3(a, 1)] * g[1] + Vi[sym3(a, 2)] * g[2];
+                pb[9 + a] = g[a];
+            }
         }
     }
     const double s = ba_block_sum(cost, sh);
@@ -787,7 +807,7 @@ __global__ void ba_solve_none(BaState* __restrict__ st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// step 4 (thread per point): point steps by back-substitution, trial points, trial cost partials
+// step 4 (kBaPointLanes lanes per point): point steps by back-substitution, trial points, trial cost partials
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __restrict__ st, const double* __restrict__ cams,
                                                             const double* __restrict__ dC, const double* __restrict__ X,
@@ -798,12 +818,17 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
     __shared__ double sh[kBaPointThreads / 32];
     if (st->done || st->accepted < 0) return;
     double cost = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nP; j += gridDim.x * blockDim.x) {
-        const double X0 = X[3 * (size_t)j], X1 = X[3 * (size_t)j + 1], X2 = X[3 * (size_t)j + 2];
-        const double* pb = pblk + 12 * (size_t)j;
+    const int sub = threadIdx.x & (kBaPointLanes - 1);
+    const int gpb = blockDim.x / kBaPointLanes;
+    const int npad = ((nP + gpb - 1) / gpb) * gpb;
+    for (int j = blockIdx.x * gpb + threadIdx.x / kBaPointLanes; j < npad; j += gridDim.x * gpb) {
+        const bool real = j < nP;
+        const size_t jj = real ? (size_t)j : 0;
+        const double X0 = X[3 * jj], X1 = X[3 * jj + 1], X2 = X[3 * jj + 2];
+        const double* pb = pblk + 12 * jj;
         double back[3] = {0, 0, 0};
-        const int lo = pt_off[j], hi = pt_off[j + 1];
-        for (int o = lo; o < hi; ++o) {
+        const int lo = real ? pt_off[j] : 0, hi = real ? pt_off[j + 1] : 0;
+        for (int o = lo + sub; o < hi; o += kBaPointLanes) {
             const double* d = dC + 12 * (size_t)ocam[o];
             double q[3];
 #pragma unroll
@@ -816,12 +841,17 @@ __global__ void __launch_bounds__(kBaPointThreads) ba_trial(const BaState* __res
             back[1] += l0.y * q[0] + l1.x * q[1] + l1.w * q[2];
             back[2] += l0.z * q[0] + l1.y * q[1] + t22 * q[2];
         }
+#pragma unroll
+        for (int o = kBaPointLanes / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) back[k] += __shfl_xor_sync(0xffffffffu, back[k], o);
+        }
         const double r0 = pb[9] - back[0], r1 = pb[10] - back[1], r2 = pb[11] - back[2];
         const double n0 = X0 + pb[0] * r0 + pb[1] * r1 + pb[2] * r2;
         const double n1 = X1 + pb[1] * r0 + pb[3] * r1 + pb[4] * r2;
         const double n2 = X2 + pb[2] * r0 + pb[4] * r1 + pb[5] * r2;
-        Xtrial[3 * (size_t)j] = n0; Xtrial[3 * (size_t)j + 1] = n1; Xtrial[3 * (size_t)j + 2] = n2;
-        for (int o = lo; o < hi; ++o) {
+        if (real && sub == 0) { Xtrial[3 * jj] = n0; Xtrial[3 * jj + 1] = n1; Xtrial[3 * jj + 2] = n2; }
+        for (int o = lo + sub; o < hi; o += kBaPointLanes) {
             if (lin[kBaLin * (size_t)o + 9] == 0.0) continue;                  // skipped in the linearisation: skipped here
             const size_t k = (size_t)ocam[o];
             double Cn[12];
@@ -845,21 +875,26 @@ __global__ void __launch_bounds__(256) ba_accept(BaState* __restrict__ st, doubl
                                                  const int* __restrict__ bad_part, const double* __restrict__ obs2_part,
                                                  int nparts, double ftol, int max_iter) {
     __shared__ int better_s;
+    __shared__ double sh[256 / 32];
     if (st->done) return;
+    // ordered sums of the per-block partials: thread t adds partials t, t + 256, ...; then the fixed tree of ba_block_sum
+    const bool need_cost = st->have_cost == 0, have_trial = st->accepted > 0;
+    double ps = 0.0, ps2 = 0.0, pt = 0.0;
+    int pnb = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+        if (need_cost) { ps += cost_part[i]; ps2 += obs2_part[i]; }
+        if (have_trial) pt += trial_part[i];
+        pnb += bad_part[i];
+    }
+    const double s = ba_block_sum(ps, sh), s2 = ba_block_sum(ps2, sh), t = ba_block_sum(pt, sh);
+    const double nbd = ba_block_sum((double)pnb, sh);
     if (threadIdx.x == 0) {
-        if (!st->have_cost) {
-            double s = 0.0, s2 = 0.0;
-            for (int i = 0; i < nparts; ++i) { s += cost_part[i]; s2 += obs2_part[i]; }
+        if (need_cost) {
             st->cost = 0.5 * s;
             st->floor = 0.5 * s2 * (64.0 * 2.220446049250313e-16) * (64.0 * 2.220446049250313e-16);
             st->have_cost = 1;
         }
-        int nb = 0;
-        for (int i = 0; i < nparts; ++i) nb += bad_part[i];
-        st->n_bad = nb;
-        double t = 0.0;
-        if (st->accepted > 0)
-            for (int i = 0; i < nparts; ++i) t += trial_part[i];
+        st->n_bad = (int)nbd;
         st->cost_trial = 0.5 * t;
         st->iters += 1;
         const bool better = st->accepted > 0 && st->cost_trial < st->cost;       // NaN / Inf trial cost: not better
