@@ -32,6 +32,9 @@ def run(last_view=34, bundle_adjust=True, r_f=10000, verbose=True):
         return np.array(y1[ok]), np.array(y2[ok])
 
     times = {"f_ransac": 0.0, "ba": 0.0, "add_view": 0.0, "add_points": 0.0, "init": 0.0}
+    t0 = time.perf_counter()
+    rg._cabi.context()                                        # CUDA context + library load: not part of the pipeline
+    times["cuda_context (not in total)"] = time.perf_counter() - t0
     t_all = time.perf_counter()
     T = Tables()
     C = Ps[None]
