@@ -140,7 +140,7 @@ def bundle_adjust_lm(cams, pts, uv, cam_idx, pt_idx, n_fixed=1, max_iter=50, fto
                 for o2 in oj:
                     k, l = cam_idx[o], cam_idx[o2]
                     S[12 * k:12 * k + 12, 12 * l:12 * l + 12] -= np.kron(T[o] @ Vi[j] @ T[o2].T, XX[o])
-        S[np.arange(n), np.arange(n)] += lam * dU
+        S[np.arange(n), np.arange(n)] += np.where(dU > 0.0, lam * dU, 1.0)      # no information: unit diagonal, zero step
         f0 = 12 * n_fixed
         dc = np.zeros(n)
         ok = True

@@ -333,7 +333,9 @@ __global__ void __launch_bounds__(kBaBlockThreads, 3) ba_blocks(const BaState* _
     }
     const size_t ld = (size_t)12 * nF + 1;
     if (tid < 144) {
-        if (diag && er == ec) acc += lambda * accd;
+        // Marquardt damping; a parameter without any information (a view without observations) gets a unit diagonal:
+        // its row and right-hand side are zero, so it simply does not move instead of making the system singular
+        if (diag && er == ec) acc += accd > 0.0 ? lambda * accd : 1.0;
         S[(size_t)(12 * kf + er) + (size_t)(12 * lf + ec) * ld] = acc;
     } else if (diag && rz < 12) {
         S[(size_t)12 * nF + (size_t)(12 * kf + rz) * ld] = acc;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks_reduce(const BaStat
             a += part[(size_t)(f + s) * kBaPart + tid];
             if (diag && er == ec) d += part[(size_t)(f + s) * kBaPart + 156 + er];
         }
-        if (diag && er == ec) a += st->lambda * d;
+        if (diag && er == ec) a += d > 0.0 ? st->lambda * d : 1.0;      // see ba_blocks
         S[(size_t)(12 * kf + er) + (size_t)(12 * lf + ec) * ld] = a;
     } else if (diag && tid < 156) {
         double a = 0.0;
