@@ -295,6 +295,12 @@ def run_ours(args) -> None:
 
     extras = {}
     cpu_baseline = None
+    split = None
+    if world > 1 and not args.no_extras:
+        try:
+            split = run_split_hypotheses(rg, cabi, lib, ctx, stream, dev, torch, dist, rank, world)
+        except Exception as e:                          # never take the headline down with an extra
+            split = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_extras:
         extras = run_extras(args, rg, rt, cabi, lib, ctx, stream, dev, torch, fp32_peak_tflops)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -340,6 +346,8 @@ def run_ours(args) -> None:
             "pipes": peaks, "clocks": clocks, "cpu_baseline": cpu_baseline,
         }
         line.update(extras)
+        if split is not None:
+            line["config3_split_hypotheses"] = split
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -447,6 +455,71 @@ def _tri_cpu_worker(a):
     from oracle import geom_path as og
     C1, C2, x1, x2 = a
     return og.triangulate_optimal_batch(C1, C2, x1, x2)
+
+
+def run_split_hypotheses(rg, cabi, lib, ctx, stream, dev, torch, dist, rank, world) -> dict:
+    """BASELINE config 3 (ONE pair, 100 000 correspondences x 16 384 hypotheses) with the hypotheses split over the ranks
+    (SURVEY 8e case 2): every rank holds all correspondences, scores its block with rg_f_ransac_dev, packs
+    (count, global index) into a key on the device (rg_argmax_pack_dev), ONE 8-byte NCCL max-all-reduce picks the winner,
+    rg_argmax_unpack_dev decodes it; the owner's F is broadcast (72 bytes).  Device resident, CUDA events, max over ranks."""
+    from tsbb15_b200 import sampling, synth
+    vp, pi32 = C.c_void_p, C.POINTER(C.c_int32)
+    N, H = 100000, 16384
+    pts, _ = synth.two_view(N, seed=1)
+    idx = sampling.fast(N, H, 8, seed=2)
+    lo, hi = rank * H // world, (rank + 1) * H // world
+    d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to(dev)
+    d_idx = torch.from_numpy(np.ascontiguousarray(idx[lo:hi])).to(dev)
+    d_all = torch.from_numpy(np.ascontiguousarray(idx)).to(dev) if rank == 0 else None
+    po = np.array([0, N], dtype=np.int32)
+    ho = np.array([0, hi - lo], dtype=np.int32)
+    d_bi = torch.empty(1, dtype=torch.int32, device=dev)
+    d_bc = torch.empty(1, dtype=torch.int32, device=dev)
+    d_F = torch.empty(9, dtype=torch.float64, device=dev)
+    d_key = torch.empty(1, dtype=torch.int64, device=dev)
+    d_gi = torch.empty(1, dtype=torch.int32, device=dev)
+    d_gc = torch.empty(1, dtype=torch.int32, device=dev)
+    d_Fw = torch.empty(9, dtype=torch.float64, device=dev)
+
+    def call():
+        cabi.check(lib.rg_f_ransac_dev(vp(ctx), vp(stream), 1, vp(d_pts.data_ptr()), po.ctypes.data_as(pi32), vp(d_idx.data_ptr()),
+                                       ho.ctypes.data_as(pi32), 1.5, rg.MODE_EPI_MAX, rg.TIE_FIRST, rg.SOLVER_QR,
+                                       rg.SCORE_FP32_GUARDED, vp(d_bi.data_ptr()), vp(d_bc.data_ptr()), vp(d_F.data_ptr()), None))
+        cabi.check(lib.rg_argmax_pack_dev(vp(stream), 1, vp(d_bi.data_ptr()), vp(d_bc.data_ptr()), lo, vp(d_key.data_ptr())))
+        dist.all_reduce(d_key, op=dist.ReduceOp.MAX)
+        cabi.check(lib.rg_argmax_unpack_dev(vp(stream), 1, vp(d_key.data_ptr()), vp(d_gi.data_ptr()), vp(d_gc.data_ptr())))
+
+    def ev(fn, reps):
+        fn(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = ev(call, 10)
+    gi, gc = int(d_gi.item()), int(d_gc.item())
+    owner = next(r for r in range(world) if r * H // world <= gi < (r + 1) * H // world) if gi >= 0 else 0
+    d_Fw.copy_(d_F)
+    dist.broadcast(d_Fw, src=owner)                      # the winner's F from its owner
+    out = {"workload": "config 3: one pair, 100000 correspondences x 16384 hypotheses split over the ranks",
+           "ms": ms, "evals_per_s": float(N) * H / (ms * 1e-3), "winner": gi, "count": gc, "owner_rank": owner,
+           "collective": "one 8-byte ncclAllReduce(max) per call + a 72-byte broadcast of the winner's F"}
+    if rank == 0:                                        # the same problem on one GPU: identical winner
+        d_bi1 = torch.empty(1, dtype=torch.int32, device=dev)
+        d_bc1 = torch.empty(1, dtype=torch.int32, device=dev)
+        d_F1 = torch.empty(9, dtype=torch.float64, device=dev)
+        ho1 = np.array([0, H], dtype=np.int32)
+        cabi.check(lib.rg_f_ransac_dev(vp(ctx), vp(stream), 1, vp(d_pts.data_ptr()), po.ctypes.data_as(pi32), vp(d_all.data_ptr()),
+                                       ho1.ctypes.data_as(pi32), 1.5, rg.MODE_EPI_MAX, rg.TIE_FIRST, rg.SOLVER_QR,
+                                       rg.SCORE_FP32_GUARDED, vp(d_bi1.data_ptr()), vp(d_bc1.data_ptr()), vp(d_F1.data_ptr()), None))
+        torch.cuda.synchronize()
+        out["same_winner_as_one_gpu"] = bool(int(d_bi1.item()) == gi and int(d_bc1.item()) == gc
+                                             and torch.equal(d_F1, d_Fw))
+    return out
 
 
 def run_next_rows(args, rg, rt, cabi, lib, ctx, stream, dev, torch) -> dict:
