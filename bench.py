@@ -296,7 +296,7 @@ def run_ours(args) -> None:
     extras = {}
     cpu_baseline = None
     split = None
-    if world > 1 and not args.no_extras:
+    if world > 1 and args.split_hypotheses:             # opt-in: a failing rank would leave the others in a collective
         try:
             split = run_split_hypotheses(rg, cabi, lib, ctx, stream, dev, torch, dist, rank, world)
         except Exception as e:                          # never take the headline down with an extra
@@ -780,6 +780,8 @@ def main() -> None:
     ap.add_argument("--solver", type=int, default=0)
     ap.add_argument("--host-slices", type=int, default=0, help="sub-batches of the host entry point (0 = automatic)")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--split-hypotheses", action="store_true",
+                    help="under torchrun: also time config 3 with one pair's hypotheses split over the ranks (NCCL argmax)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
