@@ -370,49 +370,8 @@ __global__ void __launch_bounds__(kBaBlockThreads) ba_blocks_reduce(const BaStat
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// 12x12 Cholesky of a diagonal block by one warp: lane r holds row r in registers; column j is scaled by rsqrt(d)
-// (MUFU.RSQ64H + Newton: no DSQRT / division chain) and broadcast to the other rows through shared memory.
-// Ld: row-major lower triangle in shared memory (in: the block, out: its factor), Li[j] = 1 / L[j][j],
-// cb: 24 doubles of scratch.  Returns false (uniformly) when a pivot is not positive / finite.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool ba_chol12(double* __restrict__ Ld, double* __restrict__ Li, double* __restrict__ cb,
-                                          const int lane) {
-    double a[12], dg[12];                                       // own row; every lane's copy of the remaining diagonal
-#pragma unroll
-    for (int c = 0; c < 12; ++c) {
-        a[c] = (lane < 12 && c <= lane) ? Ld[lane * 12 + c] : 0.0;
-        dg[c] = Ld[c * 12 + c];
-    }
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        const double d = dg[j];                                 // kept up to date below: no shuffle on the critical chain
-        ok = ok && d > 0.0 && isfinite(d);                      // no early exit: the loop stays fully unrolled
-        const double inv = rsqrt(d);
-        if (lane == j) { a[j] = d * inv; Li[j] = inv; }
-        else if (lane > j) a[j] *= inv;
-        double* col = cb + 12 * (j & 1);
-        if (lane > j && lane < 12) col[lane] = a[j];
-        __syncwarp();
-#pragma unroll
-        for (int c = j + 1; c < 12; ++c) {
-            const double t = col[c];                            // L[c][j]
-            if (lane > c) a[c] = fma(-a[j], t, a[c]);           // L[lane][c] -= L[lane][j] L[c][j]
-            dg[c] = fma(-t, t, dg[c]);
-            if (lane == c) a[c] = dg[c];                        // the diagonal entry of the own row: same value in every lane
-        }
-    }
-    if (ok && lane < 12) {
-#pragma unroll
-        for (int c = 0; c < 12; ++c)
-            if (c <= lane) Ld[lane * 12 + c] = a[c];
-    }
-    return ok;
-}
-
 // one panel row: x L_kk^T = a  (forward substitution with the reciprocal diagonal)
-__device__ __forceinline__ void ba_panel_row(double (&x)[12], const double* __restrict__ Ld, const double* __restrict__ Li) {
+__device__ __forceinline__ void ba_panel_row(double (&x)[12], const double* Ld, const double* Li) {
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
         double a = x[c];
@@ -423,8 +382,7 @@ __device__ __forceinline__ void ba_panel_row(double (&x)[12], const double* __re
 }
 
 // backward substitution of one 12-block by one thread: x_blk = L_kk^-T (y_blk - tv); L(c, m) = Lb[m * ldb + c], c >= m
-__device__ __forceinline__ void ba_back12(double* __restrict__ yb, const double* __restrict__ tv, const double* __restrict__ Lb,
-                                          const int ldb, const double* __restrict__ Li) {
+__device__ __forceinline__ void ba_back12(double* yb, const double* tv, const double* Lb, const int ldb, const double* Li) {
     double v[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) v[c] = yb[c] - tv[c];

@@ -163,6 +163,7 @@ struct Ctx {
     Buffer gs_ws;                                  // gold-standard refinement: per-pair state, sums, cameras, points
     Buffer ba_ws;                                  // bundle adjustment: state, step, trial points, point blocks, camera system
     int opt_ba_cluster = 0;                        // option 3: CTAs in the cluster of the camera-system factorisation (0 = 8)
+    int opt_gs_multi = 0;                          // option 5: 1 = gold standard always on the multi-kernel path (no gs_fused)
     int opt_ba_l2 = 0;                             // option 4: 1 = keep the camera system in L2 (ba_solve) even when it fits in DSMEM
     Buffer h_ba_items;                             // pinned: work items of ba_blocks (blocks with a common point x segments)
     Buffer h_ba_flags;                             // pinned: the solver's `done` flag after every iteration (host entry point)

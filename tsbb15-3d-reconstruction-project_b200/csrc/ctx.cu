@@ -132,6 +132,8 @@ int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 // option 2: number of sub-batches of rg_f_ransac_host (0 = automatic): uploads overlap the previous sub-batch's kernels
 // option 3: thread-block cluster size of the bundle-adjustment Cholesky (0 = default 8; 1, 2, 4, 8)
 // option 4: 1 = factorise the bundle-adjustment camera system in L2 even when it fits in distributed shared memory
+// option 5: 1 = gold-standard refinement always on the multi-kernel path (default: pairs of <= 4096 points run the whole
+//           Levenberg-Marquardt loop in one CTA, one launch)
 int rg_set_option(void* ctx, int option, long long value) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
@@ -163,6 +165,10 @@ int rg_set_option(void* ctx, int option, long long value) {
     }
     if (option == 4) {
         c->opt_ba_l2 = value != 0;
+        return RG_OK;
+    }
+    if (option == 5) {
+        c->opt_gs_multi = value != 0;
         return RG_OK;
     }
     set_error("invalid argument: unknown option %d", option);

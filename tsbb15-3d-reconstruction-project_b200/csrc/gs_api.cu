@@ -55,38 +55,45 @@ static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64
         memcpy(c->h_stage.ptr, pair_off, sizeof(int) * (p + 1));
         RG_CUDA(cudaMemcpyAsync(doff, c->h_stage.ptr, sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
         RG_CUDA(cudaEventRecord(c->staging_free, st));
-        const int nbx = std::max(1, std::min(32, ceil_div(maxN, kGsThreads * 4)));
-        const dim3 grid(nbx, P);
-        // host_paced (the host-buffer entry point, which ends with a synchronisation anyway): the number of pairs still
-        // running is copied to pinned memory after every iteration and the enqueue loop stays at most two iterations
-        // ahead of the device: it stops two iterations after the last pair converged instead of enqueueing 4 x max_iter
-        // launches that return at once.
-        volatile int* h_act = nullptr;
-        if (host_paced && max_iter > 2) {
-            if ((rc = ensure_pinned(c->h_ba_flags, sizeof(int) * (size_t)max_iter))) return rc;
-            h_act = (volatile int*)c->h_ba_flags.ptr;
-            for (int i = 0; i < 2; ++i)
-                if (!c->ba_iter_ev[i]) RG_CUDA(cudaEventCreateWithFlags(&c->ba_iter_ev[i], cudaEventDisableTiming));
-            RG_CUDA(cudaMemsetAsync(active, 0, sizeof(int) * (size_t)max_iter, st));
-        }
-        for (int it = 0; it < max_iter; ++it) {
-            if (h_act && it >= 2) {
-                RG_CUDA(cudaEventSynchronize(c->ba_iter_ev[it & 1]));      // iteration it - 2 has finished
-                if (h_act[it - 2] == 0) break;
+        if (maxN <= kGsFusedMaxPts && !c->opt_gs_multi) {
+            // small pairs: the whole LM loop of a pair in one CTA, one launch (gs_fused)
+            gs_fused<<<P, kGsFusedThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial, C1, ftol, max_iter);
+            launches += 1;
+            RG_CUDA(cudaGetLastError());
+        } else {
+            const int nbx = std::max(1, std::min(32, ceil_div(maxN, kGsThreads * 4)));
+            const dim3 grid(nbx, P);
+            // host_paced (the host-buffer entry point, which ends with a synchronisation anyway): the number of pairs still
+            // running is copied to pinned memory after every iteration and the enqueue loop stays at most two iterations
+            // ahead of the device: it stops two iterations after the last pair converged instead of enqueueing 4 x max_iter
+            // launches that return at once.
+            volatile int* h_act = nullptr;
+            if (host_paced && max_iter > 2) {
+                if ((rc = ensure_pinned(c->h_ba_flags, sizeof(int) * (size_t)max_iter))) return rc;
+                h_act = (volatile int*)c->h_ba_flags.ptr;
+                for (int i = 0; i < 2; ++i)
+                    if (!c->ba_iter_ev[i]) RG_CUDA(cudaEventCreateWithFlags(&c->ba_iter_ev[i], cudaEventDisableTiming));
+                RG_CUDA(cudaMemsetAsync(active, 0, sizeof(int) * (size_t)max_iter, st));
             }
-            gs_accumulate<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial, sums);
-            gs_solve<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P);
-            gs_trial<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial);
-            gs_accept<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P, ftol, max_iter, h_act ? active + it : nullptr);
-            launches += 4;
-            if (h_act) {
-                RG_CUDA(cudaMemcpyAsync((void*)&h_act[it], active + it, sizeof(int), cudaMemcpyDeviceToHost, st));
-                RG_CUDA(cudaEventRecord(c->ba_iter_ev[it & 1], st));
+            for (int it = 0; it < max_iter; ++it) {
+                if (h_act && it >= 2) {
+                    RG_CUDA(cudaEventSynchronize(c->ba_iter_ev[it & 1]));      // iteration it - 2 has finished
+                    if (h_act[it - 2] == 0) break;
+                }
+                gs_accumulate<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial, sums);
+                gs_solve<<<ceil_div(P, kGsSolveWarps), 32 * kGsSolveWarps, 0, st>>>(gp, sums, P);
+                gs_trial<<<grid, kGsThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial);
+                gs_accept<<<ceil_div(P, 32), 32, 0, st>>>(gp, sums, P, ftol, max_iter, h_act ? active + it : nullptr);
+                launches += 4;
+                if (h_act) {
+                    RG_CUDA(cudaMemcpyAsync((void*)&h_act[it], active + it, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    RG_CUDA(cudaEventRecord(c->ba_iter_ev[it & 1], st));
+                }
             }
+            RG_CUDA(cudaGetLastError());
+            gs_finish<<<grid, kGsThreads, 0, st>>>(doff, gp, Xcur, Xtrial, C1);
+            launches += 1;
         }
-        RG_CUDA(cudaGetLastError());
-        gs_finish<<<grid, kGsThreads, 0, st>>>(doff, gp, Xcur, Xtrial, C1);
-        launches += 1;
     }
     // F_gold = lab3.fmatrix_from_cameras(C1, [I | 0])   (fun.py:368)
     PairGeom* G = nullptr;

@@ -102,6 +102,48 @@ __device__ __forceinline__ bool gs_blocks(const GsPoint& g, double lambda, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
+// 12x12 Cholesky of a diagonal block by one warp: lane r holds row r in registers; column j is scaled by rsqrt(d)
+// (MUFU.RSQ64H + Newton: no DSQRT / division chain) and broadcast to the other rows through shared memory.
+// Ld: row-major lower triangle in shared memory (in: the block, out: its factor), Li[j] = 1 / L[j][j],
+// cb: 24 doubles of scratch.  Returns false (uniformly) when a pivot is not positive / finite.
+// ------------------------------------------------------------------------------------------------
+// (no __restrict__ on these pointers: the lanes communicate through this shared memory, and a restrict-qualified pointer
+// lets the compiler move its loads across __syncwarp() — seen as a wrong last pivot in every lane but the writer's)
+__device__ __forceinline__ bool ba_chol12(double* Ld, double* Li, double* cb, const int lane) {
+    double a[12], dg[12];                                       // own row; every lane's copy of the remaining diagonal
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+        a[c] = (lane < 12 && c <= lane) ? Ld[lane * 12 + c] : 0.0;
+        dg[c] = Ld[c * 12 + c];
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const double d = dg[j];                                 // kept up to date below: no shuffle on the critical chain
+        ok = ok && d > 0.0 && isfinite(d);                      // no early exit: the loop stays fully unrolled
+        const double inv = rsqrt(d);
+        if (lane == j) { a[j] = d * inv; Li[j] = inv; }
+        else if (lane > j) a[j] *= inv;
+        double* col = cb + 12 * (j & 1);
+        if (lane > j && lane < 12) col[lane] = a[j];
+        __syncwarp();
+#pragma unroll
+        for (int c = j + 1; c < 12; ++c) {
+            const double t = col[c];                            // L[c][j]
+            if (lane > c) a[c] = fma(-a[j], t, a[c]);           // L[lane][c] -= L[lane][j] L[c][j]
+            dg[c] = fma(-t, t, dg[c]);
+            if (lane == c) a[c] = dg[c];                        // the diagonal entry of the own row: same value in every lane
+        }
+    }
+    if (ok && lane < 12) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+            if (c <= lane) Ld[lane * 12 + c] = a[c];
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
 // initial cameras from F (lab3.fmatrix_cameras, lab3.py:353-380): C1 = ([e1]_x F | e1), e1 = left null vector of F
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) gs_init(const double* __restrict__ F0, int P, double lambda0, GsPair* __restrict__ gp,
@@ -232,56 +274,66 @@ __global__ void __launch_bounds__(kGsThreads) gs_accumulate(const double4* __res
         if (red[k] != 0.0) atomicAdd(&sums[(size_t)p * kGsSums + k], red[k]);
 }
 
-// step 2 (one thread per pair): assemble S, Cholesky, camera step
-__global__ void __launch_bounds__(32) gs_solve(GsPair* __restrict__ gpair, const double* __restrict__ sums, int P) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+// the reduced 12x12 camera system of one pair from its sums s[kGsSums] -> camera step x[12] (one warp; Ld 144, Li 16,
+// cb 24, x 12 doubles of shared memory); false if the damped system is not positive definite
+__device__ __forceinline__ bool gs_solve_warp(const double* s, const double lambda, double* Ld, double* Li, double* cb,
+                                              double* x, const int lane) {
+    if (lane < 12) {
+        const int a = lane >> 2, b = lane & 3;
+        for (int c = 0; c <= lane; ++c) {
+            const int a2 = c >> 2, b2 = c & 3;
+            Ld[lane * 12 + c] = s[sym3(a, a2) * 10 + sym4(b, b2)];
+        }
+        for (int c = lane + 1; c < 12; ++c) Ld[lane * 12 + c] = 0.0;
+        Ld[lane * 12 + lane] += lambda * s[72 + lane];
+        x[lane] = s[60 + lane];
+    }
+    __syncwarp();
+    bool ok = ba_chol12(Ld, Li, cb, lane);
+    __syncwarp();
+    if (lane == 0 && ok) {                                  // L y = rhs, L^T x = y with the reciprocal diagonal
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            double v = x[i];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                if (k < i) v = fma(-Ld[i * 12 + k], x[k], v);
+            x[i] = v * Li[i];
+        }
+#pragma unroll
+        for (int i = 11; i >= 0; --i) {
+            double v = x[i];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                if (k > i) v = fma(-Ld[k * 12 + i], x[k], v);
+            x[i] = v * Li[i];
+            ok = ok && isfinite(x[i]);
+        }
+    }
+    __syncwarp();                                           // x (written by lane 0) is read by the other lanes of the caller
+    return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+}
+
+// step 2 (one warp per pair): assemble S, Cholesky (ba_chol12: rows in registers, rsqrt pivots), camera step
+constexpr int kGsSolveWarps = 4;
+__global__ void __launch_bounds__(32 * kGsSolveWarps) gs_solve(GsPair* __restrict__ gpair, const double* __restrict__ sums, int P) {
+    __shared__ double sh[kGsSolveWarps][144 + 16 + 24 + 12];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * kGsSolveWarps + w;
+    if (p >= P) return;                                     // whole warp
     GsPair& G = gpair[p];
     if (G.done) return;
+    double* Ld = sh[w];
+    double* x = Ld + 144 + 16 + 24;
     const double* s = sums + (size_t)p * kGsSums;
-    if (!G.have_cost) { G.cost = 0.5 * s[84]; G.have_cost = 1; }
-    G.cost_trial = 0.0;
-    double S[12][12], rhs[12];
-#pragma unroll 1
-    for (int a = 0; a < 3; ++a)
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
-            const int r = a * 4 + b;
-            rhs[r] = s[60 + r];
-            for (int a2 = 0; a2 < 3; ++a2)
-                for (int b2 = 0; b2 < 4; ++b2) S[r][a2 * 4 + b2] = s[sym3(a, a2) * 10 + sym4(b, b2)];
-            S[r][r] += G.lambda * s[72 + r];
-        }
-    // in-place Cholesky S = L L^T (lower), forward / backward substitution
-    bool ok = true;
-#pragma unroll 1
-    for (int j = 0; j < 12 && ok; ++j) {
-        double d = S[j][j];
-        for (int k = 0; k < j; ++k) d -= S[j][k] * S[j][k];
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }
-        const double l = sqrt(d);
-        S[j][j] = l;
-        for (int i = j + 1; i < 12; ++i) {
-            double v = S[i][j];
-            for (int k = 0; k < j; ++k) v -= S[i][k] * S[j][k];
-            S[i][j] = v / l;
-        }
+    const double lambda = G.lambda;
+    const bool ok = gs_solve_warp(s, lambda, Ld, Ld + 144, Ld + 160, x, lane);
+    if (lane == 0) {
+        if (!G.have_cost) { G.cost = 0.5 * s[84]; G.have_cost = 1; }
+        G.cost_trial = 0.0;
+        for (int k = 0; k < 12; ++k) G.dc[k] = ok ? x[k] : 0.0;
+        G.accepted = ok ? 1 : -1;          // -1: no step could be computed -> gs_accept raises lambda
     }
-    if (ok) {
-        for (int i = 0; i < 12; ++i) {
-            double v = rhs[i];
-            for (int k = 0; k < i; ++k) v -= S[i][k] * rhs[k];
-            rhs[i] = v / S[i][i];
-        }
-        for (int i = 11; i >= 0; --i) {
-            double v = rhs[i];
-            for (int k = i + 1; k < 12; ++k) v -= S[k][i] * rhs[k];
-            rhs[i] = v / S[i][i];
-            ok = ok && isfinite(rhs[i]);
-        }
-    }
-    for (int k = 0; k < 12; ++k) G.dc[k] = ok ? rhs[k] : 0.0;
-    G.accepted = ok ? 1 : -1;          // -1: no step could be computed -> gs_accept raises lambda
 }
 
 // step 3: point steps by back-substitution, trial parameters, trial cost
@@ -375,6 +427,195 @@ __global__ void __launch_bounds__(kGsThreads) gs_finish(const int* __restrict__ 
         Xcur[3 * (size_t)i] = Xtrial[3 * (size_t)i];
         Xcur[3 * (size_t)i + 1] = Xtrial[3 * (size_t)i + 1];
         Xcur[3 * (size_t)i + 2] = Xtrial[3 * (size_t)i + 2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole Levenberg-Marquardt loop of ONE pair in ONE CTA (pairs of up to a few thousand correspondences: the
+// reference's own case has 257): no launch per step, no atomics, every sum in a fixed order.  Per iteration:
+//   linearise the points in chunks of kGsFusedThreads into shared-memory records (W = M - T D'^-1 T^T, Xh, z, diag M);
+//   3 x 84 entry threads add W (x) Xh Xh^T, z (x) Xh, diag(M) (x) Xh^2 over the chunk; warp 0 solves the 12x12 system;
+//   all threads take the point steps and the trial cost; thread 0 accepts / rejects.  Accepted points are swapped in by
+//   exchanging the roles of the two point buffers.  grid = P.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGsFusedThreads = 256;
+constexpr int kGsFusedMaxPts = 4096;      // per pair; larger pairs use the multi-kernel path (more than one SM per pair)
+constexpr int kGsRec = 15;                // W (6) | X (3) | z (3) | M00, M11, M22
+
+__device__ __forceinline__ double gs_block_sum(double v, double* sh) {      // fixed tree; result in every thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(kGsFusedThreads) gs_fused(const double4* __restrict__ pts, const unsigned char* __restrict__ mask,
+                                                            const int* __restrict__ pair_off, GsPair* __restrict__ gpair,
+                                                            double* __restrict__ Xa, double* __restrict__ Xb,
+                                                            double* __restrict__ C1out, double ftol, int max_iter) {
+    __shared__ double rec[kGsFusedThreads * kGsRec];
+    __shared__ double part[3][84];
+    __shared__ double sums[kGsSums];
+    __shared__ double solve_ws[144 + 16 + 24 + 12];
+    __shared__ double red[kGsFusedThreads / 32];
+    __shared__ double sC1[12], sdc[12];
+    __shared__ double s_lambda, s_cost;
+    __shared__ int s_done, s_ok, s_iters;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GsPair& G = gpair[p];
+    const int lo = pair_off[p], hi = pair_off[p + 1];
+    if (tid < 12) sC1[tid] = G.C1[tid];
+    if (tid == 0) { s_lambda = G.lambda; s_done = G.done; s_iters = 0; s_cost = 0.0; }
+    __syncthreads();
+    double* Xc = Xa;                                        // current points / trial points (roles swap on acceptance)
+    double* Xt = Xb;
+    const int grp = tid / 84, ent = tid - 84 * grp;         // entry threads: 3 groups x 84 sums (tid < 252)
+    // static description of the entry owned by this thread
+    int e_w = 0, e_a = 0, e_b = 0, e_kind = -1;             // kind 0: W[e_w] Xh[e_a] Xh[e_b]; 1: z[e_w] Xh[e_a]; 2: Md[e_w] Xh[e_a]^2
+    if (grp < 3) {
+        if (ent < 60) {
+            e_kind = 0; e_w = ent / 10;
+            const int x = ent - 10 * e_w;
+            const int a4[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, b4[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+            e_a = a4[x]; e_b = b4[x];
+        } else if (ent < 72) { e_kind = 1; e_w = (ent - 60) >> 2; e_a = (ent - 60) & 3; }
+        else { e_kind = 2; e_w = (ent - 72) >> 2; e_a = (ent - 72) & 3; }
+    }
+    bool have_cost = false;
+    for (int it = 0; it < max_iter && !s_done; ++it) {
+        double C1[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) C1[k] = sC1[k];
+        const double lambda = s_lambda;
+        // ---- accumulate ---------------------------------------------------------------------------------------
+        double acc = 0.0, cost = 0.0;
+        for (int base = lo; base < hi; base += kGsFusedThreads) {
+            const int i = base + tid;
+            double* r = rec + tid * kGsRec;
+            bool used = false;
+            if (i < hi && (mask == nullptr || mask[i] != 0)) {
+                GsPoint g;
+                gs_point(C1, pts[i], Xc[3 * (size_t)i], Xc[3 * (size_t)i + 1], Xc[3 * (size_t)i + 2], g);
+                double M[6], T[3][3], Di[6], gp[3];
+                if (g.ok && gs_blocks(g, lambda, M, T, Di, gp)) {
+                    double TD[3][3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            TD[a][c] = T[a][0] * Di[sym3(0, c)] + T[a][1] * Di[sym3(1, c)] + T[a][2] * Di[sym3(2, c)];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                        for (int b = a; b < 3; ++b)
+                            r[sym3(a, b)] = M[sym3(a, b)] - (TD[a][0] * T[b][0] + TD[a][1] * T[b][1] + TD[a][2] * T[b][2]);
+                        r[9 + a] = g.P2[0][a] * g.rl[0] + g.P2[1][a] * g.rl[1] + TD[a][0] * gp[0] + TD[a][1] * gp[1] + TD[a][2] * gp[2];
+                        r[12 + a] = M[sym3(a, a)];
+                        r[6 + a] = g.Xh[a];
+                    }
+                    cost += g.rl[0] * g.rl[0] + g.rl[1] * g.rl[1] + g.rr[0] * g.rr[0] + g.rr[1] * g.rr[1];
+                    used = true;
+                }
+            }
+            if (!used) {
+#pragma unroll
+                for (int k = 0; k < kGsRec; ++k) r[k] = 0.0;
+            }
+            __syncthreads();
+            if (e_kind >= 0) {
+                const int n = min(kGsFusedThreads, hi - base);
+                for (int q = grp; q < n; q += 3) {
+                    const double* rq = rec + q * kGsRec;
+                    const double xa = e_a < 3 ? rq[6 + e_a] : 1.0;
+                    if (e_kind == 0) acc = fma(rq[e_w] * xa, e_b < 3 ? rq[6 + e_b] : 1.0, acc);
+                    else if (e_kind == 1) acc = fma(rq[9 + e_w], xa, acc);
+                    else acc = fma(rq[12 + e_w] * xa, xa, acc);
+                }
+            }
+            __syncthreads();
+        }
+        if (e_kind >= 0) part[grp][ent] = acc;
+        const double csum = gs_block_sum(cost, red);        // (contains the barriers that publish part[][])
+        if (tid < 84) sums[tid] = (part[0][tid] + part[1][tid]) + part[2][tid];
+        if (tid == 0 && !have_cost) s_cost = 0.5 * csum;
+        have_cost = true;
+        __syncthreads();
+        // ---- solve --------------------------------------------------------------------------------------------
+        if (warp == 0) {
+            double* x = solve_ws + 144 + 16 + 24;
+            const bool ok = gs_solve_warp(sums, lambda, solve_ws, solve_ws + 144, solve_ws + 160, x, lane);
+            if (lane < 12) sdc[lane] = ok ? x[lane] : 0.0;
+            if (lane == 0) s_ok = ok ? 1 : 0;
+        }
+        __syncthreads();
+        // ---- trial --------------------------------------------------------------------------------------------
+        double tcost = 0.0;
+        if (s_ok) {
+            double dc[12], Cn[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { dc[k] = sdc[k]; Cn[k] = C1[k] + dc[k]; }
+            for (int i = lo + tid; i < hi; i += kGsFusedThreads) {
+                const double X0 = Xc[3 * (size_t)i], X1 = Xc[3 * (size_t)i + 1], X2 = Xc[3 * (size_t)i + 2];
+                double n0 = X0, n1 = X1, n2 = X2;
+                if (mask == nullptr || mask[i] != 0) {
+                    const double4 m = pts[i];
+                    GsPoint g;
+                    gs_point(C1, m, X0, X1, X2, g);
+                    double M[6], T[3][3], Di[6], gp[3];
+                    if (g.ok && gs_blocks(g, lambda, M, T, Di, gp)) {
+                        double q[3];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            q[a] = dc[4 * a] * g.Xh[0] + dc[4 * a + 1] * g.Xh[1] + dc[4 * a + 2] * g.Xh[2] + dc[4 * a + 3];
+                        double rp[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) rp[c] = -gp[c] - (T[0][c] * q[0] + T[1][c] * q[1] + T[2][c] * q[2]);
+                        n0 += Di[0] * rp[0] + Di[1] * rp[1] + Di[2] * rp[2];
+                        n1 += Di[1] * rp[0] + Di[3] * rp[1] + Di[4] * rp[2];
+                        n2 += Di[2] * rp[0] + Di[4] * rp[1] + Di[5] * rp[2];
+                        GsPoint t;
+                        gs_point(Cn, m, n0, n1, n2, t);
+                        tcost += t.ok ? t.rl[0] * t.rl[0] + t.rl[1] * t.rl[1] + t.rr[0] * t.rr[0] + t.rr[1] * t.rr[1] : INFINITY;
+                    }
+                }
+                Xt[3 * (size_t)i] = n0; Xt[3 * (size_t)i + 1] = n1; Xt[3 * (size_t)i + 2] = n2;
+            }
+        }
+        const double ct = 0.5 * gs_block_sum(tcost, red);
+        // ---- accept (every thread evaluates the same decision from shared state) --------------------------------
+        const double cur = s_cost;
+        const bool better = s_ok && ct < cur;                // NaN / Inf trial cost: not better
+        __syncthreads();
+        if (better) {
+            if (tid < 12) sC1[tid] += sdc[tid];
+            double* sw = Xc; Xc = Xt; Xt = sw;
+        }
+        if (tid == 0) {
+            s_iters = it + 1;
+            if (better) {
+                const bool conv = (cur - ct) <= ftol * cur;
+                s_cost = ct;
+                s_lambda = fmax(lambda * 0.1, 1e-15);
+                if (conv) s_done = 2;
+            } else {
+                s_lambda = lambda * 10.0;
+                if (s_lambda > 1e12) s_done = 3;
+            }
+            if (!s_done && it + 1 >= max_iter) s_done = 4;
+        }
+        __syncthreads();
+    }
+    // results: points in Xa, camera, state
+    if (Xc != Xa)
+        for (int i = 3 * lo + tid; i < 3 * hi; i += kGsFusedThreads) Xa[i] = Xc[i];
+    if (tid < 12) { C1out[(size_t)p * 12 + tid] = sC1[tid]; G.C1[tid] = sC1[tid]; }
+    if (tid == 0) {
+        G.lambda = s_lambda; G.cost = s_cost; G.have_cost = have_cost ? 1 : G.have_cost;
+        G.iters = s_iters; G.done = s_done; G.accepted = 0;
     }
 }
 
