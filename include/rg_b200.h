@@ -47,7 +47,9 @@ int rg_device_sm_count(void* ctx);
  * option 3 = CTAs in the thread-block cluster that factorises the bundle-adjustment camera system (0 = default 8; 1, 2, 4,
  *            8); results do not depend on it
  * option 4 = 1: factorise that system in global memory / L2 even when it fits in the cluster's distributed shared memory
- *            (the default picks shared memory when it fits); results do not depend on it */
+ *            (the default picks shared memory when it fits); results do not depend on it
+ * option 5 = 1: gold-standard refinement always on the multi-kernel path (default: pairs of <= 4096 correspondences run
+ *            the whole Levenberg-Marquardt loop in one CTA and one launch); same iteration, sums in a different order */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the calls since the last read
  * (at most 256 calls are remembered); synchronises `stream` */

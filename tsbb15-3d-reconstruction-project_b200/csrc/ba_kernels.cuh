@@ -403,8 +403,8 @@ __device__ __forceinline__ void ba_back12(double* yb, const double* tv, const do
 // own shared memory, the trailing update is split over the warps of all CTAs by column; one cluster barrier per panel.
 // Row n comes out as y = L^-1 rhs; CTA 0 finishes with the backward substitution L^T x = y and writes the camera step.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict__ st, double* __restrict__ S,
-                                                            double* __restrict__ dinv, int n_fixed, int nF,
+// (S and dinv carry data between the CTAs of the cluster across barriers: deliberately not __restrict__)
+__global__ void __launch_bounds__(kBaSolveThreads) ba_solve(BaState* __restrict__ st, double* S, double* dinv, int n_fixed, int nF,
                                                             double* __restrict__ dC) {
     cg::cluster_group cluster = cg::this_cluster();
     if (st->done) return;                                   // uniform over the cluster
@@ -552,8 +552,9 @@ __host__ __device__ inline size_t ba_dsmem_doubles(int nF, int nr) {
            ba_dsmem_own_elems(nF, nr, 0);                                                       // rank 0 owns the most
 }
 
+// (Pg carries the published panels between the CTAs across barriers: deliberately not __restrict__)
 __global__ void __launch_bounds__(kBaSolveThreads) ba_solve_dsmem(BaState* __restrict__ st, const double* __restrict__ S,
-                                                                  double* __restrict__ Pg, int n_fixed, int nF,
+                                                                  double* Pg, int n_fixed, int nF,
                                                                   double* __restrict__ dC) {
     cg::cluster_group cluster = cg::this_cluster();
     if (st->done) return;                                   // uniform over the cluster
