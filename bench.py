@@ -420,7 +420,7 @@ def run_extras(args, rg, rt, cabi, lib, ctx, stream, dev, torch, fp32_peak) -> d
     # ---- config 2: Dino sequence through the host API (real data shapes, launch/latency bound) ---------------------
     try:
         pairs = [np.ascontiguousarray(np.hstack(synth.dino_noisy_pair(i, i + 1))) for i in range(35)]
-        idl = [sampling.fast(p.shape[0], 10000, 8, seed=i) for i, p in enumerate(pairs)]
+        idl = sampling.fast_batch([p.shape[0] for p in pairs], 10000, 8, seed=0)     # one buffer: no host concatenation
         rt.f_ransac_batched(pairs, idl, thr=1.5)
         t0 = time.perf_counter()
         for _ in range(5):

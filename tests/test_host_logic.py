@@ -183,3 +183,22 @@ def test_tables_bookkeeping_matches_reference_semantics(rg):
     # fun.getEFromCameras / crossProductMat are host helpers
     E = rg.fun.getEFromCameras(T.T_views[0].camera_pose, T.T_views[1].camera_pose)
     assert np.allclose(E, rg.fun.crossProductMat(np.array([1.0, 0.0, 0.0])))
+
+
+def test_fast_batch_is_the_per_pair_sampler_in_one_buffer(rg):
+    """sampling.fast_batch: same index sets as fast(n_p, H, k, seed + p), stored as consecutive row blocks of one array, which
+    runtime._consecutive recognises (no concatenation on the way to the library); anything else falls back to a copy."""
+    import numpy as np
+    from tsbb15_b200 import runtime as rt, sampling
+    ns = [300, 257, 40, 9]
+    blocks = sampling.fast_batch(ns, 500, 8, seed=11)
+    for p, n in enumerate(ns):
+        assert blocks[p].dtype == np.int32 and np.array_equal(blocks[p], sampling.fast(n, 500, 8, 11 + p))
+    whole = rt._consecutive(blocks)
+    assert whole is not None and whole.shape == (2000, 8) and np.array_equal(whole, np.concatenate(blocks))
+    assert whole.ctypes.data == blocks[0].ctypes.data                       # a view of the same memory, not a copy
+    assert rt._consecutive([blocks[0], blocks[2]]) is None                  # a gap
+    assert rt._consecutive([blocks[1], blocks[0]]) is None                  # wrong order
+    assert rt._consecutive([blocks[0], blocks[1].astype(np.int64)]) is None
+    assert rt._consecutive([blocks[0][:, :4], blocks[1][:, :4]]) is None    # not contiguous
+    assert rt._consecutive([]) is None

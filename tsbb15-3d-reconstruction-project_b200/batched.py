@@ -19,7 +19,7 @@ def f_ransac_pairs(pairs, n_hyp=10000, thr=1.5, seed=0, idx_list=None, **kw) -> 
         else:
             pts.append(np.ascontiguousarray(pr, dtype=np.float64).reshape(-1, 4))
     if idx_list is None:
-        idx_list = [_sampling.fast(p.shape[0], n_hyp, 8, seed + k) for k, p in enumerate(pts)]
+        idx_list = _sampling.fast_batch([p.shape[0] for p in pts], n_hyp, 8, seed)       # one buffer: no concatenation
     return _rt.f_ransac_batched(pts, idx_list, thr=thr, **kw)
 
 

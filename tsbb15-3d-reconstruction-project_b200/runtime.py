@@ -40,6 +40,26 @@ def _concat_into(key, arrays, tail, dtype) -> np.ndarray:
     return out
 
 
+def _consecutive(arrays):
+    """The arrays as ONE array without copying when they are C-contiguous row blocks that follow each other in memory
+    (e.g. the blocks of sampling.fast_batch), else None."""
+    if not arrays:
+        return None
+    a0 = arrays[0]
+    addr = a0.ctypes.data
+    rows = 0
+    for a in arrays:
+        if a.dtype != a0.dtype or a.shape[1:] != a0.shape[1:] or not a.flags.c_contiguous or a.ctypes.data != addr:
+            return None
+        addr += a.nbytes
+        rows += a.shape[0]
+    if rows == 0:
+        return None
+    flat = np.ctypeslib.as_array((np.ctypeslib.as_ctypes_type(a0.dtype) * (rows * int(np.prod(a0.shape[1:])))).from_address(
+        a0.ctypes.data))
+    return flat.reshape((rows,) + a0.shape[1:])           # memory stays owned by the callers' arrays (alive during the call)
+
+
 def pack_pairs(p1, p2) -> np.ndarray:
     """(2, N) + (2, N) reference layout  ->  (N, 4) rows (x0, x1, y0, y1)."""
     p1 = np.asarray(p1, dtype=np.float64)
@@ -95,7 +115,9 @@ def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TI
     #  call fail with ValueError — no host pass over the index arrays)
     Ntot, Htot = int(pair_off[-1]), int(hyp_off[-1])
     pts_all = _concat_into("f_pts", pts, (4,), np.float64)
-    idx_all = _concat_into("f_idx", idx, (8,), np.int32)
+    idx_all = _consecutive(idx)
+    if idx_all is None:
+        idx_all = _concat_into("f_idx", idx, (8,), np.int32)
     best_idx = np.full(P, -1, dtype=np.int32)
     best_count = np.zeros(P, dtype=np.int32)
     best_F = np.full((P, 3, 3), np.nan)
