@@ -41,6 +41,10 @@ const char* rg_last_error(void);
 int rg_init(int device, void** out_ctx);
 int rg_shutdown(void* ctx);
 int rg_device_sm_count(void* ctx);
+/* page-locked host memory for input batches built in place (the host-buffer entry points accept any host memory; uploads
+ * from pageable memory are staged by the driver at a fraction of the link rate) */
+int rg_host_alloc(size_t bytes, void** out);
+int rg_host_free(void* p);
 /* option 1 = phase profiling on/off: CUDA events on the launching stream around the phases of every RANSAC call
  * option 2 = number of sub-batches of rg_f_ransac_host (0 = automatic, 1 = monolithic, up to 8): the upload of sub-batch
  *            k+1 runs on a second stream while sub-batch k is scored; results do not depend on it

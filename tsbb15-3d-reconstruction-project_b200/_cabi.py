@@ -35,6 +35,8 @@ SIGNATURES = {
     "rg_init": (_i, [_i, C.POINTER(_vp)]),
     "rg_shutdown": (_i, [_vp]),
     "rg_device_sm_count": (_i, [_vp]),
+    "rg_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "rg_host_free": (_i, [_vp]),
     "rg_set_option": (_i, [_vp, _i, C.c_longlong]),
     "rg_get_profile": (_i, [_vp, _vp, _pd, C.POINTER(C.c_int)]),
     "rg_microbench_run": (_i, [_pd, _vp]),
@@ -130,6 +132,26 @@ def shutdown_all() -> None:
         for dev, h in list(_contexts.items()):
             lib.rg_shutdown(_vp(h))
             del _contexts[dev]
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """An uninitialised array in page-locked host memory (rg_host_alloc), freed when the array is collected.  Falls back
+    to ordinary memory when no CUDA device is usable (this only affects upload speed, never results)."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    try:
+        lib = load_library()
+        context()                                   # a device context must exist before page-locking
+        p = _vp()
+        if lib.rg_host_alloc(n, C.byref(p)) != 0 or not p.value:
+            raise RGError("rg_host_alloc failed")
+    except Exception:
+        return np.empty(shape, dtype=dtype)
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.rg_host_free, _vp(p.value))
+    return arr
 
 
 def ptr(a) -> int | None:

@@ -126,6 +126,20 @@ int rg_shutdown(void* ctx) {
     return RG_OK;
 }
 
+// page-locked host memory for callers that build their input batches in place (uploads from pageable memory are staged
+// by the driver at a fraction of the link rate); freed with rg_host_free
+int rg_host_alloc(size_t bytes, void** out) {
+    RG_CHECK_ARG(out != nullptr, "out is null");
+    *out = nullptr;
+    RG_CUDA(cudaMallocHost(out, bytes > 0 ? bytes : 1));
+    return RG_OK;
+}
+
+int rg_host_free(void* p) {
+    if (p) RG_CUDA(cudaFreeHost(p));
+    return RG_OK;
+}
+
 int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 
 // option 1: phase profiling (CUDA events on the launching stream around the phases of every RANSAC call)
