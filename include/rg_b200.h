@@ -53,10 +53,16 @@ int rg_host_free(void* p);
  * option 4 = 1: factorise that system in global memory / L2 even when it fits in the cluster's distributed shared memory
  *            (the default picks shared memory when it fits); results do not depend on it
  * option 5 = 1: gold-standard refinement always on the multi-kernel path (default: pairs of <= 4096 correspondences run
- *            the whole Levenberg-Marquardt loop in one CTA and one launch); same iteration, sums in a different order */
+ *            the whole Levenberg-Marquardt loop in one CTA and one launch); same iteration, sums in a different order
+ * option 6 = hypothesis x correspondence evaluations per PASS of a large RANSAC batch (0 = default 2.7e10 = 64 pairs of
+ *            50 000 x 8 192): a batch is processed in passes so that its workspaces stay bounded; results do not depend on it
+ * option 7 = PnP minimal-sample solver: 0 = Givens QR + Jacobi on the rows of R, one thread per hypothesis (default);
+ *            1 = register-resident one-sided Jacobi in a 16-lane group (the solver BASELINE.json names)
+ * option 8 = test hook: capacity of the guard-band flag list in records (0 = automatic); a small value forces the
+ *            FP64 recount of the hypotheses whose flags did not fit; results do not depend on it */
 int rg_set_option(void* ctx, int option, long long value);
-/* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the calls since the last read
- * (at most 256 calls are remembered); synchronises `stream` */
+/* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the PASSES since the last read
+ * (at most 256 passes are remembered; *out_calls = passes covered); synchronises `stream` */
 int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 
 /* Pipe micro-benchmarks on the context's device (roofline denominators for bench.py):
@@ -64,7 +70,8 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 int rg_microbench_run(double* out6, void* stream);
 
 /* out8 = {guard-band groups flagged by the FP32 scorer, band evaluations redone in FP64, decisions changed by that,
- *         0, hypotheses with an out-of-range sample index, 0, 0, kernel launches of the last call}.  Synchronises `stream`. */
+ *         hypotheses recounted in FP64 because the flag list was full, hypotheses with an out-of-range sample index, 0,
+ *         passes of the last call, kernel launches of the last call}.  Synchronises `stream`. */
 int rg_get_last_stats(void* ctx, void* stream, long long* out8);
 
 /* ---- F-matrix RANSAC: replaces the loop of fun.getFFromLabCode (fun.py:303-328), which calls
@@ -77,6 +84,35 @@ int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, con
                     const int32_t* idx_dev, const int32_t* hyp_off_host, double thr, int mode, int tie_mode, int solver,
                     int score_path, int32_t* best_idx_dev, int32_t* best_count_dev, double* best_F_dev,
                     unsigned char* mask_dev /* may be NULL */);
+/* Extended form (round 2).  Everything rg_f_ransac_dev does, plus
+ *   idx_dev == NULL : the (H, 8) sample index sets are drawn on the DEVICE (Philox4x32-10, csrc/philox.cuh) as a pure
+ *                     function of (sample_seed, first_pair_id + pair, hyp_index_base + hypothesis); they never cross
+ *                     PCIe and the host replays them bit for bit (tsbb15_b200/philox.py, rg_sample_indices_dev) — the
+ *                     reference draws np.random.choice(N, 8, replace=False) per trial, fun.py:305-308;
+ *   flags & RG_FLAG_REUSE_POINTS : the points, pair table and threshold are those of the previous call on this context:
+ *                     skip the bounding-box / FP32-copy kernels (hypothesis-split mode scores many hypothesis sets
+ *                     against one pair);
+ *   hyp_index_base  : hypothesis-split mode: this rank holds hypotheses [base, base + H_p) of every pair;
+ *   key_dev (P, optional) : the cross-GPU argmax key of every pair, (count << 32) | (0xFFFFFFFF - global hypothesis
+ *                     index), 0 if no hypothesis of this rank has an inlier (fun.py:320-323: first maximum wins). */
+#define RG_FLAG_REUSE_POINTS 1
+int rg_f_ransac_dev2(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                     const int32_t* idx_dev /* may be NULL */, const int32_t* hyp_off_host, double thr, int mode,
+                     int tie_mode, int solver, int score_path, int flags, unsigned long long sample_seed, int first_pair_id,
+                     int hyp_index_base, int32_t* best_idx_dev, int32_t* best_count_dev, double* best_F_dev,
+                     unsigned char* mask_dev /* may be NULL */, unsigned long long* key_dev /* may be NULL */);
+/* the index sets a seeded call draws (k = 6, 7, 8), for callers / oracles that want to see them: idx_out (hyp_off[P], k) */
+int rg_sample_indices_dev(void* ctx, void* stream, int P, const int32_t* n_points_host, const int32_t* hyp_off_host, int k,
+                          unsigned long long seed, int first_pair_id, int hyp_index_base, int32_t* idx_out_dev);
+/* synthetic correspondences of BASELINE configs 3-5 generated on the device (X ~ U(box) seen by two of the
+ * n_cams cameras drawn from seed_base + pair id, Gaussian pixel noise (Irwin-Hall 12), the first outlier_frac of the image-2
+ * points uniform in the image); host-replayable (tsbb15_b200/philox.py).  pts_out (P x N x 4), cam_pair_out (P x 2, opt.) */
+int rg_synth_two_view_dev(void* ctx, void* stream, int P, int first_pair_id, int N, const double* cams_host, int n_cams,
+                          const double* bbox6_host, unsigned long long seed_base, double outlier_frac, double sigma_px,
+                          double width, double height, double* pts_out_dev, int32_t* cam_pair_out_dev);
+/* inlier mask (reference criterion, fun.py:315-317) of ONE caller-supplied F per pair, device buffers */
+int rg_f_inlier_mask_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int32_t* pair_off_host,
+                         const double* F_dev, double thr, int mode, unsigned char* mask_dev);
 /* per-hypothesis results of the last rg_f_ransac_dev call on this context (device pointers, valid until the next call;
  * after rg_f_ransac_host they cover only its last sub-batch — use that function's counts / F_all / flags outputs):
  * counts (hyp_off[P] int32), F_all (hyp_off[P] x 9 doubles), flags (bit0: rank-deficient sample, bit1: non-finite F,
@@ -84,11 +120,20 @@ int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, con
  * rg_get_last_stats reports the number of such hypotheses in out8[4]) */
 int rg_f_last_hypotheses_dev(void* ctx, const int32_t** counts_dev, const double** F_all_dev,
                              const unsigned char** flags_dev);
-/* Same with host buffers; counts / F_all / flags / mask are optional (NULL = not copied back). */
+/* Same with host buffers; counts / F_all / flags / mask are optional (NULL = not copied back).  The batch is uploaded pass
+ * by pass on a second stream, so the copy of pass k+1 overlaps the scoring of pass k (page-locked buffers needed for the
+ * overlap; pageable ones are still correct). */
 int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off, const int32_t* idx,
                      const int32_t* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path,
                      int32_t* best_idx, int32_t* best_count, double* best_F, unsigned char* mask, int32_t* counts,
                      double* F_all, unsigned char* flags);
+
+/* idx == NULL: samples drawn on the device from (sample_seed, first_pair_id), see rg_f_ransac_dev2 */
+int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const int32_t* pair_off,
+                      const int32_t* idx /* may be NULL */, const int32_t* hyp_off, double thr, int mode, int tie_mode,
+                      int solver, int score_path, unsigned long long sample_seed, int first_pair_id, int32_t* best_idx,
+                      int32_t* best_count, double* best_F, unsigned char* mask, int32_t* counts, double* F_all,
+                      unsigned char* flags);
 
 /* Stage entry points (same kernels, one pair):
  * 8-point solve of H samples — lab3.fmatrix_stls on 8 points (lab3.py:269-329) */
@@ -126,6 +171,13 @@ int rg_pnp_ransac_batched_dev(void* ctx, void* stream, int V, const double* X_de
                               const int32_t* view_off_host, const int32_t* n_vote_host, const int32_t* idx_dev,
                               const int32_t* hyp_off_host, int n, double thr2, int score_path, int32_t* best_idx_dev,
                               int32_t* best_count_dev, double* Rt_dev, unsigned char* mask_dev);
+/* hypothesis-split mode (see rg_f_ransac_dev2): this rank holds hypotheses [hyp_index_base, hyp_index_base + H_v) of every
+ * view; key_dev (V, optional) receives the cross-GPU argmax keys (ransac.py:108: first maximum wins) */
+int rg_pnp_ransac_batched_dev2(void* ctx, void* stream, int V, const double* X_dev, const double* y_dev,
+                               const int32_t* view_off_host, const int32_t* n_vote_host, const int32_t* idx_dev,
+                               const int32_t* hyp_off_host, int n, double thr2, int score_path, int hyp_index_base,
+                               int32_t* best_idx_dev, int32_t* best_count_dev, double* Rt_dev, unsigned char* mask_dev,
+                               unsigned long long* key_dev);
 /* pnp.pnp_minimize(_3d_pts, img_pts, m) (pnp.py:132-152) for any m >= 6: X (m, 3), y (m, 2) -> R (3x3), t (3) */
 int rg_pnp_minimize_host(void* ctx, void* stream, int m, const double* X, const double* y, double* R, double* t);
 /* reprojection scoring of H caller-supplied poses (H x 12: R row-major then t) — ransac.py:96-105 */
@@ -236,6 +288,24 @@ int rg_argmax_pack_dev(void* stream, int P, const int32_t* best_idx_dev, const i
                        unsigned long long* key_dev);
 int rg_argmax_allreduce(void* nccl_comm, void* stream, unsigned long long* key_dev, int count);
 int rg_argmax_unpack_dev(void* stream, int P, const unsigned long long* key_dev, int32_t* best_idx_dev, int32_t* best_count_dev);
+
+/* The same reduction WITHOUT NCCL, fused into one kernel over NVLink peer memory (csrc/p2p_api.cu): every rank owns a small
+ * buffer that its peers map through CUDA IPC; one launch stores {key, payload} into every peer's buffer, raises a flag,
+ * waits (bounded) for the peers' flags and picks the maximum key with its payload (the winner's F, or R|t) — the key and
+ * the winner's model arrive in the same exchange, so no second collective is needed.
+ *   rg_p2p_create   every rank: allocate the buffer, return its 64-byte IPC handle
+ *   rg_p2p_connect  every rank, after the host all-gathered the handles (world x 64 bytes, rank order)
+ *   rg_p2p_argmax_exchange  collective on `stream`: P <= 64 keys as written by rg_f_ransac_dev2 / rg_pnp_ransac_batched_dev2
+ *                   (key_dev), payload_dev (P x npay doubles, npay <= 12); outputs the winner's GLOBAL index, count and
+ *                   payload on every rank; *status_dev (device int, zero it once) becomes 1 + r if rank r did not arrive
+ *                   within ~3 s instead of hanging the GPU
+ * One rank per GPU. */
+int rg_p2p_create(void* ctx, int rank, int world, void* handle_out64);
+int rg_p2p_connect(void* ctx, const void* handles_all);
+int rg_p2p_destroy(void* ctx);
+int rg_p2p_argmax_exchange(void* ctx, void* stream, int P, const unsigned long long* key_dev, const double* payload_dev,
+                           int npay, int32_t* best_idx_dev, int32_t* best_count_dev, double* payload_out_dev,
+                           int32_t* status_dev);
 
 #ifdef __cplusplus
 }

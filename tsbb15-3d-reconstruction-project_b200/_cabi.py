@@ -19,6 +19,7 @@ TIE_FIRST, TIE_REFERENCE = 0, 1
 SOLVER_QR, SOLVER_JACOBI = 0, 1
 SCORE_FP32_GUARDED, SCORE_FP64 = 0, 1
 TRI_OPTIMAL, TRI_LINEAR = 0, 1
+FLAG_REUSE_POINTS = 1
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -42,6 +43,16 @@ SIGNATURES = {
     "rg_microbench_run": (_i, [_pd, _vp]),
     "rg_get_last_stats": (_i, [_vp, _vp, _pll]),
     "rg_f_ransac_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "rg_f_ransac_dev2": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _i, C.c_ulonglong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rg_f_ransac_host2": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, C.c_ulonglong, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_sample_indices_dev": (_i, [_vp, _vp, _i, _pi, _pi, _i, C.c_ulonglong, _i, _i, _vp]),
+    "rg_synth_two_view_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, C.c_ulonglong, _d, _d, _d, _d, _vp, _vp]),
+    "rg_f_inlier_mask_dev": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _d, _i, _vp]),
+    "rg_pnp_ransac_batched_dev2": (_i, [_vp, _vp, _i, _vp, _vp, _pi, _pi, _vp, _pi, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rg_p2p_create": (_i, [_vp, _i, _i, _vp]),
+    "rg_p2p_connect": (_i, [_vp, _vp]),
+    "rg_p2p_destroy": (_i, [_vp]),
+    "rg_p2p_argmax_exchange": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rg_f_last_hypotheses_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "rg_f_ransac_host": (_i, [_vp, _vp, _i, _vp, _pi, _vp, _pi, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_f8pt_solve_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
@@ -134,19 +145,19 @@ def shutdown_all() -> None:
             del _contexts[dev]
 
 
-def pinned_empty(shape, dtype) -> np.ndarray:
+def pinned_empty(shape, dtype, device: int | None = None) -> np.ndarray:
     """An uninitialised array in page-locked host memory (rg_host_alloc), freed when the array is collected.  Falls back
-    to ordinary memory when no CUDA device is usable (this only affects upload speed, never results)."""
+    to ordinary memory when the library or a CUDA device is not usable (this only affects upload speed, never results)."""
     import weakref
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     try:
         lib = load_library()
-        context()                                   # a device context must exist before page-locking
+        context(device)                             # a context on the TARGET device must exist before page-locking
         p = _vp()
         if lib.rg_host_alloc(n, C.byref(p)) != 0 or not p.value:
             raise RGError("rg_host_alloc failed")
-    except Exception:
+    except (RGError, OSError):
         return np.empty(shape, dtype=dtype)
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

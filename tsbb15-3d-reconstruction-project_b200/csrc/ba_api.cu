@@ -40,10 +40,10 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
     // ---- host: observations sorted by point (stable), CSR by point and by view -------------------------------------
     const size_t n_int_base = (size_t)4 * nO + (size_t)nP + 1 + (size_t)nC + 1;
     const size_t n_int = n_int_base;
-    RG_CUDA(cudaEventSynchronize(c->staging_free));
+    RG_CUDA(cudaEventSynchronize(c->staging_free[0]));
     int rc;
-    if ((rc = ensure_pinned(c->h_stage, sizeof(int) * n_int))) return rc;
-    int* h = (int*)c->h_stage.ptr;
+    if ((rc = ensure_pinned(c->h_stage[0], sizeof(int) * n_int))) return rc;
+    int* h = (int*)c->h_stage[0].ptr;
     int* h_perm = h;                     // sorted position -> caller's observation index
     int* h_ocam = h_perm + nO;           // view of the sorted observation
     int* h_opt = h_ocam + nO;            // point of the sorted observation
@@ -154,7 +154,7 @@ static int bundle_adjust_dev(Ctx* c, cudaStream_t st, int nC, int nP, int nO, do
 
     RG_CUDA(cudaMemcpyAsync(d_int, h, sizeof(int) * n_int, cudaMemcpyHostToDevice, st));
     if (n_items) RG_CUDA(cudaMemcpyAsync(d_items_raw, h_items, sizeof(int) * item_ints, cudaMemcpyHostToDevice, st));
-    RG_CUDA(cudaEventRecord(c->staging_free, st));
+    RG_CUDA(cudaEventRecord(c->staging_free[0], st));
     RG_CUDA(cudaMemsetAsync(dC, 0, sizeof(double) * 12 * std::max(nC, 1), st));
     int launches = 0;
     ba_init<<<1, 1, 0, st>>>(bs, 1e-3);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <vector>
 
 namespace rg {
 
@@ -66,7 +67,7 @@ struct __align__(16) Pose32 {
 };
 static_assert(sizeof(Pose32) == 64, "Pose32 layout");
 
-constexpr int kSub = 8;             // points per guard-band flag bit (FP32 scorer); 32 flags = one bitmap word = 256 points
+constexpr int kSub = 8;             // points per guard-band flag (FP32 scorer); a thread collects 32 flags (256 points) per list append
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -133,19 +134,24 @@ struct Buffer {
     size_t cap = 0;
 };
 
-// Per image pair: integer geometry of the batch (filled on the host, uploaded once per call) and the
-// FP32 scoring frame (filled on the device by the prepare kernels).
+// Per image pair: integer geometry of the batch (filled on the host, uploaded once per pass).
 struct PairInfo {
     int pt_off, n;             // offset / count in the caller's pts64 array (points)
     int pt_off32, n_pad;       // offset / count in the normalised FP32 copy (points, multiples of kSub)
     int hyp_off, H;            // offset / count in the hypothesis arrays
     int item_off, nsplit;      // scorer work items of this pair: [item_off, item_off + ceil(H/kHypPerBlock)*nsplit)
-    int groups_per_split;      // kSub-point groups handled by one item (multiple of 32 when nsplit > 1)
-    int words_per_hyp;         // guard-band bitmap: one bit per (hypothesis, group) -> ceil(n_pad / kSub / 32) words
-    int n_all, pad1;           // PnP: all correspondences of the view (n = those that vote, n <= n_all); F path: n_all == n
-    long long word_off;        // offset of this pair's words in the bitmap: word(h, w) = word_off + h * words_per_hyp + w
+    int groups_per_split;      // kSub-point groups handled by one item
+    int n_all;                 // PnP: all correspondences of the view (n = those that vote, n <= n_all); F path: n_all == n
+    int hyp_first;             // index of the pair's first hypothesis inside the pair's full hypothesis set (hypothesis-split
+                               // mode: this rank holds hypotheses [hyp_first, hyp_first + H) of the pair); 0 otherwise
+    int pad0;
+};
+static_assert(sizeof(PairInfo) == 48, "PairInfo layout");
 
-    // frame of the FP32 scorer: x~ = (x - c1)/thr, y~ = (y - c2)/thr  => threshold is exactly 1, |x~|,|y~| <= B
+// Frame of the FP32 scorer, computed on the device from the pair's bounding box (f_normalise):
+// x~ = (x - c1)/thr, y~ = (y - c2)/thr  => threshold is exactly 1, |x~|,|y~| <= B.  Kept apart from PairInfo so that a
+// caller who scores several hypothesis sets against the same points (hypothesis-split mode) prepares the points once.
+struct PairFrame {
     double c1x, c1y, c2x, c2y;
     double thr, B;
 };
@@ -154,7 +160,25 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     // device workspaces (grow-only)
-    Buffer pair_info, bbox, pts32, F64, hyp32, flags, counts, bitmap, stats, best, tie_stats;
+    Buffer pair_info, pair_frame, state, pts32, F64, hyp32, flags, flag_list, stats, best, tie_stats, bbox;
+    // `state` = everything one cudaMemsetAsync clears per pass: [bbox keys][counts][work counter, list size][ovf bytes]
+    int* counts_ptr = nullptr;                     // inside `state` (valid after f_state_layout of the current pass)
+    unsigned char* ovf_ptr = nullptr;
+    Buffer gen_idx;                                // device-drawn sample indices of the current pass (seeded calls)
+    // points prepared by the last F pass (RG_FLAG_REUSE_POINTS: score another hypothesis set against the same points)
+    const void* prep_pts = nullptr; int prep_P = 0; long long prep_N = 0; double prep_thr = 0.0; unsigned long long prep_hash = 0;
+    int last_passes = 0;                           // passes of the last RANSAC call (per-hypothesis results cover the last pass)
+    // measured rates (exponential averages over the host-buffer calls) that size the first upload sub-batch
+    double rate_evals_per_s = 0.0, rate_h2d_bytes_per_s = 0.0;
+    cudaEvent_t rate_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool pnp_rows_attr_set = false;                // dynamic shared memory limit of pnp_solve_rows raised on this device
+    int opt_pnp_solver = 0;                        // option 7: 0 = Givens-QR + row Jacobi (default), 1 = 16-lane group Jacobi
+    long long opt_list_cap = 0;                    // option 8 (test hook): capacity of the guard-band flag list in records (0 = automatic)
+    long long opt_pass_evals = 0;                  // option 6: evaluations per pass of a large batch (0 = default)
+    // peer-to-peer argmax exchange (hypothesis-split mode over NVLink), see p2p_api.cu
+    void* p2p_local = nullptr; size_t p2p_bytes = 0; int p2p_rank = 0, p2p_world = 0; unsigned p2p_seq = 0;
+    void* p2p_peer[16] = {nullptr};
+
     Buffer d_in_a, d_in_b, d_in_c;                 // device copies of host inputs (host-buffer entry points)
     Buffer d_out_a, d_out_b, d_out_c, d_out_d;     // device outputs of host-buffer entry points
     Buffer pose64, pose32, X32;                    // PnP path
@@ -170,13 +194,14 @@ struct Ctx {
     cudaEvent_t ba_iter_ev[2] = {nullptr, nullptr};
     bool ba_attr_set = false;                      // dynamic shared memory limit of ba_solve raised on this device
     // pinned host staging for the small per-call tables and the statistics read-back
-    Buffer h_stage, h_stats;
-    cudaEvent_t staging_free = nullptr;            // recorded after the last H2D that reads h_stage
+    Buffer h_stage[2], h_stats;                    // PairInfo staging, double buffered: the host plans pass k+1 while pass k runs
+    cudaEvent_t staging_free[2] = {nullptr, nullptr};   // recorded after the H2D that reads h_stage[i]
+    int stage_turn = 0;
     // host-buffer entry points: inputs are uploaded on a second stream in sub-batches so that the copy of sub-batch
     // k+1 overlaps the kernels of sub-batch k
     static constexpr int kMaxSlices = 8;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t slice_ready[kMaxSlices] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> pass_ready;           // one per pass of the host entry point: its inputs have arrived
     cudaEvent_t copy_gate = nullptr;               // recorded on the caller's stream before the first upload
     int opt_host_slices = 0;                       // option 2: 0 = automatic, n >= 1 = force n sub-batches
     bool accumulate_stats = false;                 // sub-batches after the first add to the call's statistics
@@ -186,7 +211,9 @@ struct Ctx {
     static constexpr int kProfPhases = 5;          // prepare, solve, score kernel, fixup+repair, select
     static constexpr int kProfRing = 256;          // calls remembered between two reads
     cudaEvent_t* prof_ev = nullptr;                // kProfRing * (kProfPhases + 1) events
-    int prof_calls = 0;                            // test hook: cap of the recheck work-list (0 = automatic)
+    int prof_calls = 0;                            // calls recorded in the ring since profiling was switched on / last read
+    bool prof_open = false;                        // boundary 0 of the current call was recorded (ring not full)
+    unsigned prof_masks[kProfRing] = {0};          // boundaries recorded per pass
 };
 
 int ensure_pinned(Buffer& b, size_t bytes);
@@ -194,5 +221,6 @@ void prof_mark(Ctx* c, cudaStream_t st, int boundary);   // boundary 0 opens a c
 void release_pinned(Buffer& b);
 int ensure(Buffer& b, size_t bytes);      // grow-only cudaMalloc
 void release(Buffer& b);
+void p2p_release(Ctx* c);                 // p2p_api.cu
 
 }  // namespace rg

@@ -46,15 +46,22 @@ void release(Buffer& b) {
     b.cap = 0;
 }
 
+// boundary 0 opens a pass (dropped, together with the pass's other boundaries, once the ring is full); boundaries
+// 1..kProfPhases close the phases.  prof_masks[] remembers which boundaries of a pass were recorded, so a pass that
+// failed half-way is skipped by rg_get_profile instead of pairing events of different passes.
 void prof_mark(Ctx* c, cudaStream_t st, int boundary) {
     if (!c->opt_profile || !c->prof_ev) return;
     if (boundary == 0) {
-        if (c->prof_calls >= Ctx::kProfRing) return;          // ring full: later calls are not profiled
+        c->prof_open = c->prof_calls < Ctx::kProfRing;
+        if (!c->prof_open) return;
+        c->prof_masks[c->prof_calls] = 0u;
+        c->prof_calls++;
     }
-    const int call = boundary == 0 ? c->prof_calls : c->prof_calls - 1;
-    if (call < 0 || call >= Ctx::kProfRing) return;
-    cudaEventRecord(c->prof_ev[call * (Ctx::kProfPhases + 1) + boundary], st);
-    if (boundary == 0) c->prof_calls++;
+    if (!c->prof_open) return;
+    const int call = c->prof_calls - 1;
+    if (call < 0 || call >= Ctx::kProfRing || boundary < 0 || boundary > Ctx::kProfPhases) return;
+    if (cudaEventRecord(c->prof_ev[call * (Ctx::kProfPhases + 1) + boundary], st) == cudaSuccess)
+        c->prof_masks[call] |= 1u << boundary;
 }
 
 void release_pinned(Buffer& b) {
@@ -93,7 +100,7 @@ int rg_init(int device, void** out_ctx) {
     Ctx* c = new Ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    RG_CUDA(cudaEventCreateWithFlags(&c->staging_free, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) RG_CUDA(cudaEventCreateWithFlags(&c->staging_free[i], cudaEventDisableTiming));
     *out_ctx = c;
     return RG_OK;
 }
@@ -103,11 +110,12 @@ int rg_shutdown(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (Buffer* b : {&c->pair_info, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags, &c->counts, &c->bitmap,
-                      &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->ba_ws, &c->d_out_a, &c->d_out_b,
+    for (Buffer* b : {&c->pair_info, &c->pair_frame, &c->state, &c->bbox, &c->pts32, &c->F64, &c->hyp32, &c->flags,
+                      &c->flag_list, &c->gen_idx, &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->ba_ws, &c->d_out_a, &c->d_out_b,
                       &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
         release(*b);
-    release_pinned(c->h_stage);
+    release_pinned(c->h_stage[0]);
+    release_pinned(c->h_stage[1]);
     release_pinned(c->h_stats);
     release_pinned(c->h_ba_flags);
     release_pinned(c->h_ba_items);
@@ -117,10 +125,13 @@ int rg_shutdown(void* ctx) {
         for (int i = 0; i < Ctx::kProfRing * (Ctx::kProfPhases + 1); ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
     }
-    if (c->staging_free) cudaEventDestroy(c->staging_free);
+    for (int i = 0; i < 2; ++i)
+        if (c->staging_free[i]) cudaEventDestroy(c->staging_free[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
-    for (int i = 0; i < Ctx::kMaxSlices; ++i)
-        if (c->slice_ready[i]) cudaEventDestroy(c->slice_ready[i]);
+    for (cudaEvent_t e : c->pass_ready) cudaEventDestroy(e);
+    for (int i = 0; i < 4; ++i)
+        if (c->rate_ev[i]) cudaEventDestroy(c->rate_ev[i]);
+    p2p_release(c);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     return RG_OK;
@@ -148,12 +159,16 @@ int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 // option 4: 1 = factorise the bundle-adjustment camera system in L2 even when it fits in distributed shared memory
 // option 5: 1 = gold-standard refinement always on the multi-kernel path (default: pairs of <= 4096 points run the whole
 //           Levenberg-Marquardt loop in one CTA, one launch)
+// option 6: hypothesis x correspondence evaluations per pass of a large RANSAC batch (0 = default 2.7e10)
+// option 7: PnP minimal-sample solver: 0 = Givens QR + row Jacobi, thread per hypothesis (default); 1 = 16-lane group Jacobi
+// option 8: test hook: capacity of the guard-band flag list in records (0 = automatic); a tiny value forces the FP64 recount
 int rg_set_option(void* ctx, int option, long long value) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
     if (option == 1) {
         c->opt_profile = value != 0;
         c->prof_calls = 0;
+        c->prof_open = false;
         if (c->opt_profile && !c->prof_ev) {
             const int n = Ctx::kProfRing * (Ctx::kProfPhases + 1);
             c->prof_ev = new cudaEvent_t[n];
@@ -185,6 +200,21 @@ int rg_set_option(void* ctx, int option, long long value) {
         c->opt_gs_multi = value != 0;
         return RG_OK;
     }
+    if (option == 6) {
+        if (value < 0) { set_error("invalid argument: option 6 (evaluations per pass) must be >= 0"); return RG_ERR_ARG; }
+        c->opt_pass_evals = value;
+        return RG_OK;
+    }
+    if (option == 7) {
+        if (value != 0 && value != 1) { set_error("invalid argument: option 7 (PnP minimal solver) must be 0 or 1"); return RG_ERR_ARG; }
+        c->opt_pnp_solver = (int)value;
+        return RG_OK;
+    }
+    if (option == 8) {
+        if (value < 0 || value > 1000000000ll) { set_error("invalid argument: option 8 (flag list capacity) must be in [0, 1e9]"); return RG_ERR_ARG; }
+        c->opt_list_cap = value;
+        return RG_OK;
+    }
     set_error("invalid argument: unknown option %d", option);
     return RG_ERR_ARG;
 }
@@ -199,15 +229,20 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls) {
     RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     for (int k = 0; k < Ctx::kProfPhases; ++k) out_ms5[k] = 0.0;
     *out_calls = c->prof_calls;
+    int complete = 0;
     for (int call = 0; call < c->prof_calls; ++call) {
+        if (c->prof_masks[call] != (1u << (Ctx::kProfPhases + 1)) - 1u) continue;      // pass aborted between two boundaries
         cudaEvent_t* e = c->prof_ev + call * (Ctx::kProfPhases + 1);
         for (int k = 0; k < Ctx::kProfPhases; ++k) {
             float ms = 0.f;
             RG_CUDA(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
             out_ms5[k] += ms;
         }
+        ++complete;
     }
+    *out_calls = complete;
     c->prof_calls = 0;
+    c->prof_open = false;
     return RG_OK;
 }
 

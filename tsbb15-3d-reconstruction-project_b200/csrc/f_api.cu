@@ -1,56 +1,122 @@
 // Host orchestration + C ABI of the F-matrix RANSAC path.  See include/rg_b200.h for the contract of each entry point.
+//
+// One call = one or more PASSES.  A pass is the launch chain
+//   memset(state) -> [sample_indices] -> [f_bbox -> f_normalise] -> f8_solve -> score_packed -> fixup_list -> argmax_counts
+//   -> [f_tie_stats -> f_tie_resolve] -> f_mask
+// over a contiguous block of pairs whose workspaces (hypotheses, FP32 points, flag list) stay bounded; BASELINE config 5
+// (4096 pairs x 50 000 x 8 192) runs as 64 passes of 64 pairs.  The per-pass PairInfo table is planned on the host into
+// double-buffered pinned staging, so the host plans pass k+1 while pass k runs.
 #include "f_kernels.cuh"
 #include "jacobi.cuh"
+#include "philox.cuh"
 #include "plan.cuh"
 #include <algorithm>
 #include <vector>
 
 namespace rg {
 
-static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, double thr) {
-    const int P = plan.P;
-    int rc;
-    if ((rc = ensure(c->bbox, sizeof(int) * 8 * (size_t)P))) return rc;
-    if ((rc = ensure(c->pts32, sizeof(float4) * (size_t)std::max<long long>(plan.N32tot, 1)))) return rc;
-    PairInfo* pi = (PairInfo*)c->pair_info.ptr;
-    f_bbox_init<<<ceil_div(P * 8, 256), 256, 0, st>>>((int*)c->bbox.ptr, P);
-    const int nbx = std::max(1, std::min(64, ceil_div(plan.maxN, 256 * 4)));
-    f_bbox<<<dim3(nbx, P), 256, 0, st>>>((const double4*)pts64, pi, (int*)c->bbox.ptr);
-    f_frame<<<ceil_div(P, 128), 128, 0, st>>>(pi, (const int*)c->bbox.ptr, P, thr);
-    const int nbn = std::max(1, std::min(128, ceil_div(plan.maxN / 2 + kSub, 256)));
-    f_normalise<<<dim3(nbn, P), 256, 0, st>>>((const double4*)pts64, pi, (float4*)c->pts32.ptr);
-    c->last_stats[7] += 4;
-    RG_CUDA(cudaGetLastError());
+enum : int { FLAG_REUSE_POINTS = 1 };
+
+constexpr double kDefaultPassEvals = 2.7e10;        // 64 pairs of the config-5 shape
+constexpr long long kMaxPassHyp = 1ll << 22;        // hypotheses per pass (F64 workspace 288 MB)
+
+struct ScoreState {
+    unsigned* bbox; int* counts; int* work; unsigned* list_n; unsigned char* ovf;
+    size_t off_counts, bytes;
+};
+
+// [bbox keys: P x words][counts: H][work counter][list size][pad][ovf: H bytes] — one cudaMemsetAsync clears a pass's state
+int score_state_layout(Ctx* c, int P, long long Htot, int bbox_words, ScoreState& s) {
+    const size_t H = (size_t)std::max<long long>(Htot, 1);
+    const size_t bbox_bytes = (((size_t)std::max(P, 1) * bbox_words * 4) + 15) / 16 * 16;
+    const size_t cnt_bytes = ((H + 2) * 4 + 15) / 16 * 16;
+    const size_t ovf_bytes = (H + 15) / 16 * 16;
+    s.off_counts = bbox_bytes;
+    s.bytes = bbox_bytes + cnt_bytes + ovf_bytes;
+    int rc = ensure(c->state, s.bytes);
+    if (rc) return rc;
+    char* base = (char*)c->state.ptr;
+    s.bbox = (unsigned*)base;
+    s.counts = (int*)(base + bbox_bytes);
+    s.work = s.counts + H;
+    s.list_n = (unsigned*)(s.counts + H + 1);
+    s.ovf = (unsigned char*)(base + bbox_bytes + cnt_bytes);
+    c->counts_ptr = s.counts;
+    c->ovf_ptr = s.ovf;
     return RG_OK;
 }
 
-static int f_workspace(Ctx* c, const FPlan& plan) {
+FlagList flag_list_for(Ctx* c, const ScoreState& s, double evals, int* rc_out) {
+    FlagList L{nullptr, s.list_n, 0u, s.ovf};
+    double want = evals / 512.0 + 65536.0;            // ~4.3x the measured 4.5e-4 records per evaluation
+    if (c->opt_list_cap > 0) want = (double)c->opt_list_cap;
+    const unsigned cap = (unsigned)std::min(want, 1.0e9);
+    *rc_out = ensure(c->flag_list, sizeof(int2) * (size_t)cap);
+    L.rec = (int2*)c->flag_list.ptr;
+    L.cap = cap;
+    return L;
+}
+
+struct FCall {
+    int P = 0;
+    const double* pts64 = nullptr; const int* pair_off = nullptr;
+    const int* idx = nullptr;      const int* hyp_off = nullptr;
+    double thr = 1.5;
+    int mode = MODE_EPI_MAX, tie_mode = TIE_FIRST, solver = SOLVER_QR, score_path = SCORE_FP32_GUARDED, flags = 0;
+    unsigned long long sample_seed = 0; int first_pair = 0; int hyp_first = 0;
+    int* best_idx = nullptr; int* best_count = nullptr; double* best_F = nullptr; unsigned char* mask = nullptr;
+    unsigned long long* keys = nullptr;
+};
+
+static unsigned long long hash_offsets(const int* off, int n) {
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i <= n; ++i) { h ^= (unsigned)off[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static int f_workspace(Ctx* c, const FPlan& plan, bool seeded) {
     int rc;
     const size_t H = (size_t)std::max<long long>(plan.Htot, 1);
     if ((rc = ensure(c->F64, sizeof(double) * 9 * H))) return rc;
     if ((rc = ensure(c->hyp32, sizeof(Hyp32) * H))) return rc;
     if ((rc = ensure(c->flags, H))) return rc;
-    if ((rc = ensure(c->counts, sizeof(int) * (H + 1)))) return rc;      // + the scorer's work counter
     if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
     if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure(c->tie_stats, sizeof(double2) * H))) return rc;
+    if ((rc = ensure(c->pair_frame, sizeof(PairFrame) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
-    if ((rc = ensure(c->bitmap, sizeof(unsigned) * (size_t)std::max<long long>(plan.total_words, 1)))) return rc;
+    if (seeded && (rc = ensure(c->gen_idx, sizeof(int) * 8 * H))) return rc;
+    return RG_OK;
+}
+
+static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr) {
+    int rc;
+    if ((rc = ensure(c->pts32, sizeof(float4) * (size_t)std::max<long long>(plan.N32tot, 1)))) return rc;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    const int P = plan.P;
+    const int nbx = std::max(1, std::min(64, ceil_div(plan.maxN, 256 * 4)));
+    f_bbox<<<dim3(nbx, P), 256, 0, st>>>((const double4*)pts64, pi, s.bbox);
+    const int nbn = std::max(1, std::min(128, ceil_div(plan.maxN / 2 + kSub, 256)));
+    f_normalise<<<dim3(nbn, P), 256, 0, st>>>((const double4*)pts64, pi, s.bbox, thr, (PairFrame*)c->pair_frame.ptr,
+                                              (float4*)c->pts32.ptr);
+    c->last_stats[7] += 2;
+    RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
 
 template <int MODE>
 static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, const int* idx, int solver) {
-    PairInfo* pi = (PairInfo*)c->pair_info.ptr;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    const PairFrame* fr = (const PairFrame*)c->pair_frame.ptr;
     if (plan.Htot == 0) return RG_OK;
     if (solver == SOLVER_QR) {
-        f8_solve_qr<MODE><<<ceil_div(plan.Htot, 128), 128, 0, st>>>((const double4*)pts64, idx, pi, plan.P, (int)plan.Htot,
+        f8_solve_qr<MODE><<<ceil_div(plan.Htot, 128), 128, 0, st>>>((const double4*)pts64, idx, pi, fr, plan.P, (int)plan.Htot,
                                                                   (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
                                                                   (unsigned char*)c->flags.ptr);
     } else {
         const int groups_per_block = kJacobiThreads / 16;
         f8_solve_jacobi<MODE><<<ceil_div(plan.Htot, groups_per_block), kJacobiThreads, 0, st>>>(
-            (const double4*)pts64, idx, pi, plan.P, (int)plan.Htot, (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
+            (const double4*)pts64, idx, pi, fr, plan.P, (int)plan.Htot, (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
             (unsigned char*)c->flags.ptr);
     }
     c->last_stats[7] += 1;
@@ -58,33 +124,34 @@ static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     return RG_OK;
 }
 
+// counts / work counter / flag list are already cleared by the pass's memset
 template <int MODE>
-static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, int score_path) {
-    PairInfo* pi = (PairInfo*)c->pair_info.ptr;
-    int* counts = (int*)c->counts.ptr;
+static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
+                          int score_path) {
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)std::max<long long>(plan.Htot, 1) + 1), st));   // counts + work counter
-    if (!c->accumulate_stats) RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
-    if (plan.Htot == 0 || plan.Ntot == 0) return RG_OK;
+    if (plan.Htot == 0 || plan.Ntot == 0 || (score_path == SCORE_FP32_GUARDED && plan.n_items == 0)) {
+        prof_mark(c, st, 3);
+        return RG_OK;
+    }
     if (score_path == SCORE_FP32_GUARDED) {
-        if (plan.n_items > 0) {
-            constexpr size_t smem = score_smem_bytes<EpiPolicy<MODE>>();
-            const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<EpiPolicy<MODE>>());
-            score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>(
-                (const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr, pi, plan.P, plan.n_items, counts,
-                (unsigned*)c->bitmap.ptr, counts + std::max<long long>(plan.Htot, 1));
-            prof_mark(c, st, 3);
-            const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
-                                                                              (plan.total_words + 255) / 256));
-            typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
-                                             (const double*)c->F64.ptr, pi, plan.P};
-            fixup_scan<EpiFix<MODE>><<<fgrid, 256, 0, st>>>(fp, plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
-            c->last_stats[7] += 2;
-        }
+        int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE>>(&bps);
+        if (rc) return rc;
+        FlagList fl = flag_list_for(c, s, plan.evals, &rc);
+        if (rc) return rc;
+        constexpr size_t smem = score_smem_bytes<EpiPolicy<MODE>>();
+        const int grid = std::min(plan.n_items, c->sm_count * bps);
+        score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>((const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr,
+                                                                        pi, plan.P, plan.n_items, s.counts, fl, s.work);
+        prof_mark(c, st, 3);
+        typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
+                                         (const double*)c->F64.ptr, pi, (const PairFrame*)c->pair_frame.ptr, plan.P};
+        fixup_list<EpiFix<MODE>><<<c->sm_count * 4, 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
+        c->last_stats[7] += 2;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
-        f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, zs), 128, 0, st>>>(
-            (const double4*)pts64, (const double*)c->F64.ptr, pi, MODE, counts);
+        f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, zs), 128, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr,
+                                                                                 pi, thr, MODE, s.counts);
         prof_mark(c, st, 3);
         c->last_stats[7] += 1;
     }
@@ -92,69 +159,168 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     return RG_OK;
 }
 
-static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, int mode, int tie_mode,
-                           unsigned char* mask, double* best_F, int* best_idx, int* best_count) {
+static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
+                           int mode, int tie_mode, unsigned char* mask, double* best_F, int* best_idx, int* best_count,
+                           unsigned long long* keys) {
     if (plan.P == 0) return RG_OK;
-    PairInfo* pi = (PairInfo*)c->pair_info.ptr;
-    int* counts = (int*)c->counts.ptr;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     int2* best = (int2*)c->best.ptr;
-    argmax_counts<<<plan.P, 256, 0, st>>>(counts, pi, best, (const unsigned char*)c->flags.ptr,
-                                          (unsigned long long*)c->stats.ptr);
+    const bool tie = tie_mode == TIE_REFERENCE && plan.Htot > 0;
+    argmax_counts<<<plan.P, 256, 0, st>>>(s.counts, pi, best, (const unsigned char*)c->flags.ptr,
+                                          (unsigned long long*)c->stats.ptr, tie ? nullptr : keys);
     c->last_stats[7] += 1;
-    if (tie_mode == TIE_REFERENCE && plan.Htot > 0) {
+    if (tie) {
         const int nb = (int)std::min<long long>(plan.Htot, (long long)c->sm_count * 8);
-        f_tie_stats<<<nb, 256, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr, counts, pi, plan.P,
+        f_tie_stats<<<nb, 256, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr, s.counts, pi, plan.P,
                                         (int)plan.Htot, best, mode, (double2*)c->tie_stats.ptr);
-        f_tie_resolve<<<plan.P, 32, 0, st>>>(counts, pi, (const double2*)c->tie_stats.ptr, best);
+        f_tie_resolve<<<plan.P, 32, 0, st>>>(s.counts, pi, (const double2*)c->tie_stats.ptr, best, keys);
         c->last_stats[7] += 2;
     }
-    const int nbx = std::max(1, std::min(64, ceil_div(plan.maxN, 256 * 4)));
-    f_mask<<<dim3(nbx, plan.P), 256, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr, pi, best, mode, mask, best_F,
+    const int nbx = mask ? std::max(1, std::min(64, ceil_div(plan.maxN, 256 * 4))) : 1;
+    f_mask<<<dim3(nbx, plan.P), 256, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr, pi, best, thr, mode, mask, best_F,
                                               best_idx, best_count);
     c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
 
-static int f_stats_readback(Ctx* c, cudaStream_t st) {
-    RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+// one pass on device pointers; offsets are relative to the pass
+static int f_pass(Ctx* c, cudaStream_t st, const FCall& a) {
+    FPlan plan;
+    int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>(&bps);
+    if (rc) return rc;
+    if ((rc = f_plan(c, st, a.P, a.pair_off, a.hyp_off, plan, bps, nullptr, a.hyp_first))) return rc;
+    for (int p = 0; p < a.P; ++p) {
+        const int n = a.pair_off[p + 1] - a.pair_off[p], H = a.hyp_off[p + 1] - a.hyp_off[p];
+        RG_CHECK_ARG(H == 0 || n >= 8, "a pair with hypotheses needs at least 8 correspondences");
+    }
+    const bool seeded = a.idx == nullptr && plan.Htot > 0;
+    if ((rc = f_workspace(c, plan, seeded))) return rc;
+    ScoreState s;
+    if ((rc = score_state_layout(c, a.P, plan.Htot, 8, s))) return rc;
+    if (a.P == 0) return RG_OK;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+
+    bool reuse = (a.flags & FLAG_REUSE_POINTS) != 0;
+    const unsigned long long hsh = hash_offsets(a.pair_off, a.P);
+    if (reuse) {
+        RG_CHECK_ARG(c->prep_pts == (const void*)a.pts64 && c->prep_P == a.P && c->prep_N == plan.Ntot &&
+                         c->prep_thr == a.thr && c->prep_hash == hsh,
+                     "RG_FLAG_REUSE_POINTS: the previous pass on this context prepared different points / threshold");
+    }
+    prof_mark(c, st, 0);
+    // one memset clears the pass's state (the bounding boxes only when the points are prepared in this pass)
+    const size_t from = reuse ? s.off_counts : 0;
+    RG_CUDA(cudaMemsetAsync((char*)c->state.ptr + from, 0, s.bytes - from, st));
+    const int* idx = a.idx;
+    if (seeded) {
+        sample_indices_kernel<8><<<ceil_div(plan.Htot, 256), 256, 0, st>>>(pi, a.P, (int)plan.Htot, a.sample_seed,
+                                                                            (unsigned)a.first_pair, (int*)c->gen_idx.ptr);
+        c->last_stats[7] += 1;
+        idx = (const int*)c->gen_idx.ptr;
+    }
+    if (!reuse) {
+        c->prep_pts = nullptr;
+        if ((rc = f_prepare(c, st, plan, s, a.pts64, a.thr))) return rc;
+        c->prep_pts = a.pts64; c->prep_P = a.P; c->prep_N = plan.Ntot; c->prep_thr = a.thr; c->prep_hash = hsh;
+    }
+    prof_mark(c, st, 1);
+    rc = (a.mode == MODE_SAMPSON) ? f_solve_launch<MODE_SAMPSON>(c, st, plan, a.pts64, idx, a.solver)
+                                  : f_solve_launch<MODE_EPI_MAX>(c, st, plan, a.pts64, idx, a.solver);
+    if (rc) return rc;
+    prof_mark(c, st, 2);
+    rc = (a.mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, a.pts64, a.thr, a.score_path)
+                                  : f_score_launch<MODE_EPI_MAX>(c, st, plan, s, a.pts64, a.thr, a.score_path);
+    if (rc) return rc;
+    prof_mark(c, st, 4);
+    if ((rc = f_select_launch(c, st, plan, s, a.pts64, a.thr, a.mode, a.tie_mode, a.mask, a.best_F, a.best_idx, a.best_count,
+                              a.keys)))
+        return rc;
+    prof_mark(c, st, 5);
     return RG_OK;
 }
 
-// full pipeline on device pointers; asynchronous with respect to the host except for the tiny PairInfo staging
-static int f_ransac_dev(Ctx* c, cudaStream_t st, int P, const double* pts64, const int* pair_off, const int* idx,
-                        const int* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path, int* best_idx,
-                        int* best_count, double* best_F, unsigned char* mask) {
-    RG_CHECK_ARG(thr > 0.0 && std::isfinite(thr), "thr must be positive and finite");
-    RG_CHECK_ARG(mode == MODE_EPI_MAX || mode == MODE_SAMPSON, "unknown scoring mode");
-    RG_CHECK_ARG(tie_mode == TIE_FIRST || tie_mode == TIE_REFERENCE, "unknown tie mode");
-    RG_CHECK_ARG(solver == SOLVER_QR || solver == SOLVER_JACOBI, "unknown solver");
-    RG_CHECK_ARG(score_path == SCORE_FP32_GUARDED || score_path == SCORE_FP64, "unknown scoring path");
-    RG_CUDA(cudaSetDevice(c->device));
-    FPlan plan;
-    int rc = f_plan(c, st, P, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
-    if (rc) return rc;
-    for (int p = 0; p < P; ++p) {
-        const int n = pair_off[p + 1] - pair_off[p], H = hyp_off[p + 1] - hyp_off[p];
-        RG_CHECK_ARG(H == 0 || n >= 8, "a pair with hypotheses needs at least 8 correspondences");
+static int f_check_call(const FCall& a) {
+    RG_CHECK_ARG(a.P >= 0 && a.pair_off && a.hyp_off, "bad pair table");
+    RG_CHECK_ARG(a.thr > 0.0 && std::isfinite(a.thr), "thr must be positive and finite");
+    RG_CHECK_ARG(a.mode == MODE_EPI_MAX || a.mode == MODE_SAMPSON, "unknown scoring mode");
+    RG_CHECK_ARG(a.tie_mode == TIE_FIRST || a.tie_mode == TIE_REFERENCE, "unknown tie mode");
+    RG_CHECK_ARG(a.solver == SOLVER_QR || a.solver == SOLVER_JACOBI, "unknown solver");
+    RG_CHECK_ARG(a.score_path == SCORE_FP32_GUARDED || a.score_path == SCORE_FP64, "unknown scoring path");
+    RG_CHECK_ARG((a.flags & ~FLAG_REUSE_POINTS) == 0, "unknown flag bits");
+    RG_CHECK_ARG(a.hyp_first >= 0 && a.first_pair >= 0, "negative index base");
+    if (a.P > 0) {
+        RG_CHECK_ARG(a.pair_off[0] == 0 && a.hyp_off[0] == 0, "offset arrays must start at 0");
+        for (int p = 0; p < a.P; ++p)
+            RG_CHECK_ARG(a.pair_off[p + 1] >= a.pair_off[p] && a.hyp_off[p + 1] >= a.hyp_off[p],
+                         "offset arrays must be non-decreasing");
     }
-    if ((rc = f_workspace(c, plan))) return rc;
-    if (!c->accumulate_stats) c->last_stats[7] = 0;
-    if (P == 0) return RG_OK;
-    prof_mark(c, st, 0);
-    if ((rc = f_prepare(c, st, plan, pts64, thr))) return rc;
-    prof_mark(c, st, 1);
-    rc = (mode == MODE_SAMPSON) ? f_solve_launch<MODE_SAMPSON>(c, st, plan, pts64, idx, solver)
-                                : f_solve_launch<MODE_EPI_MAX>(c, st, plan, pts64, idx, solver);
+    return RG_OK;
+}
+
+// pass boundaries: contiguous blocks of pairs with bounded evaluations / hypotheses (every pass holds at least one pair)
+static void f_pass_bounds(const Ctx* c, const FCall& a, std::vector<int>& bounds) {
+    const double budget = c->opt_pass_evals > 0 ? (double)c->opt_pass_evals : kDefaultPassEvals;
+    bounds.clear();
+    bounds.push_back(0);
+    double ev = 0.0;
+    long long hy = 0;
+    for (int p = 0; p < a.P; ++p) {
+        const double e = (double)(a.pair_off[p + 1] - a.pair_off[p]) * (double)(a.hyp_off[p + 1] - a.hyp_off[p]);
+        const long long h = a.hyp_off[p + 1] - a.hyp_off[p];
+        if (p > bounds.back() && (ev + e > budget || hy + h > kMaxPassHyp || p - bounds.back() >= 32768)) {
+            bounds.push_back(p);
+            ev = 0.0; hy = 0;
+        }
+        ev += e; hy += h;
+    }
+    bounds.push_back(a.P);
+}
+
+// sub-call of pairs [p0, p1) with offsets rebased to the pass
+static FCall f_sub_call(const FCall& a, int p0, int p1, std::vector<int>& po, std::vector<int>& ho) {
+    FCall s = a;
+    const int Pk = p1 - p0;
+    const size_t n0 = (size_t)a.pair_off[p0], h0 = (size_t)a.hyp_off[p0];
+    po.resize(Pk + 1); ho.resize(Pk + 1);
+    for (int q = 0; q <= Pk; ++q) { po[q] = a.pair_off[p0 + q] - (int)n0; ho[q] = a.hyp_off[p0 + q] - (int)h0; }
+    s.P = Pk;
+    s.pair_off = po.data(); s.hyp_off = ho.data();
+    s.pts64 = a.pts64 ? a.pts64 + 4 * n0 : nullptr;
+    s.idx = a.idx ? a.idx + 8 * h0 : nullptr;
+    s.first_pair = a.first_pair + p0;
+    s.best_idx = a.best_idx + p0; s.best_count = a.best_count + p0; s.best_F = a.best_F + 9 * (size_t)p0;
+    s.mask = a.mask ? a.mask + n0 : nullptr;
+    s.keys = a.keys ? a.keys + p0 : nullptr;
+    return s;
+}
+
+// full pipeline on device pointers; asynchronous with respect to the host except for the PairInfo staging
+static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
+    int rc = f_check_call(a);
     if (rc) return rc;
-    prof_mark(c, st, 2);
-    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, pts64, score_path)
-                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, pts64, score_path);
-    if (rc) return rc;
-    prof_mark(c, st, 4);
-    if ((rc = f_select_launch(c, st, plan, pts64, mode, tie_mode, mask, best_F, best_idx, best_count))) return rc;
-    prof_mark(c, st, 5);
-    return f_stats_readback(c, st);
+    RG_CUDA(cudaSetDevice(c->device));
+    c->last_stats[7] = 0;
+    c->last_passes = 0;
+    if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
+    if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
+    if (!c->accumulate_stats) RG_CUDA(cudaMemsetAsync(c->stats.ptr, 0, sizeof(unsigned long long) * 8, st));
+    if (a.P == 0) return RG_OK;
+    std::vector<int> bounds, po, ho;
+    f_pass_bounds(c, a, bounds);
+    const int n_pass = (int)bounds.size() - 1;
+    RG_CHECK_ARG(n_pass == 1 || !(a.flags & FLAG_REUSE_POINTS), "RG_FLAG_REUSE_POINTS needs a call that fits one pass");
+    for (int k = 0; k < n_pass; ++k) {
+        if (n_pass == 1) {
+            if ((rc = f_pass(c, st, a))) return rc;
+        } else {
+            FCall s = f_sub_call(a, bounds[k], bounds[k + 1], po, ho);
+            if ((rc = f_pass(c, st, s))) return rc;
+        }
+    }
+    c->last_passes = n_pass;
+    RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    return RG_OK;
 }
 
 }  // namespace rg
@@ -163,27 +329,128 @@ using namespace rg;
 
 extern "C" {
 
+int rg_f_ransac_dev2(void* ctx, void* stream, int P, const double* pts64_dev, const int* pair_off_host, const int* idx_dev,
+                     const int* hyp_off_host, double thr, int mode, int tie_mode, int solver, int score_path, int flags,
+                     unsigned long long sample_seed, int first_pair_id, int hyp_index_base, int* best_idx_dev,
+                     int* best_count_dev, double* best_F_dev, unsigned char* mask_dev, unsigned long long* key_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(best_idx_dev && best_count_dev && best_F_dev, "output pointers are null");
+    FCall a;
+    a.P = P; a.pts64 = pts64_dev; a.pair_off = pair_off_host; a.idx = idx_dev; a.hyp_off = hyp_off_host;
+    a.thr = thr; a.mode = mode; a.tie_mode = tie_mode; a.solver = solver; a.score_path = score_path; a.flags = flags;
+    a.sample_seed = sample_seed; a.first_pair = first_pair_id; a.hyp_first = hyp_index_base;
+    a.best_idx = best_idx_dev; a.best_count = best_count_dev; a.best_F = best_F_dev; a.mask = mask_dev; a.keys = key_dev;
+    return f_ransac_dev((Ctx*)ctx, (cudaStream_t)stream, a);
+}
+
 int rg_f_ransac_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int* pair_off_host, const int* idx_dev,
                     const int* hyp_off_host, double thr, int mode, int tie_mode, int solver, int score_path,
                     int* best_idx_dev, int* best_count_dev, double* best_F_dev, unsigned char* mask_dev) {
-    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
-    RG_CHECK_ARG(best_idx_dev && best_count_dev && best_F_dev, "output pointers are null");
-    return f_ransac_dev((Ctx*)ctx, (cudaStream_t)stream, P, pts64_dev, pair_off_host, idx_dev, hyp_off_host, thr, mode,
-                        tie_mode, solver, score_path, best_idx_dev, best_count_dev, best_F_dev, mask_dev);
+    RG_CHECK_ARG(P == 0 || hyp_off_host == nullptr || hyp_off_host[P] == 0 || idx_dev != nullptr,
+                 "idx_dev is null (use rg_f_ransac_dev2 for device-drawn samples)");
+    return rg_f_ransac_dev2(ctx, stream, P, pts64_dev, pair_off_host, idx_dev, hyp_off_host, thr, mode, tie_mode, solver,
+                            score_path, 0, 0ull, 0, 0, best_idx_dev, best_count_dev, best_F_dev, mask_dev, nullptr);
 }
 
-// device pointers to the per-hypothesis results of the LAST call on this context (valid until the next call)
+// the k = 8 sample index sets rg_f_ransac_*2 draws for (seed, first_pair_id, hyp_index_base) when idx is NULL: lets a caller
+// (or the oracle) see exactly the samples a seeded call used.  n_points_host[p] points, hypotheses CSR hyp_off_host.
+int rg_sample_indices_dev(void* ctx, void* stream, int P, const int* n_points_host, const int* hyp_off_host, int k,
+                          unsigned long long seed, int first_pair_id, int hyp_index_base, int* idx_out_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(P >= 0 && n_points_host && hyp_off_host, "bad pair table");
+    RG_CHECK_ARG(k == 6 || k == 7 || k == 8, "sample size k must be 6, 7 or 8");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_CUDA(cudaSetDevice(c->device));
+    if (P == 0 || hyp_off_host[P] == 0) return RG_OK;
+    RG_CHECK_ARG(idx_out_dev != nullptr, "idx_out_dev is null");
+    std::vector<int> po(P + 1, 0);
+    for (int p = 0; p < P; ++p) {
+        RG_CHECK_ARG(n_points_host[p] >= k || hyp_off_host[p + 1] == hyp_off_host[p], "a pair with hypotheses needs at least k points");
+        po[p + 1] = po[p] + n_points_host[p];
+    }
+    FPlan plan;
+    int rc = f_plan(c, st, P, po.data(), hyp_off_host, plan, 1, nullptr, hyp_index_base);
+    if (rc) return rc;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    const int H = (int)plan.Htot, grid = ceil_div(H, 256);
+    if (k == 8) sample_indices_kernel<8><<<grid, 256, 0, st>>>(pi, P, H, seed, (unsigned)first_pair_id, idx_out_dev);
+    else if (k == 7) sample_indices_kernel<7><<<grid, 256, 0, st>>>(pi, P, H, seed, (unsigned)first_pair_id, idx_out_dev);
+    else sample_indices_kernel<6><<<grid, 256, 0, st>>>(pi, P, H, seed, (unsigned)first_pair_id, idx_out_dev);
+    c->prep_pts = nullptr;              // the PairInfo table of a prepared pass was overwritten
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// synthetic two-view correspondences of BASELINE configs 3-5, generated on the device (philox.cuh).
+// cams_host: n_cams x 12 camera matrices; bbox6_host: lo/hi of the world box per axis.
+int rg_synth_two_view_dev(void* ctx, void* stream, int P, int first_pair_id, int N, const double* cams_host, int n_cams,
+                          const double* bbox6_host, unsigned long long seed_base, double outlier_frac, double sigma_px,
+                          double width, double height, double* pts_out_dev, int* cam_pair_out_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(P >= 0 && P <= 65535 && N >= 0 && n_cams >= 2 && cams_host && bbox6_host, "bad arguments");
+    RG_CHECK_ARG(outlier_frac >= 0.0 && outlier_frac <= 1.0, "outlier_frac must be in [0, 1]");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_CUDA(cudaSetDevice(c->device));
+    if (P == 0 || N == 0) return RG_OK;
+    RG_CHECK_ARG(pts_out_dev != nullptr, "pts_out_dev is null");
+    int rc;
+    if ((rc = ensure(c->geom, sizeof(double) * 12 * (size_t)n_cams))) return rc;
+    RG_CUDA(cudaMemcpyAsync(c->geom.ptr, cams_host, sizeof(double) * 12 * (size_t)n_cams, cudaMemcpyHostToDevice, st));
+    SynthParams prm;
+    for (int k = 0; k < 6; ++k) prm.bbox[k] = bbox6_host[k];
+    prm.sigma_px = sigma_px; prm.width = width; prm.height = height;
+    prm.n_out = (int)std::floor(outlier_frac * (double)N + 0.5);
+    prm.n_cams = n_cams;
+    const int nbx = std::max(1, std::min(64, ceil_div(N, 256)));
+    synth_two_view_kernel<<<dim3(nbx, P), 256, 0, st>>>((const double*)c->geom.ptr, prm, N, seed_base, (unsigned)first_pair_id,
+                                                        (double4*)pts_out_dev, cam_pair_out_dev);
+    RG_CUDA(cudaGetLastError());
+    RG_CUDA(cudaStreamSynchronize(st));               // cams_host may be pageable: do not return before it was read
+    return RG_OK;
+}
+
+// inlier mask (FP64 reference criterion, fun.py:315-317) of one caller-supplied F per pair; everything on the device
+int rg_f_inlier_mask_dev(void* ctx, void* stream, int P, const double* pts64_dev, const int* pair_off_host, const double* F_dev,
+                         double thr, int mode, unsigned char* mask_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(P >= 0 && pair_off_host, "bad pair table");
+    RG_CHECK_ARG(thr > 0.0 && std::isfinite(thr), "thr must be positive and finite");
+    RG_CHECK_ARG(mode == MODE_EPI_MAX || mode == MODE_SAMPSON, "unknown scoring mode");
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_CUDA(cudaSetDevice(c->device));
+    if (P == 0 || pair_off_host[P] == 0) return RG_OK;
+    RG_CHECK_ARG(pts64_dev && F_dev && mask_dev, "null buffers");
+    for (int p0 = 0; p0 < P; p0 += 64) {
+        const int Pk = std::min(64, P - p0);
+        MaskPairs mp;
+        int maxn = 1;
+        for (int q = 0; q <= Pk; ++q) mp.off[q] = pair_off_host[p0 + q];
+        for (int q = 0; q < Pk; ++q) maxn = std::max(maxn, mp.off[q + 1] - mp.off[q]);
+        const int nbx = std::max(1, std::min(c->sm_count * 2, ceil_div(maxn, 256 * 4)));
+        f_mask_given<<<dim3(nbx, Pk), 256, 0, st>>>((const double4*)pts64_dev, mp, F_dev + 9 * (size_t)p0, thr, mode, mask_dev);
+    }
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// device pointers to the per-hypothesis results of the LAST call on this context (valid until the next call; a call that
+// ran in several passes only keeps its last pass, and is refused here)
 int rg_f_last_hypotheses_dev(void* ctx, const int** counts_dev, const double** F_all_dev, const unsigned char** flags_dev) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
-    if (counts_dev) *counts_dev = (const int*)c->counts.ptr;
+    RG_CHECK_ARG(c->last_passes <= 1, "the last call ran in several passes: per-hypothesis results are not retained");
+    if (counts_dev) *counts_dev = (const int*)c->counts_ptr;
     if (F_all_dev) *F_all_dev = (const double*)c->F64.ptr;
     if (flags_dev) *flags_dev = (const unsigned char*)c->flags.ptr;
     return RG_OK;
 }
 
 // out[0] guard-band groups flagged, [1] band evaluations re-done in FP64, [2] decisions changed by the recheck,
-// [7] kernel launches of the last call.  Synchronises the stream.
+// [3] hypotheses recounted in FP64 after a flag-list overflow, [4] hypotheses with a sample index out of range,
+// [6] passes of the last call, [7] kernel launches of the last call.  Synchronises the stream.
 int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
     RG_CHECK_ARG(ctx != nullptr && out8 != nullptr, "null argument");
     Ctx* c = (Ctx*)ctx;
@@ -192,126 +459,156 @@ int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
     for (int i = 0; i < 8; ++i) out8[i] = 0;
     if (c->h_stats.ptr) {
         const unsigned long long* s = (const unsigned long long*)c->h_stats.ptr;
-        for (int i = 0; i < 7; ++i) out8[i] = (long long)s[i];
+        for (int i = 0; i < 6; ++i) out8[i] = (long long)s[i];
     }
+    out8[6] = c->last_passes;
     out8[7] = c->last_stats[7];
     return RG_OK;
 }
 
-// Host-buffer entry point.  The pairs are processed in up to Ctx::kMaxSlices contiguous sub-batches: all uploads are
-// queued on a second stream (one event per sub-batch), the kernels of sub-batch k wait only for their own inputs, so the
-// upload of sub-batch k+1 overlaps the scoring of sub-batch k (needs pinned host buffers to actually overlap; pageable
-// ones are still correct).  Results are identical to a single batch: pairs are independent.
-int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const int* pair_off, const int* idx,
-                     const int* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path, int* best_idx,
-                     int* best_count, double* best_F, unsigned char* mask, int* counts, double* F_all, unsigned char* flags) {
+// Host-buffer entry point.  The pairs are processed in passes (f_pass_bounds; a batch that fits one pass is still cut in two
+// when that hides a worthwhile part of the upload: the first sub-batch is the smallest whose scoring time covers the upload
+// of the rest, both estimated with the rates MEASURED on this context by earlier calls).  All uploads are queued on a second
+// stream (one event per pass), the kernels of pass k wait only for their own inputs, so the upload of pass k+1 overlaps
+// the scoring of pass k (needs pinned host buffers to actually overlap; pageable ones are still correct).  Results are
+// identical to a single batch: pairs are independent.  idx == NULL: samples drawn on the device from sample_seed.
+int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const int* pair_off, const int* idx,
+                      const int* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path,
+                      unsigned long long sample_seed, int first_pair_id, int* best_idx, int* best_count, double* best_F,
+                      unsigned char* mask, int* counts, double* F_all, unsigned char* flags) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
-    RG_CHECK_ARG(P >= 0 && pair_off && hyp_off, "bad pair table");
     RG_CHECK_ARG(best_idx && best_count && best_F, "output pointers are null");
     Ctx* c = (Ctx*)ctx;
     cudaStream_t st = (cudaStream_t)stream;
+    FCall a;
+    a.P = P; a.pair_off = pair_off; a.hyp_off = hyp_off; a.thr = thr; a.mode = mode; a.tie_mode = tie_mode;
+    a.solver = solver; a.score_path = score_path; a.sample_seed = sample_seed; a.first_pair = first_pair_id;
+    int rc = f_check_call(a);
+    if (rc) return rc;
     RG_CUDA(cudaSetDevice(c->device));
     if (P == 0) return RG_OK;
-    RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
-    for (int p = 0; p < P; ++p)
-        RG_CHECK_ARG(pair_off[p + 1] >= pair_off[p] && hyp_off[p + 1] >= hyp_off[p], "offset arrays must be non-decreasing");
     const size_t Ntot = (size_t)pair_off[P], Htot = (size_t)hyp_off[P];
-    RG_CHECK_ARG((Ntot == 0 || pts64) && (Htot == 0 || idx), "input pointers are null");
-    int rc;
+    RG_CHECK_ARG(Ntot == 0 || pts64, "pts64 is null");
+    const bool seeded = idx == nullptr;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * std::max<size_t>(Ntot, 1)))) return rc;
-    if ((rc = ensure(c->d_in_b, sizeof(int) * 8 * std::max<size_t>(Htot, 1)))) return rc;
+    if (!seeded && (rc = ensure(c->d_in_b, sizeof(int) * 8 * std::max<size_t>(Htot, 1)))) return rc;
     if ((rc = ensure(c->d_out_a, sizeof(int) * 2 * (size_t)P))) return rc;
     if ((rc = ensure(c->d_out_b, sizeof(double) * 9 * (size_t)P))) return rc;
     if (mask && (rc = ensure(c->d_out_c, std::max<size_t>(Ntot, 1)))) return rc;
 
-    // sub-batches.  Every sub-batch pays the small prepare / solve / select kernels again (~0.15 ms), so the automatic choice
-    // is two — the first one the smallest whose scoring time covers the upload of everything after it (model: 1.5e12
-    // evaluations/s against a 50 GB/s host link), at most half of the pairs — and only when the upload time it hides
-    // exceeds that fixed cost (measured on the config-5 batch: 1 -> 5.11, 2 -> 4.80, 3 -> 4.90, 4 -> 4.99 ms; the Dino
-    // sequence, 35 small pairs, stays monolithic).
-    int first = 1;
-    double hidden_s = 0.0;
-    {
+    std::vector<int> bounds;
+    f_pass_bounds(c, a, bounds);
+    const double r_ev = c->rate_evals_per_s > 0.0 ? c->rate_evals_per_s : 1.5e12;       // until measured: round-1 figures
+    const double r_up = c->rate_h2d_bytes_per_s > 0.0 ? c->rate_h2d_bytes_per_s : 5.0e10;
+    const double bytes_per_hyp = seeded ? 0.0 : 32.0;
+    if (bounds.size() == 2 && P >= 2 && !c->opt_profile && c->opt_host_slices != 1) {
+        int first = 1;
         double score_s = 0.0;
+        auto rest_bytes = [&](int f) {
+            return 32.0 * (double)(pair_off[P] - pair_off[f]) + bytes_per_hyp * (double)(hyp_off[P] - hyp_off[f]);
+        };
         for (first = 1; first < P; ++first) {
-            const double n = pair_off[first] - pair_off[first - 1], h = hyp_off[first] - hyp_off[first - 1];
-            score_s += n * h / 1.5e12;
-            const double rest_bytes = 32.0 * ((double)(pair_off[P] - pair_off[first]) + (double)(hyp_off[P] - hyp_off[first]));
-            if (score_s >= rest_bytes / 5.0e10) break;
+            score_s += (double)(pair_off[first] - pair_off[first - 1]) * (double)(hyp_off[first] - hyp_off[first - 1]) / r_ev;
+            if (score_s >= rest_bytes(first) / r_up) break;
         }
         first = std::max(1, std::min(first, std::max(1, P / 2)));
         double sc = 0.0;
-        for (int q = 0; q < first && q < P; ++q)
-            sc += (double)(pair_off[q + 1] - pair_off[q]) * (double)(hyp_off[q + 1] - hyp_off[q]) / 1.5e12;
-        const double rest_bytes = P > 0 ? 32.0 * ((double)(pair_off[P] - pair_off[std::min(first, P)]) +
-                                                  (double)(hyp_off[P] - hyp_off[std::min(first, P)])) : 0.0;
-        hidden_s = std::min(sc, rest_bytes / 5.0e10);
+        for (int q = 0; q < first; ++q)
+            sc += (double)(pair_off[q + 1] - pair_off[q]) * (double)(hyp_off[q + 1] - hyp_off[q]) / r_ev;
+        const double hidden_s = std::min(sc, rest_bytes(first) / r_up);
+        int S = c->opt_host_slices > 0 ? c->opt_host_slices : (hidden_s > 1.5e-4 ? 2 : 1);     // a pass costs ~0.1 ms of small kernels
+        S = std::max(1, std::min(S, P));
+        if (S > 1) {
+            bounds.clear();
+            bounds.push_back(0);
+            for (int k = 1; k <= S; ++k) bounds.push_back(first + (int)((long long)(P - first) * (k - 1) / (S - 1)));
+        }
     }
-    int S = c->opt_host_slices > 0 ? c->opt_host_slices : (hidden_s > 1.5e-4 ? 2 : 1);
-    S = std::max(1, std::min(std::min(S, P), (int)Ctx::kMaxSlices));
-    if (c->opt_profile) S = 1;                       // phase events describe one monolithic call
-    if (S > 1) {
-        if (!c->copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        if (!c->copy_gate) RG_CUDA(cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming));
-        for (int k = 0; k < S; ++k)
-            if (!c->slice_ready[k]) RG_CUDA(cudaEventCreateWithFlags(&c->slice_ready[k], cudaEventDisableTiming));
+    const int S = (int)bounds.size() - 1;
+    if (!c->copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->copy_gate) RG_CUDA(cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming));
+    while ((int)c->pass_ready.size() < S) {
+        cudaEvent_t e;
+        RG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pass_ready.push_back(e);
     }
-    // the first sub-batch is small (its upload is the only one that nothing hides), the others share the rest evenly
-    int bounds[Ctx::kMaxSlices + 1];
-    bounds[0] = 0;
-    if (S == 1) {
-        bounds[1] = P;
-    } else {
-        for (int k = 1; k <= S; ++k) bounds[k] = first + (int)((long long)(P - first) * (k - 1) / (S - 1));
-    }
+    for (int k = 0; k < 4; ++k)
+        if (!c->rate_ev[k]) RG_CUDA(cudaEventCreate(&c->rate_ev[k]));
+
     double* d_pts = (double*)c->d_in_a.ptr;
-    int* d_ix = (int*)c->d_in_b.ptr;
+    int* d_ix = seeded ? nullptr : (int*)c->d_in_b.ptr;
     cudaStream_t cs = S > 1 ? c->copy_stream : st;
     if (S > 1) {                                      // uploads may not overtake earlier work queued on the caller's stream
         RG_CUDA(cudaEventRecord(c->copy_gate, st));
         RG_CUDA(cudaStreamWaitEvent(cs, c->copy_gate, 0));
     }
+    RG_CUDA(cudaEventRecord(c->rate_ev[0], cs));
     for (int k = 0; k < S; ++k) {
         const int p0 = bounds[k], p1 = bounds[k + 1];
         const size_t n0 = (size_t)pair_off[p0], n1 = (size_t)pair_off[p1], h0 = (size_t)hyp_off[p0], h1 = (size_t)hyp_off[p1];
         if (n1 > n0) RG_CUDA(cudaMemcpyAsync(d_pts + 4 * n0, pts64 + 4 * n0, sizeof(double) * 4 * (n1 - n0), cudaMemcpyHostToDevice, cs));
-        if (h1 > h0) RG_CUDA(cudaMemcpyAsync(d_ix + 8 * h0, idx + 8 * h0, sizeof(int) * 8 * (h1 - h0), cudaMemcpyHostToDevice, cs));
-        if (S > 1) RG_CUDA(cudaEventRecord(c->slice_ready[k], cs));
+        if (!seeded && h1 > h0) RG_CUDA(cudaMemcpyAsync(d_ix + 8 * h0, idx + 8 * h0, sizeof(int) * 8 * (h1 - h0), cudaMemcpyHostToDevice, cs));
+        if (S > 1) RG_CUDA(cudaEventRecord(c->pass_ready[k], cs));
     }
+    RG_CUDA(cudaEventRecord(c->rate_ev[1], cs));
+    RG_CUDA(cudaEventRecord(c->rate_ev[2], st));
     int* d_idx = (int*)c->d_out_a.ptr;
     int* d_cnt = d_idx + P;
+    a.pts64 = d_pts; a.idx = d_ix;
+    a.best_idx = d_idx; a.best_count = d_cnt; a.best_F = (double*)c->d_out_b.ptr;
+    a.mask = mask ? (unsigned char*)c->d_out_c.ptr : nullptr;
     std::vector<int> po, ho;
     rc = RG_OK;
+    long long launches = 0;
     for (int k = 0; k < S && rc == RG_OK; ++k) {
-        const int p0 = bounds[k], p1 = bounds[k + 1], Pk = p1 - p0;
-        if (Pk == 0) continue;
-        const size_t n0 = (size_t)pair_off[p0], h0 = (size_t)hyp_off[p0];
-        const int* pok = pair_off;
-        const int* hok = hyp_off;
-        if (k > 0 || S > 1) {                          // offsets relative to the sub-batch
-            po.resize(Pk + 1); ho.resize(Pk + 1);
-            for (int q = 0; q <= Pk; ++q) { po[q] = pair_off[p0 + q] - (int)n0; ho[q] = hyp_off[p0 + q] - (int)h0; }
-            pok = po.data(); hok = ho.data();
-        }
-        if (S > 1) RG_CUDA(cudaStreamWaitEvent(st, c->slice_ready[k], 0));
+        const int p0 = bounds[k], p1 = bounds[k + 1];
+        if (p1 == p0) continue;
+        const size_t h0 = (size_t)hyp_off[p0];
+        if (S > 1) RG_CUDA(cudaStreamWaitEvent(st, c->pass_ready[k], 0));
         c->accumulate_stats = k > 0;
-        rc = f_ransac_dev(c, st, Pk, d_pts + 4 * n0, pok, d_ix + 8 * h0, hok, thr, mode, tie_mode, solver, score_path,
-                          d_idx + p0, d_cnt + p0, (double*)c->d_out_b.ptr + 9 * (size_t)p0,
-                          mask ? (unsigned char*)c->d_out_c.ptr + n0 : nullptr);
+        if (S == 1) {
+            rc = f_ransac_dev(c, st, a);
+        } else {
+            FCall s = f_sub_call(a, p0, p1, po, ho);
+            rc = f_ransac_dev(c, st, s);
+        }
         c->accumulate_stats = false;
+        launches += c->last_stats[7];
         if (rc) break;
-        // per-hypothesis results live in per-call workspaces: fetch them before the next sub-batch overwrites them
+        // per-hypothesis results live in per-pass workspaces: fetch them before the next pass overwrites them
         const size_t Hk = (size_t)hyp_off[p1] - h0;
-        if (counts && Hk) RG_CUDA(cudaMemcpyAsync(counts + h0, c->counts.ptr, sizeof(int) * Hk, cudaMemcpyDeviceToHost, st));
+        if ((counts || F_all || flags) && c->last_passes > 1) {
+            set_error("invalid argument: per-hypothesis outputs need sub-batches that fit one pass");
+            rc = RG_ERR_ARG;
+            break;
+        }
+        if (counts && Hk) RG_CUDA(cudaMemcpyAsync(counts + h0, c->counts_ptr, sizeof(int) * Hk, cudaMemcpyDeviceToHost, st));
         if (F_all && Hk) RG_CUDA(cudaMemcpyAsync(F_all + 9 * h0, c->F64.ptr, sizeof(double) * 9 * Hk, cudaMemcpyDeviceToHost, st));
         if (flags && Hk) RG_CUDA(cudaMemcpyAsync(flags + h0, c->flags.ptr, Hk, cudaMemcpyDeviceToHost, st));
     }
+    c->last_stats[7] = launches;
+    c->last_passes = S;
     if (rc) { cudaStreamSynchronize(st); if (S > 1) cudaStreamSynchronize(cs); return rc; }
+    RG_CUDA(cudaEventRecord(c->rate_ev[3], st));
     RG_CUDA(cudaMemcpyAsync(best_idx, d_idx, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_count, d_cnt, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_F, c->d_out_b.ptr, sizeof(double) * 9 * (size_t)P, cudaMemcpyDeviceToHost, st));
     if (mask && Ntot) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_c.ptr, Ntot, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
+    {   // measured rates for the next call's sub-batch model (exponential average; uploads of < 1 MB say nothing)
+        float ms_up = 0.f, ms_run = 0.f;
+        const double up_bytes = 32.0 * (double)Ntot + bytes_per_hyp * (double)Htot;
+        double evals = 0.0;
+        for (int p = 0; p < P; ++p) evals += (double)(pair_off[p + 1] - pair_off[p]) * (double)(hyp_off[p + 1] - hyp_off[p]);
+        if (cudaEventElapsedTime(&ms_up, c->rate_ev[0], c->rate_ev[1]) == cudaSuccess && ms_up > 0.f && up_bytes > 1e6) {
+            const double r = up_bytes / (ms_up * 1e-3);
+            c->rate_h2d_bytes_per_s = c->rate_h2d_bytes_per_s > 0.0 ? 0.75 * c->rate_h2d_bytes_per_s + 0.25 * r : r;
+        }
+        if (cudaEventElapsedTime(&ms_run, c->rate_ev[2], c->rate_ev[3]) == cudaSuccess && ms_run > 0.f && evals > 1e9) {
+            const double r = evals / (ms_run * 1e-3);
+            c->rate_evals_per_s = c->rate_evals_per_s > 0.0 ? 0.75 * c->rate_evals_per_s + 0.25 * r : r;
+        }
+    }
     // sample indices are validated where they are read (the solver clamps them and sets flag bit 2): no host pass over idx
     if (c->h_stats.ptr && ((const unsigned long long*)c->h_stats.ptr)[4] != 0) {
         set_error("invalid argument: %llu hypotheses have a sample index outside [0, N) of their pair",
@@ -321,6 +618,15 @@ int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const 
     return RG_OK;
 }
 
+int rg_f_ransac_host(void* ctx, void* stream, int P, const double* pts64, const int* pair_off, const int* idx,
+                     const int* hyp_off, double thr, int mode, int tie_mode, int solver, int score_path, int* best_idx,
+                     int* best_count, double* best_F, unsigned char* mask, int* counts, double* F_all, unsigned char* flags) {
+    RG_CHECK_ARG(P <= 0 || hyp_off == nullptr || hyp_off[P] == 0 || idx != nullptr,
+                 "idx is null (use rg_f_ransac_host2 for device-drawn samples)");
+    return rg_f_ransac_host2(ctx, stream, P, pts64, pair_off, idx, hyp_off, thr, mode, tie_mode, solver, score_path, 0ull, 0,
+                             best_idx, best_count, best_F, mask, counts, F_all, flags);
+}
+
 // Stage entry point: score caller-supplied fundamental matrices (H x 9, row-major, pixel frame) on one pair.
 int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64, int H, const double* F_all, double thr,
                             int mode, int score_path, int* counts) {
@@ -328,31 +634,40 @@ int rg_epi_score_count_host(void* ctx, void* stream, int N, const double* pts64,
     RG_CHECK_ARG(N >= 0 && H >= 0 && counts, "bad sizes / null output");
     RG_CHECK_ARG(thr > 0.0 && std::isfinite(thr), "thr must be positive and finite");
     RG_CHECK_ARG(mode == MODE_EPI_MAX || mode == MODE_SAMPSON, "unknown scoring mode");
+    RG_CHECK_ARG(score_path == SCORE_FP32_GUARDED || score_path == SCORE_FP64, "unknown scoring path");
     Ctx* c = (Ctx*)ctx;
     cudaStream_t st = (cudaStream_t)stream;
     RG_CUDA(cudaSetDevice(c->device));
     if (H == 0) return RG_OK;
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
+    int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>(&bps);
     if (rc) return rc;
-    if ((rc = f_workspace(c, plan))) return rc;
+    if ((rc = f_plan(c, st, 1, pair_off, hyp_off, plan, bps))) return rc;
+    if ((rc = f_workspace(c, plan, false))) return rc;
+    ScoreState s;
+    if ((rc = score_state_layout(c, 1, H, 8, s))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * std::max<size_t>((size_t)N, 1)))) return rc;
     if (N) RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, st));
     RG_CUDA(cudaMemcpyAsync(c->F64.ptr, F_all, sizeof(double) * 9 * (size_t)H, cudaMemcpyHostToDevice, st));
     c->last_stats[7] = 0;
-    if ((rc = f_prepare(c, st, plan, (const double*)c->d_in_a.ptr, thr))) return rc;
-    PairInfo* pi = (PairInfo*)c->pair_info.ptr;
+    c->last_passes = 1;
+    c->prep_pts = nullptr;
+    RG_CUDA(cudaMemsetAsync(c->state.ptr, 0, s.bytes, st));
+    RG_CUDA(cudaMemsetAsync(c->stats.ptr, 0, sizeof(unsigned long long) * 8, st));
+    if ((rc = f_prepare(c, st, plan, s, (const double*)c->d_in_a.ptr, thr))) return rc;
+    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    const PairFrame* fr = (const PairFrame*)c->pair_frame.ptr;
     if (mode == MODE_SAMPSON)
-        f_make_hyp32<MODE_SAMPSON><<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->F64.ptr, pi, 1, H, (Hyp32*)c->hyp32.ptr);
+        f_make_hyp32<MODE_SAMPSON><<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->F64.ptr, pi, fr, 1, H, (Hyp32*)c->hyp32.ptr);
     else
-        f_make_hyp32<MODE_EPI_MAX><<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->F64.ptr, pi, 1, H, (Hyp32*)c->hyp32.ptr);
+        f_make_hyp32<MODE_EPI_MAX><<<ceil_div(H, 256), 256, 0, st>>>((const double*)c->F64.ptr, pi, fr, 1, H, (Hyp32*)c->hyp32.ptr);
     c->last_stats[7] += 1;
-    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, (const double*)c->d_in_a.ptr, score_path)
-                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, (const double*)c->d_in_a.ptr, score_path);
+    rc = (mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, (const double*)c->d_in_a.ptr, thr, score_path)
+                                : f_score_launch<MODE_EPI_MAX>(c, st, plan, s, (const double*)c->d_in_a.ptr, thr, score_path);
     if (rc) return rc;
-    if ((rc = f_stats_readback(c, st))) return rc;
-    RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(counts, s.counts, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     return RG_OK;
 }
@@ -370,15 +685,21 @@ int rg_f8pt_solve_host(void* ctx, void* stream, int N, const double* pts64, int 
     RG_CHECK_ARG(idx != nullptr, "idx is null");
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>());
+    int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>(&bps);
     if (rc) return rc;
-    if ((rc = f_workspace(c, plan))) return rc;
+    if ((rc = f_plan(c, st, 1, pair_off, hyp_off, plan, bps))) return rc;
+    if ((rc = f_workspace(c, plan, false))) return rc;
+    ScoreState s;
+    if ((rc = score_state_layout(c, 1, H, 8, s))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 4 * (size_t)N))) return rc;
     if ((rc = ensure(c->d_in_b, sizeof(int) * 8 * (size_t)H))) return rc;
     RG_CUDA(cudaMemcpyAsync(c->d_in_a.ptr, pts64, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, st));
     RG_CUDA(cudaMemcpyAsync(c->d_in_b.ptr, idx, sizeof(int) * 8 * (size_t)H, cudaMemcpyHostToDevice, st));
     c->last_stats[7] = 0;
-    if ((rc = f_prepare(c, st, plan, (const double*)c->d_in_a.ptr, 1.0))) return rc;
+    c->last_passes = 1;
+    c->prep_pts = nullptr;
+    RG_CUDA(cudaMemsetAsync(c->state.ptr, 0, s.bytes, st));
+    if ((rc = f_prepare(c, st, plan, s, (const double*)c->d_in_a.ptr, 1.0))) return rc;
     if ((rc = f_solve_launch<MODE_EPI_MAX>(c, st, plan, (const double*)c->d_in_a.ptr, (const int*)c->d_in_b.ptr, solver)))
         return rc;
     RG_CUDA(cudaMemcpyAsync(F_all, c->F64.ptr, sizeof(double) * 9 * (size_t)H, cudaMemcpyDeviceToHost, st));

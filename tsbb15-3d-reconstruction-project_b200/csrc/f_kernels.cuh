@@ -6,11 +6,12 @@
 //   lab3.py:188-227  fmatrix_residuals (signed point-to-epipolar-line distances in both images)
 //
 // Kernels (launch order of one batched call):
-//   f_bbox_init / f_bbox / f_frame / f_normalise   per-pair FP32 scoring frame + NaN-padded packed FP32 points
+//   f_bbox / f_normalise                           per-pair FP32 scoring frame + NaN-padded packed FP32 points
+//                                                  (bounding-box keys start at 0: cleared by the pass's one memset)
 //   f8_solve_qr (or f8_solve_jacobi)               one hypothesis per thread (or 16-lane group), FP64
-//   f_score_packed                                 FP32 fma.rn.f32x2 scorer, 2 hypotheses x 2 points per thread-step
-//   f_fixup                                        FP64 re-evaluation of guard-band groups -> exact counts
-//   f_argmax / f_tie_stats / f_tie_resolve / f_mask   selection + winner's inlier mask (FP64)
+//   score_packed<EpiPolicy>                        FP32 fma.rn.f32x2 scorer, 2 hypotheses x 2 points per thread-step
+//   fixup_list<EpiFix>                             FP64 re-evaluation of the flagged guard-band groups -> exact counts
+//   argmax_counts / f_tie_stats / f_tie_resolve / f_mask   selection + winner's inlier mask (FP64)
 #pragma once
 #include "common.cuh"
 #include "score_core.cuh"
@@ -67,7 +68,7 @@ __device__ __forceinline__ float epi_q32(const float* __restrict__ f, float x0, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// bounding boxes (FP32, rounded outwards) via ordered-int atomics
+// bounding boxes (FP32, rounded outwards) via ordered-key atomics
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int f2key(float f) {
     int i = __float_as_int(f);
@@ -75,13 +76,17 @@ __device__ __forceinline__ int f2key(float f) {
 }
 __device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
 
-__global__ void f_bbox_init(int* __restrict__ bbox, int P) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P * 8) bbox[i] = ((i & 7) < 4) ? 0x7FFFFFFF : (int)0x80000000;
+// unsigned monotone key, > 0 for every float except the NaN with all mantissa bits set: a zeroed array is the
+// identity of atomicMax, so the bounding boxes need no initialisation kernel (the pass's memset clears them)
+__device__ __forceinline__ unsigned f2ukey(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float ukey2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
 
+// bbox[p*8 + k] = key(max of -coordinate k) for k < 4, key(max of coordinate k-4) for k >= 4; 0 = no finite point seen
 __global__ void __launch_bounds__(256) f_bbox(const double4* __restrict__ pts, const PairInfo* __restrict__ pi,
-                                               int* __restrict__ bbox) {
+                                               unsigned* __restrict__ bbox) {
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
     float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
@@ -108,36 +113,43 @@ __global__ void __launch_bounds__(256) f_bbox(const double4* __restrict__ pts, c
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            atomicMin(&bbox[p * 8 + k], f2key(mn[k]));
-            atomicMax(&bbox[p * 8 + 4 + k], f2key(mx[k]));
+            if (mn[k] <= mx[k]) {       // this warp saw at least one finite value of coordinate k
+                atomicMax(&bbox[p * 8 + k], f2ukey(-mn[k]));
+                atomicMax(&bbox[p * 8 + 4 + k], f2ukey(mx[k]));
+            }
         }
     }
 }
 
-__global__ void f_frame(PairInfo* __restrict__ pi, const int* __restrict__ bbox, int P, double thr) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+__device__ __forceinline__ PairFrame frame_from_bbox(const unsigned* __restrict__ bb, double thr) {
     double c[4], half = 0.0;
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float lo = key2f(bbox[p * 8 + k]), hi = key2f(bbox[p * 8 + 4 + k]);
+        float lo = 0.f, hi = 0.f;
+        if (bb[k] != 0u && bb[4 + k] != 0u) { lo = -ukey2f(bb[k]); hi = ukey2f(bb[4 + k]); }
         if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }          // empty pair or all points non-finite
         c[k] = 0.5 * ((double)lo + (double)hi);
         half = fmax(half, fmax((double)hi - c[k], c[k] - (double)lo));
     }
-    PairInfo& o = pi[p];
+    PairFrame o;
     o.c1x = c[0]; o.c1y = c[1]; o.c2x = c[2]; o.c2y = c[3];
     o.thr = thr;
     // bound on |normalised coordinate| with head-room for the FP64 division and FP32 rounding
     o.B = (half / thr) * (1.0 + 1e-6) + 1e-30;
+    return o;
 }
 
 // FP32 copy in the scoring frame, laid out for the packed scorer: point pair (a, b) occupies 32 bytes
 //   [x0a x0b x1a x1b] [y0a y0b y1a y1b]
 // Points beyond n (padding up to a multiple of kSub) are NaN: they can never count and never flag.
+// Every block derives the pair's frame from the bounding box; block x == 0 also stores it for the later kernels.
 __global__ void __launch_bounds__(256) f_normalise(const double4* __restrict__ pts, const PairInfo* __restrict__ pi,
-                                                    float4* __restrict__ pts32) {
+                                                    const unsigned* __restrict__ bbox, double thr,
+                                                    PairFrame* __restrict__ frames, float4* __restrict__ pts32) {
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
+    const PairFrame fr = frame_from_bbox(bbox + p * 8, thr);
+    if (blockIdx.x == 0 && threadIdx.x == 0) frames[p] = fr;
     const float qnan = __int_as_float(0x7FFFFFFF);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < info.n_pad / 2; j += gridDim.x * blockDim.x) {
         float a[4], b[4];
@@ -147,10 +159,10 @@ __global__ void __launch_bounds__(256) f_normalise(const double4* __restrict__ p
             float* dst = s ? b : a;
             if (i < info.n) {
                 const double4 v = pts[info.pt_off + i];
-                dst[0] = (float)((v.x - info.c1x) / info.thr);
-                dst[1] = (float)((v.y - info.c1y) / info.thr);
-                dst[2] = (float)((v.z - info.c2x) / info.thr);
-                dst[3] = (float)((v.w - info.c2y) / info.thr);
+                dst[0] = (float)((v.x - fr.c1x) / fr.thr);
+                dst[1] = (float)((v.y - fr.c1y) / fr.thr);
+                dst[2] = (float)((v.z - fr.c2x) / fr.thr);
+                dst[3] = (float)((v.w - fr.c2y) / fr.thr);
             } else {
                 dst[0] = dst[1] = dst[2] = dst[3] = qnan;
             }
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(256) f_normalise(const double4* __restrict__ p
 //   |q^ - q| <= 2 sqrt(Mb) 8eps + 64 eps^2 + 10 eps Smax + 2 eps Mb      whenever the decision could flip,
 // where S1 = rho0^2+rho1^2, S2 = kap0^2+kap1^2, Mb = min(S1,S2) (EPI) or S1+S2 (Sampson), Smax likewise.
 template <int MODE>
-__device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const PairInfo& fr, Hyp32* __restrict__ out) {
+__device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const PairFrame& fr, Hyp32* __restrict__ out) {
     const double t = fr.thr, B = fr.B;
     double g[9], ft[9];
 #pragma unroll
@@ -224,8 +236,9 @@ __device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const P
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) f_make_hyp32(const double* __restrict__ F64, const PairInfo* __restrict__ pi, int P,
-                                                     int Htot, Hyp32* __restrict__ hyp32) {
+__global__ void __launch_bounds__(256) f_make_hyp32(const double* __restrict__ F64, const PairInfo* __restrict__ pi,
+                                                     const PairFrame* __restrict__ frames, int P, int Htot,
+                                                     Hyp32* __restrict__ hyp32) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= Htot) return;
     int lo = 0, hi = P;
@@ -233,7 +246,7 @@ __global__ void __launch_bounds__(256) f_make_hyp32(const double* __restrict__ F
     double F[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) F[k] = F64[(size_t)h * 9 + k];
-    make_hyp32<MODE>(F, pi[lo], hyp32 + h);
+    make_hyp32<MODE>(F, frames[lo], hyp32 + h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,8 +356,8 @@ __device__ __forceinline__ void denormalise(const double* __restrict__ Fs, doubl
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ pts, const int* __restrict__ idx,
-                                                    const PairInfo* __restrict__ pi, int P, int Htot,
-                                                    double* __restrict__ F64, Hyp32* __restrict__ hyp32,
+                                                    const PairInfo* __restrict__ pi, const PairFrame* __restrict__ frames,
+                                                    int P, int Htot, double* __restrict__ F64, Hyp32* __restrict__ hyp32,
                                                     unsigned char* __restrict__ flags) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= Htot) return;
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
     if (!finite) fl |= 2;
     if (bad_index) fl |= 4;                   // a sample index outside [0, n): clamped, and the host call fails
     flags[h] = fl;
-    make_hyp32<MODE>(F, info, hyp32 + h);
+    make_hyp32<MODE>(F, frames[lo], hyp32 + h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -534,17 +547,15 @@ struct EpiPolicy {
 template <int MODE>
 struct EpiFix {
     struct Params {
-        const float4* pts32; const double4* pts64; const Hyp32* hyp32; const double* F64; const PairInfo* pi; int P;
+        const float4* pts32; const double4* pts64; const Hyp32* hyp32; const double* F64; const PairInfo* pi;
+        const PairFrame* fr; int P;
     };
-    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& pair) {
+    __device__ static __forceinline__ int pair_of(const Params& p, int h) {
         int lo = 0, hi = p.P;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].word_off <= wi) lo = mid; else hi = mid; }
-        const long long local = wi - p.pi[lo].word_off;
-        const int hl = (int)(local / p.pi[lo].words_per_hyp);
-        pair = lo;
-        h = p.pi[lo].hyp_off + hl;
-        fbase = (int)(local - (long long)hl * p.pi[lo].words_per_hyp) * 32;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        return lo;
     }
+    __device__ static __forceinline__ int n_points(const Params& p, int pair) { return p.pi[pair].n; }
     // FP32 pass over one flagged group (kSub consecutive correspondences of one hypothesis)
     __device__ static __forceinline__ void scan(const Params& p, int h, int flag, int pair, unsigned& band, unsigned& sign) {
         const PairInfo& info = p.pi[pair];
@@ -569,7 +580,7 @@ struct EpiFix {
     __device__ static __forceinline__ int exact(const Params& p, int h, int i, int pair) {
         const PairInfo& info = p.pi[pair];
         const double4 v = p.pts64[info.pt_off + i];
-        return epi_inlier64(p.F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, info.thr, MODE);
+        return epi_inlier64(p.F64 + (size_t)h * 9, v.x, v.y, v.z, v.w, p.fr[pair].thr, MODE);
     }
 };
 
@@ -577,7 +588,8 @@ struct EpiFix {
 // tests.  One hypothesis per thread, points broadcast from shared memory; N may be split over gridDim.z (counts must be
 // zeroed beforehand, partial sums are added atomically).
 __global__ void __launch_bounds__(128) f_score_fp64(const double4* __restrict__ pts64, const double* __restrict__ F64,
-                                                     const PairInfo* __restrict__ pi, int mode, int* __restrict__ counts) {
+                                                     const PairInfo* __restrict__ pi, double thr, int mode,
+                                                     int* __restrict__ counts) {
     __shared__ double4 sp[256];
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
@@ -598,7 +610,7 @@ __global__ void __launch_bounds__(128) f_score_fp64(const double4* __restrict__ 
         if (active) {
             for (int i = 0; i < m; ++i) {
                 const double4 v = sp[i];
-                cnt += epi_inlier64(F, v.x, v.y, v.z, v.w, info.thr, mode);
+                cnt += epi_inlier64(F, v.x, v.y, v.z, v.w, thr, mode);
             }
         }
     }
@@ -657,11 +669,15 @@ __global__ void __launch_bounds__(256) f_tie_stats(const double4* __restrict__ p
 
 // sequential replay of fun.py:320-328 over the maximal-count hypotheses, in hypothesis order (one warp per pair)
 __global__ void __launch_bounds__(32) f_tie_resolve(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
-                                                     const double2* __restrict__ tie_stats, int2* __restrict__ best) {
+                                                     const double2* __restrict__ tie_stats, int2* __restrict__ best,
+                                                     unsigned long long* __restrict__ keys) {
     const int p = blockIdx.x;
     const PairInfo info = pi[p];
     const int2 b = best[p];
-    if (b.x < 0) return;
+    if (b.x < 0) {
+        if (keys != nullptr && threadIdx.x == 0) keys[p] = 0ull;
+        return;
+    }
     const int lane = threadIdx.x;
     int cur = -1;
     double cur_std = 0.0;
@@ -680,13 +696,17 @@ __global__ void __launch_bounds__(32) f_tie_resolve(const int* __restrict__ coun
             else if (fabs(cur_std) > nr) { cur = base + src; cur_std = sd; } // norm(std_best) > norm(d_new)
         }
     }
-    if (lane == 0) best[p] = make_int2(cur, b.y);
+    if (lane == 0) {
+        best[p] = make_int2(cur, b.y);
+        if (keys != nullptr)
+            keys[p] = ((unsigned long long)(unsigned)b.y << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(info.hyp_first + cur));
+    }
 }
 
 // inlier mask of the winner (FP64 reference formula) + copy of its F
 __global__ void __launch_bounds__(256) f_mask(const double4* __restrict__ pts64, const double* __restrict__ F64,
-                                               const PairInfo* __restrict__ pi, const int2* __restrict__ best, int mode,
-                                               unsigned char* __restrict__ mask, double* __restrict__ best_F,
+                                               const PairInfo* __restrict__ pi, const int2* __restrict__ best, double thr,
+                                               int mode, unsigned char* __restrict__ mask, double* __restrict__ best_F,
                                                int* __restrict__ best_idx, int* __restrict__ best_count) {
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
@@ -701,7 +721,23 @@ __global__ void __launch_bounds__(256) f_mask(const double4* __restrict__ pts64,
     for (int k = 0; k < 9; ++k) F[k] = b.x >= 0 ? F64[(size_t)(info.hyp_off + b.x) * 9 + k] : nan("");
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < info.n; i += gridDim.x * blockDim.x) {
         const double4 v = pts64[info.pt_off + i];
-        mask[info.pt_off + i] = (unsigned char)epi_inlier64(F, v.x, v.y, v.z, v.w, info.thr, mode);
+        mask[info.pt_off + i] = (unsigned char)epi_inlier64(F, v.x, v.y, v.z, v.w, thr, mode);
+    }
+}
+
+// inlier masks of caller-supplied F matrices (FP64 reference formula), up to 64 pairs per launch: the hypothesis-split mode
+// computes the winner's mask on every rank from the F that came out of the exchange
+struct MaskPairs { int off[65]; };
+__global__ void __launch_bounds__(256) f_mask_given(const double4* __restrict__ pts64, MaskPairs mp,
+                                                     const double* __restrict__ F_in, double thr, int mode,
+                                                     unsigned char* __restrict__ mask) {
+    const int p = blockIdx.y;
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = F_in[p * 9 + k];
+    for (int i = mp.off[p] + blockIdx.x * blockDim.x + threadIdx.x; i < mp.off[p + 1]; i += gridDim.x * blockDim.x) {
+        const double4 v = pts64[i];
+        mask[i] = (unsigned char)epi_inlier64(F, v.x, v.y, v.z, v.w, thr, mode);
     }
 }
 

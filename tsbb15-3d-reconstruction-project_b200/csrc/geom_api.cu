@@ -15,11 +15,11 @@ static int geom_stage(Ctx* c, cudaStream_t st, int P, const double* C1_dev, cons
     PairGeom* G = (PairGeom*)c->geom.ptr;
     int* off = (int*)((char*)c->geom.ptr + gbytes);
     if (pair_off_host) {
-        RG_CUDA(cudaEventSynchronize(c->staging_free));
-        if ((rc = ensure_pinned(c->h_stage, sizeof(int) * (size_t)(P + 1)))) return rc;
-        memcpy(c->h_stage.ptr, pair_off_host, sizeof(int) * (size_t)(P + 1));
-        RG_CUDA(cudaMemcpyAsync(off, c->h_stage.ptr, sizeof(int) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
-        RG_CUDA(cudaEventRecord(c->staging_free, st));
+        RG_CUDA(cudaEventSynchronize(c->staging_free[0]));
+        if ((rc = ensure_pinned(c->h_stage[0], sizeof(int) * (size_t)(P + 1)))) return rc;
+        memcpy(c->h_stage[0].ptr, pair_off_host, sizeof(int) * (size_t)(P + 1));
+        RG_CUDA(cudaMemcpyAsync(off, c->h_stage[0].ptr, sizeof(int) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
+        RG_CUDA(cudaEventRecord(c->staging_free[0], st));
     }
     if (P > 0) {
         geom_prepare<<<ceil_div(P, 64), 64, 0, st>>>(C1_dev, C2_dev, P, G);
@@ -223,12 +223,12 @@ int rg_two_view_init_dev(void* ctx, void* stream, int P, const double* pts64_dev
     double* C2 = C1 + 12 * p;
     double* dK = C2 + 12 * p;
     int* doff = (int*)(dK + 10);
-    RG_CUDA(cudaEventSynchronize(c->staging_free));
-    if ((rc = ensure_pinned(c->h_stage, sizeof(double) * 10 + sizeof(int) * (p + 1)))) return rc;
-    memcpy(c->h_stage.ptr, K, sizeof(double) * 9);
-    memcpy((char*)c->h_stage.ptr + sizeof(double) * 10, pair_off_host, sizeof(int) * (p + 1));
-    RG_CUDA(cudaMemcpyAsync(dK, c->h_stage.ptr, sizeof(double) * 10 + sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
-    RG_CUDA(cudaEventRecord(c->staging_free, st));
+    RG_CUDA(cudaEventSynchronize(c->staging_free[0]));
+    if ((rc = ensure_pinned(c->h_stage[0], sizeof(double) * 10 + sizeof(int) * (p + 1)))) return rc;
+    memcpy(c->h_stage[0].ptr, K, sizeof(double) * 9);
+    memcpy((char*)c->h_stage[0].ptr + sizeof(double) * 10, pair_off_host, sizeof(int) * (p + 1));
+    RG_CUDA(cudaMemcpyAsync(dK, c->h_stage[0].ptr, sizeof(double) * 10 + sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
+    RG_CUDA(cudaEventRecord(c->staging_free[0], st));
     if (N) tv_normalise<<<ceil_div((long long)N, 256), 256, 0, st>>>((const double4*)pts64_dev, mask_dev, (int)N, Ki, x1n, x2n);
     tv_pick<<<ceil_div((long long)P * 32, 128), 128, 0, st>>>(x1n, x2n, mask_dev, doff, P, y1, y2);
     relative_pose_kernel<<<ceil_div((long long)P * 4, kGeomThreads), kGeomThreads, 0, st>>>(F_dev, dK, 0, y1, y2, P, Rt_dev,

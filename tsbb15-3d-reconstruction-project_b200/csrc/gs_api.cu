@@ -50,11 +50,11 @@ static int gold_standard_dev(Ctx* c, cudaStream_t st, int P, const double* pts64
         if ((rc = triangulate_dev(c, st, P, C1, C2, pair_off, (const double*)x1n, (const double*)x2n, TRI_OPTIMAL, Xcur)))
             return rc;
         launches += 1 + (int)c->last_stats[7];
-        RG_CUDA(cudaEventSynchronize(c->staging_free));
-        if ((rc = ensure_pinned(c->h_stage, sizeof(int) * (p + 1)))) return rc;
-        memcpy(c->h_stage.ptr, pair_off, sizeof(int) * (p + 1));
-        RG_CUDA(cudaMemcpyAsync(doff, c->h_stage.ptr, sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
-        RG_CUDA(cudaEventRecord(c->staging_free, st));
+        RG_CUDA(cudaEventSynchronize(c->staging_free[0]));
+        if ((rc = ensure_pinned(c->h_stage[0], sizeof(int) * (p + 1)))) return rc;
+        memcpy(c->h_stage[0].ptr, pair_off, sizeof(int) * (p + 1));
+        RG_CUDA(cudaMemcpyAsync(doff, c->h_stage[0].ptr, sizeof(int) * (p + 1), cudaMemcpyHostToDevice, st));
+        RG_CUDA(cudaEventRecord(c->staging_free[0], st));
         if (maxN <= kGsFusedMaxPts && !c->opt_gs_multi) {
             // small pairs: the whole LM loop of a pair in one CTA, one launch (gs_fused)
             gs_fused<<<P, kGsFusedThreads, 0, st>>>((const double4*)pts64, mask, doff, gp, Xcur, Xtrial, C1, ftol, max_iter);

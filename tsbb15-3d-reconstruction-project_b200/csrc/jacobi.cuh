@@ -114,7 +114,8 @@ struct GroupJacobi {
 // one-sided Jacobi above; the null vector is V[:, argmin sigma]).
 template <int MODE>
 __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4* __restrict__ pts, const int* __restrict__ idx,
-                                                                   const PairInfo* __restrict__ pi, int P, int Htot,
+                                                                   const PairInfo* __restrict__ pi,
+                                                                   const PairFrame* __restrict__ frames, int P, int Htot,
                                                                    double* __restrict__ F64, Hyp32* __restrict__ hyp32,
                                                                    unsigned char* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4*
         if (!finite) fl |= 2;
         if (bad_index) fl |= 4;
         flags[h] = fl;
-        make_hyp32<MODE>(F, info, hyp32 + h);
+        make_hyp32<MODE>(F, frames[lo], hyp32 + h);
     }
 }
 

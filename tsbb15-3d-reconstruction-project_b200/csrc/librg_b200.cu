@@ -7,4 +7,5 @@
 #include "gs_api.cu"
 #include "ba_api.cu"
 #include "nccl_api.cu"
+#include "p2p_api.cu"
 #include "microbench.cu"

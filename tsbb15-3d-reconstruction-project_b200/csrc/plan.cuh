@@ -11,31 +11,35 @@ struct FPlan {
     long long Ntot = 0, Htot = 0, N32tot = 0;
     int n_items = 0;
     int maxN = 0, maxH = 0;
-    long long total_words = 0;           // guard-band bitmap size: sum_p H_p * ceil(ngroups_p / 32)
+    double evals = 0.0;                  // sum_p n_p * H_p
 };
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Fill the PairInfo table (integer part) on the host and upload it.  Work items of the packed scorer:
-// item = (pair, 512-hypothesis block, contiguous range of 32-point groups).  The ranges are sized so that the total
-// item count is a multiple of the persistent grid when the batch allows it (static round-robin has no tail then).
+// item = (pair, 512-hypothesis block, contiguous range of kSub-point groups), claimed dynamically by the persistent grid.
 // resident blocks per SM of a persistent scorer instantiation (queried once; also sets the dynamic smem attribute)
+// (cached per DEVICE: cudaFuncSetAttribute is a per-device function attribute, and one process may drive several GPUs)
 template <class Pol>
-inline int score_blocks_per_sm() {
-    static int cached = 0;
-    if (cached == 0) {
+inline int score_blocks_per_sm(int* out) {
+    static int cached[64] = {0};
+    int dev = 0;
+    RG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return RG_ERR_ARG; }
+    if (cached[dev] == 0) {
         constexpr size_t smem = score_smem_bytes<Pol>();
-        cudaFuncSetAttribute(score_packed<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        RG_CUDA(cudaFuncSetAttribute(score_packed<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_packed<Pol>, kScoreThreads, smem) != cudaSuccess || n < 1)
-            n = 1;
-        cached = n;
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_packed<Pol>, kScoreThreads, smem));
+        cached[dev] = n < 1 ? 1 : n;
     }
-    return cached;
+    *out = cached[dev];
+    return RG_OK;
 }
 
 inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int* hyp_off, FPlan& plan, int blocks_per_sm,
-                  const int* n_vote = nullptr /* PnP: per-view number of voting correspondences (<= view size) */) {
+                  const int* n_vote = nullptr /* PnP: per-view number of voting correspondences (<= view size) */,
+                  int hyp_first = 0 /* hypothesis-split mode: global index of this rank's first hypothesis */) {
     RG_CHECK_ARG(P >= 0 && P <= 65535, "number of pairs must be in [0, 65535]");
     RG_CHECK_ARG(pair_off != nullptr && hyp_off != nullptr, "offset arrays are null");
     RG_CHECK_ARG(pair_off[0] == 0 && hyp_off[0] == 0, "offset arrays must start at 0");
@@ -45,10 +49,12 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     for (int p = 0; p < P; ++p) {
         RG_CHECK_ARG(pair_off[p + 1] >= pair_off[p] && hyp_off[p + 1] >= hyp_off[p], "offset arrays must be non-decreasing");
     }
-    int rc = ensure_pinned(c->h_stage, sizeof(PairInfo) * (size_t)P);
+    const int turn = c->stage_turn;       // double-buffered staging: planning pass k+1 does not wait for pass k's kernels
+    c->stage_turn ^= 1;
+    int rc = ensure_pinned(c->h_stage[turn], sizeof(PairInfo) * (size_t)P);
     if (rc) return rc;
-    RG_CUDA(cudaEventSynchronize(c->staging_free));
-    PairInfo* pi = (PairInfo*)c->h_stage.ptr;
+    RG_CUDA(cudaEventSynchronize(c->staging_free[turn]));
+    PairInfo* pi = (PairInfo*)c->h_stage[turn].ptr;
 
     long long unit_total = 0;      // work in units of (hypothesis block x point group)
     long long off32 = 0;
@@ -61,6 +67,7 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         RG_CHECK_ARG(o.n >= 0 && o.n <= o.n_all, "voting count must be in [0, view size]");
         o.hyp_off = hyp_off[p];
         o.H = hyp_off[p + 1] - hyp_off[p];
+        o.hyp_first = hyp_first;
         o.n_pad = ((o.n + kSub - 1) / kSub) * kSub;
         o.pt_off32 = (int)off32;
         off32 += o.n_pad;
@@ -68,9 +75,7 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         plan.maxH = std::max(plan.maxH, o.H);
         const long long nhb = ceil_div(o.H, kHypPerBlock), ng = o.n_pad / kSub;
         unit_total += nhb * ng;
-        o.words_per_hyp = (int)((ng + 31) / 32);
-        o.word_off = plan.total_words;
-        plan.total_words += (long long)o.H * o.words_per_hyp;
+        plan.evals += (double)o.n * (double)o.H;
     }
     RG_CHECK_ARG(off32 < (1ll << 31) && (long long)hyp_off[P] * 9 < (1ll << 40), "batch too large for 32-bit offsets");
     plan.Ntot = pair_off[P];
@@ -78,33 +83,37 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     plan.N32tot = off32;
 
     const long long grid = (long long)c->sm_count * blocks_per_sm;
-    // aim for ~kItemsPerBlock items per resident block (dynamic scheduling: the tail is about half an item), never below
-    // 64 groups (512 points) per item
+    // Items are claimed dynamically, so what matters is (a) enough items per resident block that the tail is short and
+    // (b), for SMALL batches (one pair split over GPUs: a few hundred items), an item count that fills whole rounds of the
+    // grid: 784 equal items on 444 resident blocks take two rounds (88 % busy), 444 take one.  Aim for ~kItemsPerBlock
+    // items per block, never below 16 groups (128 points) per item, then search the neighbourhood of that size for the
+    // split whose rounded-up rounds waste the least (uniform batches; ragged ones take the target as is).  Since the
+    // guard-band flags went from a bitmap to a list, item boundaries may fall on any group.
     static const long long kItemsPerBlock = [] {
         const char* e = getenv("RG_ITEMS_PER_BLOCK");
         const long long v = e ? atoll(e) : 0;
         return v > 0 ? v : 24ll;              // measured on B200, config-5 batch: 8 -> 4.17 ms, 24 -> 4.07 ms, 48 -> 4.07 ms
     }();
     long long gps_target = std::max<long long>(64, unit_total / std::max<long long>(1, grid * kItemsPerBlock));
-    long long hb_total = 0;
-    for (int p = 0; p < P; ++p) hb_total += ceil_div(pi[p].H, kHypPerBlock) * (pi[p].n_pad > 0 ? 1 : 0);
-    // uniform batches: nudge the split so that (#items) % grid == 0
     bool uniform = true;
     for (int p = 1; p < P; ++p) uniform = uniform && pi[p].n_pad == pi[0].n_pad && pi[p].H == pi[0].H;
-    if (uniform && hb_total > 0 && pi[0].n_pad > 0) {
+    if (uniform && pi[0].n_pad > 0 && pi[0].H > 0) {
         const long long ng = pi[0].n_pad / kSub;
-        long long ns0 = std::max<long long>(1, ceil_div(ng, gps_target));
-        long long best_ns = ns0;
-        // the split that is actually realised after rounding the range to whole bitmap words
-        auto realised = [&](long long ns) {
-            long long gps = ceil_div(ng, ns);
-            if (ns > 1) gps = ((gps + 31) / 32) * 32;
-            return (long long)ceil_div(ng, gps);
-        };
-        for (long long ns = ns0; ns <= std::min<long long>(ng, ns0 * 2 + 4); ++ns) {
-            if ((hb_total * realised(ns)) % grid == 0) { best_ns = ns; break; }
+        const long long hb_total = (long long)P * ceil_div(pi[0].H, kHypPerBlock);
+        // large batches keep >= kItemsPerBlock items per block (the dynamic tail is half an item); a batch so small that the
+        // target sits on its floor may also use fewer, larger items when that fills the grid's rounds better
+        const bool small = gps_target == 64;
+        const long long lo = std::max<long long>(16, gps_target / 2), hi = std::min<long long>(ng, small ? gps_target * 2 : gps_target);
+        double best_cost = 1e300;
+        long long best_gps = std::min<long long>(ng, gps_target);
+        for (long long gps = lo; gps <= hi; ++gps) {
+            const long long items = hb_total * ceil_div(ng, gps);
+            const long long rounds = (items + grid - 1) / grid;
+            // makespan in group-units per block (+ a per-item cost of ~6 groups: hypothesis reload, claim, count atomics)
+            const double cost = (double)rounds * (double)(gps + 6);
+            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best_gps = gps; }
         }
-        gps_target = std::max<long long>(1, ceil_div(ng, best_ns));
+        gps_target = best_gps;
     }
     long long item_off = 0;
     for (int p = 0; p < P; ++p) {
@@ -116,7 +125,6 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         int gps = (int)std::min<long long>(ng, gps_target);
         int ns = ceil_div(ng, gps);
         gps = ceil_div(ng, ns);
-        if (ns > 1) gps = ((gps + 31) / 32) * 32;      // item boundaries fall on bitmap-word boundaries (1024 points)
         ns = ceil_div(ng, gps);
         o.nsplit = ns;
         o.groups_per_split = gps;
@@ -129,7 +137,7 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     rc = ensure(c->pair_info, sizeof(PairInfo) * (size_t)P);
     if (rc) return rc;
     RG_CUDA(cudaMemcpyAsync(c->pair_info.ptr, pi, sizeof(PairInfo) * (size_t)P, cudaMemcpyHostToDevice, st));
-    RG_CUDA(cudaEventRecord(c->staging_free, st));
+    RG_CUDA(cudaEventRecord(c->staging_free[turn], st));
     return RG_OK;
 }
 

@@ -5,6 +5,10 @@
 
 namespace rg {
 
+struct ScoreState;                                   // f_api.cu (same translation unit)
+int score_state_layout(Ctx* c, int P, long long Htot, int bbox_words, ScoreState& s);
+FlagList flag_list_for(Ctx* c, const ScoreState& s, double evals, int* rc_out);
+
 static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const double* y, const int* idx, const FPlan& plan,
                             int n, const PnpFrame* fr) {
     const int H = (int)plan.Htot;
@@ -15,11 +19,27 @@ static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const doub
     double* pose64 = (double*)c->pose64.ptr;
     Pose32* pose32 = (Pose32*)c->pose32.ptr;
     unsigned char* flags = (unsigned char*)c->flags.ptr;
-    switch (n) {
-        case 6: pnp_solve_jacobi<6><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
-        case 7: pnp_solve_jacobi<7><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
-        case 8: pnp_solve_jacobi<8><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
-        default: set_error("invalid argument: PnP sample size n must be 6, 7 or 8"); return RG_ERR_ARG;
+    if (c->opt_pnp_solver == 0) {                    // default: thread per hypothesis, Givens QR + row Jacobi in shared memory
+        if (!c->pnp_rows_attr_set) {
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+            c->pnp_rows_attr_set = true;             // per context = per device
+        }
+        const int g2 = ceil_div(H, kRowsThreads);
+        switch (n) {
+            case 6: pnp_solve_rows<6><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 7: pnp_solve_rows<7><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 8: pnp_solve_rows<8><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            default: set_error("invalid argument: PnP sample size n must be 6, 7 or 8"); return RG_ERR_ARG;
+        }
+    } else {
+        switch (n) {
+            case 6: pnp_solve_jacobi<6><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 7: pnp_solve_jacobi<7><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 8: pnp_solve_jacobi<8><<<grid, kJacobiThreads, 0, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            default: set_error("invalid argument: PnP sample size n must be 6, 7 or 8"); return RG_ERR_ARG;
+        }
     }
     c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
@@ -55,42 +75,44 @@ static int pnp_workspace(Ctx* c, const FPlan& plan) {
     if ((rc = ensure(c->pose64, sizeof(double) * 12 * H))) return rc;
     if ((rc = ensure(c->pose32, sizeof(Pose32) * H))) return rc;
     if ((rc = ensure(c->flags, H))) return rc;
-    if ((rc = ensure(c->counts, sizeof(int) * (H + 1)))) return rc;      // + the scorer's work counter
     if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
     if ((rc = ensure(c->best, sizeof(int2) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
-    if ((rc = ensure(c->bitmap, sizeof(unsigned) * (size_t)std::max<long long>(plan.total_words, 1)))) return rc;
+    c->prep_pts = nullptr;                            // the F path's prepared points do not survive a PnP call's PairInfo table
     return RG_OK;
 }
 
 static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* X, const double* y, double thr2,
                             int score_path) {
-    int* counts = (int*)c->counts.ptr;
+    ScoreState s;
+    int rc = score_state_layout(c, plan.P, plan.Htot, 0, s);
+    if (rc) return rc;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    RG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)std::max<long long>(plan.Htot, 1) + 1), st));   // counts + work counter
+    RG_CUDA(cudaMemsetAsync(c->state.ptr, 0, s.bytes, st));     // counts + work counter + flag-list size + overflow marks
     RG_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 8, st));
-    if (plan.Htot == 0) return RG_OK;
+    if (plan.Htot == 0 || (score_path == SCORE_FP32_GUARDED && plan.n_items == 0)) {
+        prof_mark(c, st, 3);
+        return RG_OK;
+    }
     PairInfo* pi = (PairInfo*)c->pair_info.ptr;
     if (score_path == SCORE_FP32_GUARDED) {
-        if (plan.n_items > 0) {
-            constexpr size_t smem = score_smem_bytes<PnpPolicy>();
-            const int grid = std::min(plan.n_items, c->sm_count * score_blocks_per_sm<PnpPolicy>());
-            score_packed<PnpPolicy><<<grid, kScoreThreads, smem, st>>>((const float4*)c->X32.ptr, (const Pose32*)c->pose32.ptr,
-                                                                      pi, plan.P, plan.n_items, counts,
-                                                                      (unsigned*)c->bitmap.ptr,
-                                                                      counts + std::max<long long>(plan.Htot, 1));
-            prof_mark(c, st, 3);
-            const int fgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8,
-                                                                              (plan.total_words + 255) / 256));
-            PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, (const Pose32*)c->pose32.ptr, (const double*)c->pose64.ptr,
-                              pi, plan.P, thr2};
-            fixup_scan<PnpFix><<<fgrid, 256, 0, st>>>(fp, plan.total_words, (const unsigned*)c->bitmap.ptr, counts, stats);
-            c->last_stats[7] += 2;
-        }
+        int bps = 1;
+        if ((rc = score_blocks_per_sm<PnpPolicy>(&bps))) return rc;
+        FlagList fl = flag_list_for(c, s, plan.evals, &rc);
+        if (rc) return rc;
+        constexpr size_t smem = score_smem_bytes<PnpPolicy>();
+        const int grid = std::min(plan.n_items, c->sm_count * bps);
+        score_packed<PnpPolicy><<<grid, kScoreThreads, smem, st>>>((const float4*)c->X32.ptr, (const Pose32*)c->pose32.ptr, pi,
+                                                                  plan.P, plan.n_items, s.counts, fl, s.work);
+        prof_mark(c, st, 3);
+        PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, (const Pose32*)c->pose32.ptr, (const double*)c->pose64.ptr,
+                          pi, plan.P, thr2};
+        fixup_list<PnpFix><<<c->sm_count * 4, 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
+        c->last_stats[7] += 2;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
         pnp_score_fp64<<<dim3(std::max(1, ceil_div(plan.maxH, 128)), plan.P, zs), 128, 0, st>>>(
-            X, y, pi, (const double*)c->pose64.ptr, thr2, counts);
+            X, y, pi, (const double*)c->pose64.ptr, thr2, s.counts);
         prof_mark(c, st, 3);
         c->last_stats[7] += 1;
     }
@@ -101,18 +123,21 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
 // views batched in CSR form; n_vote (host, optional) = per-view number of leading correspondences that vote
 static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const double* y, const int* view_off,
                           const int* n_vote, const int* idx, const int* hyp_off, int n, double thr2, int score_path,
-                          int* best_idx, int* best_count, double* Rt, unsigned char* mask) {
+                          int* best_idx, int* best_count, double* Rt, unsigned char* mask, int hyp_first = 0,
+                          unsigned long long* keys = nullptr) {
     RG_CHECK_ARG(n >= 6 && n <= 8, "PnP sample size n must be 6, 7 or 8 (DLT needs m >= 6)");
     RG_CHECK_ARG(thr2 >= 0.0 && std::isfinite(thr2), "thr2 must be finite and >= 0");
     RG_CHECK_ARG(score_path == SCORE_FP32_GUARDED || score_path == SCORE_FP64, "unknown scoring path");
     RG_CUDA(cudaSetDevice(c->device));
     FPlan plan;
-    int rc = f_plan(c, st, V, view_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>(), n_vote);
+    int bps = 1, rc = score_blocks_per_sm<PnpPolicy>(&bps);
     if (rc) return rc;
+    if ((rc = f_plan(c, st, V, view_off, hyp_off, plan, bps, n_vote, hyp_first))) return rc;
     for (int v = 0; v < V; ++v)
         RG_CHECK_ARG(hyp_off[v + 1] == hyp_off[v] || view_off[v + 1] - view_off[v] >= n, "a view with hypotheses needs at least n correspondences");
     if ((rc = pnp_workspace(c, plan))) return rc;
     c->last_stats[7] = 0;
+    c->last_passes = 1;
     if (V == 0) return RG_OK;
     // a zero threshold makes the FP32 frame singular: score such calls in FP64 only
     if (!(thr2 > 0.0)) score_path = SCORE_FP64;
@@ -126,7 +151,7 @@ static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const
     prof_mark(c, st, 4);
     int2* best = (int2*)c->best.ptr;
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
-    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts.ptr, pi, best, nullptr, nullptr);
+    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys);
     const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
     pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
                                             best_count);
@@ -180,6 +205,20 @@ int rg_pnp_ransac_batched_dev(void* ctx, void* stream, int V, const double* X_de
                           hyp_off_host, n, thr2, score_path, best_idx_dev, best_count_dev, Rt_dev, mask_dev);
 }
 
+// hypothesis-split mode: this rank's hypotheses are [hyp_index_base, hyp_index_base + H_v) of every view; key_dev (V, optional)
+// receives the cross-GPU argmax keys (count << 32 | ~global index)
+int rg_pnp_ransac_batched_dev2(void* ctx, void* stream, int V, const double* X_dev, const double* y_dev,
+                               const int* view_off_host, const int* n_vote_host, const int* idx_dev, const int* hyp_off_host,
+                               int n, double thr2, int score_path, int hyp_index_base, int* best_idx_dev, int* best_count_dev,
+                               double* Rt_dev, unsigned char* mask_dev, unsigned long long* key_dev) {
+    RG_CHECK_ARG(ctx != nullptr, "ctx is null");
+    RG_CHECK_ARG(V >= 0 && view_off_host && hyp_off_host && hyp_index_base >= 0, "bad view table");
+    RG_CHECK_ARG(best_idx_dev && best_count_dev && Rt_dev, "output pointers are null");
+    return pnp_ransac_dev((Ctx*)ctx, (cudaStream_t)stream, V, X_dev, y_dev, view_off_host, n_vote_host, idx_dev,
+                          hyp_off_host, n, thr2, score_path, best_idx_dev, best_count_dev, Rt_dev, mask_dev, hyp_index_base,
+                          key_dev);
+}
+
 int rg_pnp_ransac_dev(void* ctx, void* stream, int N, int N_sel, const double* X_dev, const double* y_dev, int H, int n,
                       const int* idx_dev, double thr2, int score_path, int* best_idx_dev, int* best_count_dev, double* Rt_dev,
                       unsigned char* mask_dev) {
@@ -223,7 +262,7 @@ int rg_pnp_ransac_batched_host(void* ctx, void* stream, int V, const double* X, 
     RG_CUDA(cudaMemcpyAsync(best_count, d_i + V, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(Rt, c->d_out_b.ptr, sizeof(double) * 12 * (size_t)V, cudaMemcpyDeviceToHost, st));
     if (mask && N) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_d.ptr, N, cudaMemcpyDeviceToHost, st));
-    if (counts && H) RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * H, cudaMemcpyDeviceToHost, st));
+    if (counts && H) RG_CUDA(cudaMemcpyAsync(counts, c->counts_ptr, sizeof(int) * H, cudaMemcpyDeviceToHost, st));
     if (poses && H) RG_CUDA(cudaMemcpyAsync(poses, c->pose64.ptr, sizeof(double) * 12 * H, cudaMemcpyDeviceToHost, st));
     if (flags && H) RG_CUDA(cudaMemcpyAsync(flags, c->flags.ptr, H, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
@@ -257,8 +296,9 @@ int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, con
     RG_CHECK_ARG(poses && (N == 0 || (X && y)), "input pointers are null");
     const int pair_off[2] = {0, N}, hyp_off[2] = {0, H};
     FPlan plan;
-    int rc = f_plan(c, st, 1, pair_off, hyp_off, plan, score_blocks_per_sm<PnpPolicy>());
+    int bps = 1, rc = score_blocks_per_sm<PnpPolicy>(&bps);
     if (rc) return rc;
+    if ((rc = f_plan(c, st, 1, pair_off, hyp_off, plan, bps))) return rc;
     if ((rc = pnp_workspace(c, plan))) return rc;
     if ((rc = ensure(c->d_in_a, sizeof(double) * 3 * std::max<size_t>((size_t)N, 1)))) return rc;
     if ((rc = ensure(c->d_in_c, sizeof(double) * 2 * std::max<size_t>((size_t)N, 1)))) return rc;
@@ -278,7 +318,7 @@ int rg_pnp_score_count_host(void* ctx, void* stream, int N, const double* X, con
     c->last_stats[7] += 1;
     if ((rc = pnp_score_launch(c, st, plan, dX, dy, thr2, score_path))) return rc;
     RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaMemcpyAsync(counts, c->counts.ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(counts, c->counts_ptr, sizeof(int) * (size_t)H, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     return RG_OK;
 }

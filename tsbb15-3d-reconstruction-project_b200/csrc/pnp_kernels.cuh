@@ -6,8 +6,8 @@
 //   ransac.py:96-111  y' = R x + t for every correspondence; e = |pnorm(y) - pnorm(y')|^2; member iff thresh >= e;
 //                     keep the pose with the largest consensus
 //
-// Kernels: pnp_bbox_init / pnp_bbox / pnp_frame / pnp_normalise, pnp_solve_jacobi<n>, score_packed<PnpPolicy>,
-//          pnp_fixup, pnp_score_fp64, argmax_counts, pnp_finish.
+// Kernels: pnp_bbox_init / pnp_bbox / pnp_frame / pnp_normalise, pnp_solve_rows<n> (default) or pnp_solve_jacobi<n>,
+//          score_packed<PnpPolicy>, fixup_list<PnpFix>, pnp_score_fp64, argmax_counts, pnp_finish.
 #pragma once
 #include "f_kernels.cuh"
 #include "jacobi.cuh"
@@ -366,6 +366,228 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
 }
 
 // ------------------------------------------------------------------------------------------------
+// minimal-sample DLT-PnP, default solver (round 2): ONE THREAD per hypothesis, no shuffles.
+//   1. the 3n x 12 design matrix never exists: its rows (r_l (x) Xh_k, 8 non-zeros each) are rotated one by one into the
+//      12 x 12 triangular factor R (Givens row insertion, backward stable), R lives in shared memory [element][thread];
+//   2. the rows of R are orthogonalised by one-sided Jacobi rotations (= Hestenes on R^T): at convergence row i is
+//      sigma_i v_i^T, the right singular vectors of A scaled by the singular values — no V accumulation, 12 instead of
+//      18 + 12 doubles per column, and QR preconditioning roughly halves the sweeps;
+//   3. the minimiser c0 = v_12 is the normalised smallest row; when that row is below 1e-4 sigma_1 (exact data: it is pure
+//      rounding noise) c0 is instead the unit vector orthogonal to the other eleven rows (projection of the best
+//      coordinate vector, applied twice), which has the same eps * sigma_1 / gap accuracy as any SVD.
+// Round 1's 16-lane group Jacobi (pnp_solve_jacobi, the solver BASELINE.json names) spent its time in 60 SHFL per rotation
+// round: 0.30 ms for 8192 hypotheses; it stays selectable (rg_set_option(ctx, 7, 1)) and is parity-tested against this one.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsThreads = 64;
+constexpr size_t kRowsSmem = (144 + 12) * kRowsThreads * sizeof(double);
+
+// 1/sqrt(x) to full double precision from the 20-bit hardware seed (MUFU.RSQ64H) + two Newton steps: ~10 dependent
+// instructions instead of the ~60 of sqrt() followed by a division.  x > 0, normal range.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+__device__ __forceinline__ double rcp_approx(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+// Jacobi rotation for the thread-per-hypothesis solver.  Any rotation with c^2 + s^2 = 1 (to rounding) keeps the
+// iteration an orthogonal transformation, so only c and s = c t have to be exact functions of t; the ANGLE itself only
+// steers convergence and is computed from 20-bit reciprocal / reciprocal-square-root seeds (a 1e-6 relative error in t
+// leaves an off-diagonal of 1e-6 of the old one instead of zero: at most one extra sweep, measured none).  The exact
+// formula (jacobi_rot: two divisions, two square roots) was ~750 dependent cycles of the ~1100 per rotation.
+__device__ __forceinline__ void jacobi_rot_fast(double a, double b, double g, double& c, double& s) {
+    const double zeta = (b - a) * 0.5 * rcp_approx(g);
+    const double w = fma(zeta, zeta, 1.0);
+    double rs;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(w));
+    const double root = w * rs;                                   // ~ sqrt(1 + zeta^2)
+    double t = copysign(rcp_approx(fabs(zeta) + root), zeta);
+    if (!(fabs(t) <= 1.0)) t = 0.0;       // zeta^2 overflowed (needs a column ratio > 1e278, excluded by the `tiny` test): no rotation
+    c = rsqrt_nr(fma(t, t, 1.0));
+    s = c * t;
+}
+
+template <int NPTS>
+__global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __restrict__ X, const double* __restrict__ y,
+                                                                const int* __restrict__ idx, const PairInfo* __restrict__ pi,
+                                                                int V, int H, const PnpFrame* __restrict__ fr,
+                                                                double* __restrict__ pose64, Pose32* __restrict__ pose32,
+                                                                unsigned char* __restrict__ flags) {
+    extern __shared__ double rows_sm[];
+    constexpr int T = kRowsThreads;
+    double* R = rows_sm + threadIdx.x;                 // R[i][j] at R[(12 * i + j) * T]
+    double* row = rows_sm + 144 * T + threadIdx.x;     // the row being inserted, row[j] at row[j * T]
+    const int hq = blockIdx.x * T + threadIdx.x;
+    const bool live = hq < H;
+    const int h = live ? hq : H - 1;
+    int view = 0;
+    {
+        int lo = 0, hi = V;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        view = lo;
+    }
+    const int N = pi[view].n_all;
+    const size_t pbase = (size_t)pi[view].pt_off;
+    for (int e = 0; e < 144; ++e) R[e * T] = 0.0;
+
+    // ---- 1. Givens row insertion -------------------------------------------------------------------------
+    for (int k = 0; k < NPTS; ++k) {
+        int q = idx[(size_t)h * NPTS + k];
+        q = q < 0 ? 0 : (q >= N ? N - 1 : q);
+        const size_t gq = pbase + q;
+        const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
+        const double y0 = y[2 * gq], y1 = y[2 * gq + 1];
+        for (int l = 0; l < 3; ++l) {
+            // rows of [y]_x for y = (y0, y1, 1):  r0 = (0,-1,y1)  r1 = (1,0,-y0)  r2 = (-y1,y0,0)
+            const double ra = l == 0 ? 0.0 : (l == 1 ? 1.0 : -y1);
+            const double rb = l == 0 ? -1.0 : (l == 1 ? 0.0 : y0);
+            const double rc = l == 0 ? y1 : (l == 1 ? -y0 : 0.0);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { row[b * T] = ra * Xh[b]; row[(4 + b) * T] = rb * Xh[b]; row[(8 + b) * T] = rc * Xh[b]; }
+            for (int i = 0; i < 12; ++i) {
+                const double v = row[i * T];
+                if (v == 0.0) continue;
+                const double d = R[(13 * i) * T];
+                const double x2 = fma(d, d, v * v);
+                if (x2 < 1e-280) continue;                          // |v| below 1e-140: zero for every purpose (NaN still propagates)
+                const double inv = rsqrt_nr(x2);
+                const double cs = d * inv, sn = v * inv;
+                for (int j = i; j < 12; ++j) {
+                    const double a = R[(12 * i + j) * T], b = row[j * T];
+                    R[(12 * i + j) * T] = cs * a + sn * b;
+                    row[j * T] = cs * b - sn * a;
+                }
+            }
+        }
+    }
+
+    // ---- 2. one-sided Jacobi on the rows of R ----------------------------------------------------------------
+    double normF2 = 0.0;
+    for (int e = 0; e < 144; ++e) { const double t = R[e * T]; normF2 += t * t; }
+    const double tiny = 7.9e-31 * normF2;
+    // round-robin tournament: 11 rounds x 6 DISJOINT row pairs.  The kernel runs one warp per SM sub-partition at best
+    // (8192 hypotheses = 256 warps), so nothing hides the latency of a rotation's dependent chain (dot products, seeds,
+    // Newton steps): kIlp independent pairs are therefore rotated together by the same thread, interleaved by the compiler.
+    constexpr int kIlp = 3;
+    for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
+        bool rotated = false;
+        for (int r = 0; r < 11; ++r) {
+            for (int m0 = 0; m0 < 6; m0 += kIlp) {
+                int pi_[kIlp], qi_[kIlp];
+                double rp[kIlp][12], rq[kIlp][12];
+#pragma unroll
+                for (int u = 0; u < kIlp; ++u) {
+                    const int m = m0 + u;
+                    int p = (m == 0) ? r : (r + m) % 11;
+                    int q = (m == 0) ? 11 : (r + 11 - m) % 11;
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    pi_[u] = p; qi_[u] = q;
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) { rp[u][k] = R[(12 * p + k) * T]; rq[u][k] = R[(12 * q + k) * T]; }
+                }
+#pragma unroll
+                for (int u = 0; u < kIlp; ++u) {
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 12; k += 2) {
+                        a0 = fma(rp[u][k], rp[u][k], a0); a1 = fma(rp[u][k + 1], rp[u][k + 1], a1);
+                        b0 = fma(rq[u][k], rq[u][k], b0); b1 = fma(rq[u][k + 1], rq[u][k + 1], b1);
+                        g0 = fma(rp[u][k], rq[u][k], g0); g1 = fma(rp[u][k + 1], rq[u][k + 1], g1);
+                    }
+                    const double a = a0 + a1, b = b0 + b1, g = g0 + g1;
+                    const bool conv = !(g * g > 1e-30 * (a * b)) || !(fmin(a, b) > tiny);
+                    if (!conv) {
+                        double c, s;
+                        jacobi_rot_fast(a, b, g, c, s);
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) {
+                            const double x = rp[u][k], z = rq[u][k];
+                            R[(12 * pi_[u] + k) * T] = c * x - s * z;
+                            R[(12 * qi_[u] + k) * T] = s * x + c * z;
+                        }
+                        rotated = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
+    }
+
+    // ---- 3. smallest row -> c0 -----------------------------------------------------------------------------
+    double nrm[12];
+    double s0 = INFINITY, s1 = INFINITY, smax = 0.0;
+    int jm = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { const double r = R[(12 * i + k) * T]; t = fma(r, r, t); }
+        nrm[i] = t;
+        const double key = (t == t) ? t : INFINITY;
+        if (key < s0) { s1 = s0; s0 = key; jm = i; }
+        else if (key < s1) s1 = key;
+        if (t == t) smax = fmax(smax, t);
+    }
+    double c0[12];
+    if (s0 > 1e-8 * smax) {
+        const double inv = rsqrt(s0);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c0[k] = R[(12 * jm + k) * T] * inv;
+    } else {
+        // unit vector orthogonal to the eleven other rows; start from the coordinate vector the projector keeps best
+        double dg[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) dg[k] = 1.0;
+        for (int i = 0; i < 12; ++i) {
+            if (i == jm || !(nrm[i] > tiny)) continue;
+            const double inv = 1.0 / nrm[i];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { const double r = R[(12 * i + k) * T]; dg[k] -= r * r * inv; }
+        }
+        int e = 0;
+#pragma unroll
+        for (int k = 1; k < 12; ++k) if (dg[k] > dg[e]) e = k;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c0[k] = (k == e) ? 1.0 : 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = 0; i < 12; ++i) {
+                if (i == jm || !(nrm[i] > tiny)) continue;
+                double dot = 0.0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) dot = fma(R[(12 * i + k) * T], c0[k], dot);
+                dot /= nrm[i];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) c0[k] -= dot * R[(12 * i + k) * T];
+            }
+        }
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) t = fma(c0[k], c0[k], t);
+        const double inv = rsqrt(t);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c0[k] *= inv;
+    }
+    double Rt[12];
+    const bool ok = enforce_pose(c0, Rt);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pose64[(size_t)h * 12 + k] = Rt[k];
+        unsigned char fl = 0;
+        // minimiser not unique: sigma_11 ~ sigma_12 relative to sigma_1
+        if (!(sqrt(s1) - sqrt(s0) > 1e-9 * sqrt(smax))) fl |= 1;
+        if (!ok) fl |= 2;
+        flags[h] = fl;
+        make_pose32(Rt, fr[view], pose32 + h);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // packed FP32 scorer policy for the reprojection criterion
 // ------------------------------------------------------------------------------------------------
 struct Pose2 { float p[12]; };
@@ -374,7 +596,7 @@ struct PnpPolicy {
     typedef Pose32 Rec;
     typedef Pose2 Regs;
     static constexpr int kVec4PerPair = 3;
-    static constexpr int kChunkPts = 512;       // 12 KB of points per stage (half a bitmap word)
+    static constexpr int kChunkPts = 512;       // 12 KB of points per stage (two flag words)
 
     __device__ static __forceinline__ void load(const Pose32* __restrict__ sh, int slot, bool valid, Pose2& out, float& G) {
         if (valid) {
@@ -437,15 +659,12 @@ struct PnpFix {
         const float4* pts32; const double* X; const double* y; const Pose32* pose32; const double* pose64;
         const PairInfo* pi; int V; double thr2;
     };
-    __device__ static __forceinline__ void decode(const Params& p, long long wi, int& h, int& fbase, int& view) {
+    __device__ static __forceinline__ int pair_of(const Params& p, int h) {
         int lo = 0, hi = p.V;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].word_off <= wi) lo = mid; else hi = mid; }
-        const long long local = wi - p.pi[lo].word_off;
-        const int hl = (int)(local / p.pi[lo].words_per_hyp);
-        view = lo;
-        h = p.pi[lo].hyp_off + hl;
-        fbase = (int)(local - (long long)hl * p.pi[lo].words_per_hyp) * 32;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (p.pi[mid].hyp_off <= h) lo = mid; else hi = mid; }
+        return lo;
     }
+    __device__ static __forceinline__ int n_points(const Params& p, int view) { return p.pi[view].n; }
     __device__ static __forceinline__ void scan(const Params& p, int h, int flag, int view, unsigned& band, unsigned& sign) {
         const PairInfo& info = p.pi[view];
         const Pose32 ps = p.pose32[h];

@@ -47,9 +47,7 @@ __device__ __forceinline__ float2 ffma2_sbs(float s, float2 b, float c) {       
 
 struct ScoreItem {
     int pair, h_base, H_end;        // hypotheses [h_base, min(h_base + kHypPerBlock, H_end)) (global indices)
-    int g0, g1;                     // kSub-point groups [g0, g1) of the pair (g0 is a multiple of 32)
-    int W;                          // bitmap words per hypothesis of this pair
-    long long wbase;                // bitmap word of (first hypothesis of the item, group g0)
+    int g0, g1;                     // kSub-point groups [g0, g1) of the pair
 };
 
 __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi, int P, int item) {
@@ -66,15 +64,53 @@ __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi
     const int ngroups = info.n_pad / kSub;
     it.g0 = min(sp * info.groups_per_split, ngroups);
     it.g1 = min(it.g0 + info.groups_per_split, ngroups);
-    it.W = info.words_per_hyp;
-    it.wbase = info.word_off + (long long)(hb * kHypPerBlock) * info.words_per_hyp + (it.g0 >> 5);
     return it;
 }
 
-// Guard-band bookkeeping: one bit per (hypothesis, kSub-point group).  A set bit means "the FP32 result of at least
-// one evaluation of this group lies inside the rounding band of this hypothesis" and makes the fix-up kernel re-evaluate
-// that group in FP64.  Every 32-bit word (32 groups = 256 points of one hypothesis) is written by exactly one thread of
-// exactly one work item, so the scorer needs no atomics and the bitmap needs no clearing.
+// Guard-band bookkeeping: one flag per (hypothesis, kSub-point group) = "the FP32 result of at least one evaluation of this
+// group lies inside the rounding band of this hypothesis"; the fix-up kernel re-evaluates exactly those groups in FP64.
+// Round 1 kept the flags in a bitmap (1 bit per hypothesis and group: 102 MB written by the scorer and scanned by the
+// fix-up for a 16-pair batch although only 0.36 % of the bits are set).  Now a thread collects the 32 flags of 256
+// consecutive correspondences in a register and, once per such word, the warp appends its set flags as dense
+// (hypothesis, group) records to ONE global list (warp-aggregated: REDUX + prefix + one atomicAdd per warp and word, outside
+// the evaluation loop).  If the list is full the hypothesis is marked in `ovf` and recounted entirely in FP64 by the fix-up
+// kernel, so adversarial inputs (everything on the threshold) degrade to the FP64 path instead of failing.
+struct FlagList {
+    int2* rec;                 // {global hypothesis index, group index inside the pair}
+    unsigned* n;               // records appended so far (may exceed cap: the excess was not stored)
+    unsigned cap;
+    unsigned char* ovf;        // per hypothesis: 1 = some records of this hypothesis were dropped
+};
+
+// all 32 lanes call this (fl = 0 for lanes with nothing to append)
+__device__ __forceinline__ void flag_append(const FlagList& L, unsigned fl, int h, int group_base) {
+    const unsigned full = 0xffffffffu;
+    const int nb = __popc(fl);
+    const int tot = __reduce_add_sync(full, nb);
+    if (tot == 0) return;
+    const int lane = threadIdx.x & 31;
+    int incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += v;
+    }
+    unsigned base = 0u;
+    if (lane == 0) base = atomicAdd(L.n, (unsigned)tot);
+    base = __shfl_sync(full, base, 0);
+    if (nb == 0) return;
+    unsigned pos = base + (unsigned)(incl - nb);
+    if (base + (unsigned)tot > L.cap || base + (unsigned)tot < base) {      // list full: FP64 recount of this hypothesis
+        L.ovf[h] = 1;
+        return;
+    }
+    while (fl) {
+        const int b = __ffs(fl) - 1;
+        fl &= fl - 1;
+        L.rec[pos++] = make_int2(h, group_base + b);
+    }
+}
+
 // Policy requirements:
 //   typedef Rec;                       hypothesis record in global/shared memory (sizeof % 16 == 0)
 //   typedef Regs;                      hypothesis in registers
@@ -100,7 +136,7 @@ template <class Pol>
 __global__ void __launch_bounds__(kScoreThreads, kScoreBlocksPerSM)
 score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restrict__ hyp32,
              const PairInfo* __restrict__ pi, int P, int n_items, int* __restrict__ counts,
-             unsigned* __restrict__ bitmap, int* __restrict__ work_counter) {
+             FlagList flist, int* __restrict__ work_counter) {
     __shared__ int s_next;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScoreStage<Pol>* st = reinterpret_cast<ScoreStage<Pol>*>(smem_raw);
@@ -149,12 +185,10 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
         float G[kHypPerThread];
         unsigned cnt[kHypPerThread];
         int hid[kHypPerThread];
-        unsigned* wptr[kHypPerThread];
 #pragma unroll
         for (int k = 0; k < kHypPerThread; ++k) {
             G[k] = 0.f; cnt[k] = 0u;
             hid[k] = cur.h_base + k * kScoreThreads + tid;
-            wptr[k] = bitmap + cur.wbase + (long long)(k * kScoreThreads + tid) * cur.W;
         }
 
         const int total_pts = (cur.g1 - cur.g0) * kSub;
@@ -185,9 +219,9 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
                     Pol::load(st[stage].hyp, k * kScoreThreads + tid, hid[k] < cur.H_end, Hy[k], G[k]);
             }
             const float4* sp = st[stage].pts;
-            // chunk = whole bitmap words (32 flag groups of kSub points each), except the last word of an item
+            // chunk = whole flag words (32 flag groups of kSub points each), except the last word of an item
             const int ngr = npts / kSub;
-            const int wfirst = done / (kSub * 32);
+            const int gfirst = cur.g0 + done / kSub;
             for (int wq = 0; wq * 32 < ngr; ++wq) {
                 const int ng = min(32, ngr - wq * 32);
                 unsigned flag[kHypPerThread];
@@ -206,7 +240,7 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
                 }
 #pragma unroll
                 for (int k = 0; k < kHypPerThread; ++k)
-                    if (hid[k] < cur.H_end) wptr[k][wfirst + wq] = flag[k];
+                    flag_append(flist, hid[k] < cur.H_end ? flag[k] : 0u, hid[k], gfirst + wq * 32);
             }
             __syncthreads();          // everyone is done with this stage before it is refilled
             stage ^= 1;
@@ -221,29 +255,51 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
     }
 }
 
-// FP64 fix-up.  Two levels of warp compaction keep all 32 lanes busy although only ~0.4 % of the bitmap bits are set
-// and only ~1 in 8 evaluations of a flagged group is inside the band:
-//   level 1  scan the bitmap (coalesced, 4 words per lane in flight), queue the set bits; one lane per flagged group
-//            re-evaluates its kSub correspondences in FP32 (bit-identical op sequence) -> band mask + FP32 decisions;
+// FP64 fix-up.  Two levels of warp compaction keep all 32 lanes busy although only ~1 in 8 evaluations of a flagged group
+// is inside the band:
+//   level 1  one lane per record of the flag list: re-evaluate the group's kSub correspondences in FP32 (bit-identical
+//            op sequence) -> band mask + FP32 decisions;
 //   level 2  queue the band evaluations; one lane per evaluation applies the reference formula in FP64 and corrects
 //            counts[h] by (exact decision - FP32 decision).
-// stats: [0] flagged groups, [1] band evaluations, [2] changed decisions.
-//   Fix::decode(params, word_index, h, flag_base, aux)            hypothesis / first flag index / pair of a bitmap word
-//   Fix::scan(params, h, flag, aux, band, sign)                   FP32 pass over one group (bit k = correspondence k)
+// Hypotheses marked in flist.ovf (list overflow) are recounted over all their correspondences in FP64 first.
+// stats: [0] flagged groups, [1] band evaluations, [2] changed decisions, [3] hypotheses recounted after a list overflow.
+//   Fix::pair_of(params, h)                                       pair / view of a global hypothesis index
+//   Fix::n_points(params, aux)                                    voting correspondences of that pair / view
+//   Fix::scan(params, h, group, aux, band, sign)                  FP32 pass over one group (bit k = correspondence k)
 //   Fix::exact(params, h, i, aux)                                 FP64 decision for correspondence i of the pair/view
 template <class Fix>
-__global__ void __launch_bounds__(256) fixup_scan(typename Fix::Params prm, long long total_words,
-                                                   const unsigned* __restrict__ bitmap, int* __restrict__ counts,
-                                                   unsigned long long* __restrict__ stats) {
-    __shared__ int4 queue[8][64];
+__global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, FlagList flist, int Htot,
+                                                   int* __restrict__ counts, unsigned long long* __restrict__ stats) {
     __shared__ int4 queue2[8][64];
+    __shared__ int s_red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int4* q = queue[warp];
     int4* q2 = queue2[warp];
-    int qn = 0, q2n = 0;
+    int q2n = 0;
     unsigned long long n_groups = 0, n_band = 0, n_flip = 0;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned full = 0xffffffffu;
+    const unsigned n_rec_raw = *flist.n;
+    const unsigned n_rec = n_rec_raw < flist.cap ? n_rec_raw : flist.cap;
+
+    if (n_rec_raw > flist.cap) {                       // rare: some hypotheses lost records -> exact recount (block per hypothesis)
+        for (int h = blockIdx.x; h < Htot; h += gridDim.x) {
+            if (!flist.ovf[h]) continue;               // uniform per block
+            const int aux = Fix::pair_of(prm, h);
+            const int n = Fix::n_points(prm, aux);
+            int c = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) c += Fix::exact(prm, h, i, aux);
+            c = __reduce_add_sync(full, c);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int t = 0;
+                for (int w = 0; w < 8; ++w) t += s_red[w];
+                counts[h] = t;
+                atomicAdd(&stats[3], 1ull);
+            }
+        }
+    }
 
     auto drain2 = [&](int n) {                      // lanes < n: one band evaluation each, FP64
         if (lane < n) {
@@ -270,61 +326,28 @@ __global__ void __launch_bounds__(256) fixup_scan(typename Fix::Params prm, long
             q2n = rest;
         }
     };
-    auto drain = [&](int n) {                       // lanes < n: one flagged group each, FP32 re-evaluation
+
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rec; base += stride) {
+        const unsigned i = base + lane;
         unsigned band = 0u, sign = 0u;
-        int4 r = make_int4(0, 0, 0, 0);
-        if (lane < n) {
-            r = q[lane];
-            Fix::scan(prm, r.x, r.y, r.z, band, sign);
-            n_groups += 1;
+        int2 r = make_int2(0, 0);
+        int aux = 0;
+        if (i < n_rec) {
+            r = flist.rec[i];
+            if (!flist.ovf[r.x]) {
+                aux = Fix::pair_of(prm, r.x);
+                Fix::scan(prm, r.x, r.y, aux, band, sign);
+                n_groups += 1;
+            }
         }
-        __syncwarp();
         while (__any_sync(full, band != 0u)) {
             const bool has = band != 0u;
             int k = 0;
             if (has) { k = __ffs(band) - 1; band &= band - 1; }
-            push2(has, make_int4(r.x, r.y * kSub + k, r.z, (int)((sign >> k) & 1u)));
-        }
-    };
-
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < total_words; wbase += 4 * stride) {
-        unsigned words[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {               // four independent loads in flight per lane
-            const long long wi = wbase + u * stride + lane;
-            words[u] = (wi < total_words) ? bitmap[wi] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            unsigned word = words[u];
-            if (!__any_sync(full, word != 0u)) continue;
-            int h = 0, fbase = 0, aux = 0;
-            if (word) Fix::decode(prm, wbase + u * stride + lane, h, fbase, aux);
-            while (__any_sync(full, word != 0u)) {
-                const bool has = word != 0u;
-                const unsigned m = __ballot_sync(full, has);
-                if (has) {
-                    const int b = __ffs(word) - 1;
-                    word &= word - 1;
-                    q[qn + __popc(m & lt)] = make_int4(h, fbase + b, aux, 0);
-                }
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    drain(32);
-                    const int rest = qn - 32;
-                    int4 mv = make_int4(0, 0, 0, 0);
-                    if (lane < rest) mv = q[32 + lane];
-                    __syncwarp();
-                    if (lane < rest) q[lane] = mv;
-                    __syncwarp();
-                    qn = rest;
-                }
-            }
+            push2(has, make_int4(r.x, r.y * kSub + k, aux, (int)((sign >> k) & 1u)));
         }
     }
-    drain(qn);
     drain2(q2n);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -341,9 +364,12 @@ __global__ void __launch_bounds__(256) fixup_scan(typename Fix::Params prm, long
 
 // best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
 // flags / stats (optional): hypotheses whose flag byte has bit 2 set (sample index out of range) are counted in stats[4]
+// keys (optional): the cross-GPU argmax key of the pair, (count << 32) | (0xFFFFFFFF - (hyp_first + index)), 0 when no
+// hypothesis of this rank has an inlier — what rg_argmax_pack_dev computed with a separate launch in round 1
 __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
                                                       int2* __restrict__ best, const unsigned char* __restrict__ flags,
-                                                      unsigned long long* __restrict__ stats) {
+                                                      unsigned long long* __restrict__ stats,
+                                                      unsigned long long* __restrict__ keys) {
     __shared__ unsigned long long sk[8];
     const int p = blockIdx.x;
     const PairInfo info = pi[p];
@@ -368,6 +394,10 @@ __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ cou
         const int cnt = (int)(key >> 32);
         const int idx = cnt > 0 ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : -1;
         best[p] = make_int2(idx, cnt);
+        if (keys != nullptr)
+            keys[p] = idx >= 0 ? (((unsigned long long)(unsigned)cnt << 32) |
+                                  (unsigned long long)(0xFFFFFFFFu - (unsigned)(info.hyp_first + idx)))
+                               : 0ull;
     }
 }
 

@@ -28,7 +28,11 @@ _STAGE: dict = {}
 
 def _concat_into(key, arrays, tail, dtype) -> np.ndarray:
     """np.concatenate into a cached grow-only buffer: the batched entry points are called in loops with the same shapes,
-    and a fresh 10 MB allocation per call costs more than the GPU work of a small batch."""
+    and a fresh 10 MB allocation per call costs more than the GPU work of a small batch.  The cache is keyed by the calling
+    THREAD as well: ctypes releases the GIL during the library call, so two threads (one per device, say) would otherwise
+    overwrite each other's staged inputs while an upload is in flight."""
+    import threading
+    key = (key, threading.get_ident())
     n = sum(a.shape[0] for a in arrays)
     buf = _STAGE.get(key)
     if buf is None or buf.shape[0] < n:
@@ -87,37 +91,49 @@ def last_stats(device=None, stream=0) -> dict:
     out = (C.c_longlong * 8)()
     cabi.check(lib.rg_get_last_stats(_vp(cabi.context(device)), _vp(stream), out))
     return {"recheck_groups": out[0], "band_evals": out[1], "flips": out[2], "overflow": out[3], "bad_index_hyps": out[4],
-            "launches": out[7]}
+            "passes": out[6], "launches": out[7]}
 
 
 def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TIE_FIRST, solver=SOLVER_QR,
                      score_path=SCORE_FP32_GUARDED, want_counts=False, want_F_all=False, want_mask=True,
-                     want_flags=False, device=None, stream=0) -> dict:
+                     want_flags=False, device=None, stream=0, n_hyp=None, sample_seed=0, first_pair=0) -> dict:
     """F-matrix RANSAC over a batch of image pairs in ONE library call.
 
     pts_list[p] : (N_p, 4) float64 rows (x0, x1, y0, y1);  idx_list[p] : (H_p, 8) int sample indices (host-drawn).
+    idx_list=None: ``n_hyp`` (int or per-pair list) index sets per pair are drawn ON THE DEVICE from ``sample_seed`` (pair p
+    has global id ``first_pair + p``) and never cross PCIe; ``philox.sample_indices(N_p, H_p, 8, sample_seed, first_pair + p)``
+    replays them on the host.
     Returns per-pair arrays ``best_idx`` (-1 = no hypothesis has any inlier), ``best_count``, ``F`` (P, 3, 3) and
     lists ``mask`` / ``counts`` / ``F_all`` / ``flags`` split per pair when requested.
     """
     lib = cabi.load_library()
     ctx = cabi.context(device)
     P = len(pts_list)
-    if len(idx_list) != P:
+    seeded = idx_list is None
+    if seeded:
+        if n_hyp is None:
+            raise ValueError("idx_list=None needs n_hyp")
+        hyps = [int(n_hyp)] * P if np.isscalar(n_hyp) else [int(h) for h in n_hyp]
+        if len(hyps) != P:
+            raise ValueError("n_hyp must be an int or one value per pair")
+    elif len(idx_list) != P:
         raise ValueError("pts_list and idx_list must have the same length")
     pts = [_f64(p).reshape(-1, 4) for p in pts_list]
-    idx = [np.ascontiguousarray(i, dtype=np.int32).reshape(-1, 8) for i in idx_list]
+    idx = [] if seeded else [np.ascontiguousarray(i, dtype=np.int32).reshape(-1, 8) for i in idx_list]
     pair_off = np.zeros(P + 1, dtype=np.int32)
     hyp_off = np.zeros(P + 1, dtype=np.int32)
     for p in range(P):
         pair_off[p + 1] = pair_off[p] + pts[p].shape[0]
-        hyp_off[p + 1] = hyp_off[p] + idx[p].shape[0]
+        hyp_off[p + 1] = hyp_off[p] + (hyps[p] if seeded else idx[p].shape[0])
     # (sample indices are range-checked on the device where they are read: an index outside [0, N_p) makes the library
     #  call fail with ValueError — no host pass over the index arrays)
     Ntot, Htot = int(pair_off[-1]), int(hyp_off[-1])
     pts_all = _concat_into("f_pts", pts, (4,), np.float64)
-    idx_all = _consecutive(idx)
-    if idx_all is None:
-        idx_all = _concat_into("f_idx", idx, (8,), np.int32)
+    idx_all = None
+    if not seeded:
+        idx_all = _consecutive(idx)
+        if idx_all is None:
+            idx_all = _concat_into("f_idx", idx, (8,), np.int32)
     best_idx = np.full(P, -1, dtype=np.int32)
     best_count = np.zeros(P, dtype=np.int32)
     best_F = np.full((P, 3, 3), np.nan)
@@ -125,11 +141,11 @@ def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TI
     counts = np.zeros(Htot, dtype=np.int32) if want_counts else None
     F_all = np.zeros((Htot, 3, 3)) if want_F_all else None
     flags = np.zeros(Htot, dtype=np.uint8) if want_flags else None
-    cabi.check(lib.rg_f_ransac_host(
+    cabi.check(lib.rg_f_ransac_host2(
         _vp(ctx), _vp(stream), P, _vp(cabi.ptr(pts_all)), pair_off.ctypes.data_as(C.POINTER(C.c_int32)),
         _vp(cabi.ptr(idx_all)), hyp_off.ctypes.data_as(C.POINTER(C.c_int32)), float(thr), int(mode), int(tie_mode),
-        int(solver), int(score_path), _vp(cabi.ptr(best_idx)), _vp(cabi.ptr(best_count)), _vp(cabi.ptr(best_F)),
-        _vp(cabi.ptr(mask)), _vp(cabi.ptr(counts)), _vp(cabi.ptr(F_all)), _vp(cabi.ptr(flags))))
+        int(solver), int(score_path), int(sample_seed), int(first_pair), _vp(cabi.ptr(best_idx)), _vp(cabi.ptr(best_count)),
+        _vp(cabi.ptr(best_F)), _vp(cabi.ptr(mask)), _vp(cabi.ptr(counts)), _vp(cabi.ptr(F_all)), _vp(cabi.ptr(flags))))
     out = {"best_idx": best_idx, "best_count": best_count, "F": best_F, "pair_off": pair_off, "hyp_off": hyp_off}
     split_n = lambda a: [a[pair_off[p]:pair_off[p + 1]] for p in range(P)]
     split_h = lambda a: [a[hyp_off[p]:hyp_off[p + 1]] for p in range(P)]

@@ -38,16 +38,28 @@ def fast(n_points: int, n_hyp: int, k: int = 8, seed: int | None = 0) -> np.ndar
     return out.astype(np.int32)
 
 
-def fast_batch(n_points_list, n_hyp: int, k: int = 8, seed: int = 0, pinned: bool = True) -> list:
+_PINNED: dict = {}
+
+
+def fast_batch(n_points_list, n_hyp: int, k: int = 8, seed: int = 0, pinned: bool = False, device=None) -> list:
     """``fast(n_p, n_hyp, k, seed + p)`` for every pair / view p, drawn into ONE contiguous (sum H, k) int32 array and
     returned as the list of its row blocks: the batched entry points recognise consecutive blocks and hand the parent array
     to the library without concatenating (for the Dino sequence the 11 MB copy was two thirds of the host call).
-    pinned: allocate that array in page-locked memory when a CUDA device is present (faster upload, same values)."""
+    pinned=True: draw into a page-locked buffer that is CACHED per (thread, size) and reused by the next call of the same
+    shape (cudaMallocHost / cudaFreeHost cost milliseconds and synchronise the device, so a fresh buffer per call would be a
+    net loss; the returned blocks are only valid until the next pinned call of that shape from the same thread).
+    Callers that do not need host-visible samples should let the library draw them on the device instead
+    (runtime.f_ransac_batched(idx_list=None, n_hyp=..., sample_seed=...))."""
     n_points_list = [int(n) for n in n_points_list]
     shape = (len(n_points_list) * int(n_hyp), k)
     if pinned:
+        import threading
         from . import _cabi
-        parent = _cabi.pinned_empty(shape, np.int32)
+        key = (threading.get_ident(), shape, device)
+        parent = _PINNED.get(key)
+        if parent is None:
+            parent = _cabi.pinned_empty(shape, np.int32, device=device)
+            _PINNED[key] = parent
     else:
         parent = np.empty(shape, dtype=np.int32)
     out = []
