@@ -53,7 +53,7 @@ def main() -> None:
     assert np.array_equal(tracks_i / 100.0, tracks), "points.txt is not exactly 2-decimal"
     Fmatrix = np.load(os.path.join(ref, "Fmatrix.npy"), allow_pickle=True)
     clean_eval = np.load(os.path.join(ref, "clean_data_eval.npy"), allow_pickle=True)
-    np.savez_compressed(os.path.join(OUT, "dino_data.npz"), Ps=Ps, x2d=x2d, X3d=X3d, tracks_x100=tracks_i,
+    np.savez_compressed(os.path.join(ROOT, "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"), Ps=Ps, x2d=x2d, X3d=X3d, tracks_x100=tracks_i,
                         Fmatrix=Fmatrix, clean_data_eval=clean_eval)
 
     g = {}

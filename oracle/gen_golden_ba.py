@@ -51,7 +51,7 @@ def reference_tables(tables, hc, cams, pts, uv, cam_idx, pt_idx):
 
 def main() -> None:
     tables, fun, hc = ri.import_reference("tables", "fun", "help_classes")
-    d = np.load(os.path.join(OUT, "dino_data.npz"))
+    d = np.load(os.path.join(os.path.dirname(OUT), "..", "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"))
     out = {}
     real = tables.least_squares
     for nv in (3, 8, 36):

@@ -39,7 +39,8 @@ def _load(name):
 
 @pytest.fixture(scope="session")
 def dino():
-    d = _load("dino_data.npz")
+    with np.load(os.path.join(ROOT, "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz")) as z:
+        d = {k: z[k] for k in z.files}
     d["tracks"] = d.pop("tracks_x100").astype(np.float64) / 100.0
     return d
 

@@ -6,7 +6,7 @@ import torch
 import tsbb15_b200 as rg
 from tsbb15_b200 import _cabi as cabi
 lib = cabi.load_library(); ctx = cabi.context(0)
-d = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "dino_data.npz"))
+d = np.load(os.path.join(os.path.dirname(__file__), "..", "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"))
 Ps = d["Ps"]
 rng = np.random.default_rng(0)
 out = {}

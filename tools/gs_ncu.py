@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import tsbb15_b200 as rg  # noqa: E402
 from oracle import geom_path as og  # noqa: E402
 
-d = np.load(os.path.join(ROOT, "tests", "golden", "dino_data.npz"))
+d = np.load(os.path.join(ROOT, "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"))
 Ps = d["Ps"]
 rng = np.random.default_rng(0)
 P, N = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 50000)

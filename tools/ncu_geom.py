@@ -6,7 +6,7 @@ import torch
 from tsbb15_b200 import _cabi as cabi
 lib = cabi.load_library(); ctx = cabi.context(0)
 vp = C.c_void_p
-d = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "dino_data.npz"))
+d = np.load(os.path.join(os.path.dirname(__file__), "..", "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"))
 Ps = d["Ps"]
 rng = np.random.default_rng(0)
 N = 1_000_000

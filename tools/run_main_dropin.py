@@ -22,7 +22,7 @@ def run(last_view=34, bundle_adjust=True, r_f=10000, verbose=True):
     import tsbb15_b200 as rg
     fun = rg.fun
     Tables, CameraPose = rg.tables.Tables, rg.help_classes.CameraPose
-    d = np.load(os.path.join(ROOT, "tests", "golden", "dino_data.npz"))
+    d = np.load(os.path.join(ROOT, "tsbb15-3d-reconstruction-project_b200", "data", "dino_data.npz"))
     x2d, Ps = d["x2d"], d["Ps"]
     pnp_kw = dict(r=256, reproj_px=1.5)
 

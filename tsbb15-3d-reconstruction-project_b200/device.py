@@ -162,16 +162,32 @@ class P2PExchange:
         self.ctx = cabi.context(self.dev.index)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # every step below is followed by a collective that ALL ranks reach even when a local CUDA call failed, so that a
+        # rank whose IPC mapping is refused (containers without shared IPC namespaces) makes everybody raise, not hang
         h = (C.c_char * 64)()
-        cabi.check(self.lib.rg_p2p_create(_vp(self.ctx), self.rank, self.world, h))
-        handles = [bytes(h.raw)]
+        err = None
+        try:
+            cabi.check(self.lib.rg_p2p_create(_vp(self.ctx), self.rank, self.world, h))
+        except Exception as e:           # noqa: BLE001 - reported to every rank below
+            err = repr(e)
+        mine = (err, bytes(h.raw))
+        got = [mine]
         if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(h.raw), group=group)
-        blob = b"".join(handles)
-        cabi.check(self.lib.rg_p2p_connect(_vp(self.ctx), blob))
+            got = [None] * self.world
+            dist.all_gather_object(got, mine, group=group)
+        if err is None and all(g[0] is None for g in got):
+            try:
+                cabi.check(self.lib.rg_p2p_connect(_vp(self.ctx), b"".join(g[1] for g in got)))
+            except Exception as e:       # noqa: BLE001
+                err = repr(e)
+        errs = [err]
         if self.world > 1:
-            dist.barrier(group=group)                  # every peer has mapped every buffer before the first exchange
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)          # also the barrier: every peer mapped every buffer
+        bad = [(r, e) for r, e in enumerate(errs) if e is not None] + [(r, g[0]) for r, g in enumerate(got) if g[0] is not None]
+        if bad:
+            self.lib.rg_p2p_destroy(_vp(self.ctx))
+            raise cabi.RGError(f"peer-memory exchange unavailable (rank {bad[0][0]}: {bad[0][1]})")
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     def argmax(self, key, payload, best_idx, best_count, payload_out):

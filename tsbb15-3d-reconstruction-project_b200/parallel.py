@@ -385,6 +385,43 @@ class PairShardedRansac:
                              first_pair=self.lo, **kw)
         return self.out
 
+    # ---- the same through the HOST-buffer entry point (end-to-end: uploads and result downloads inside the call)
+    def alloc_host(self, want_mask: bool = True):
+        """Page-locked host buffers for the local shard: inputs (P, N, 4) f64 and the per-pair results."""
+        import torch
+        self.h_pts = torch.empty((max(self.P, 1), self.N, 4), dtype=torch.float64, pin_memory=True)
+        self.h_block = torch.zeros(self.per * 80, dtype=torch.uint8, pin_memory=True)
+        self.h_F = self.h_block[: self.per * 72].view(torch.float64).view(self.per, 9)
+        self.h_best_idx = self.h_block[self.per * 72: self.per * 76].view(torch.int32)
+        self.h_best_count = self.h_block[self.per * 76:].view(torch.int32)
+        self.h_mask = torch.empty(max(self.P * self.N, 1), dtype=torch.uint8, pin_memory=True) if want_mask else None
+        self.h_all_block = torch.empty(self.world * self.per * 80, dtype=torch.uint8, pin_memory=True) if self.world > 1 else None
+        return self.h_pts
+
+    def run_host(self, thr=1.5, sample_seed: int = 0, mode=0, tie_mode=0, solver=0, score_path=0, h_idx=None):
+        """rg_f_ransac_host2 on the local shard (synchronous: returns when the shard's results are in host memory), then the
+        all-gather of the 80-byte results of all ranks (H2D of the local block, NCCL, D2H of everything)."""
+        import ctypes as C
+        from . import _cabi as cabi
+        lib = cabi.load_library()
+        pi32 = C.POINTER(C.c_int32)
+        st = self.dv._stream()
+        if self.P:
+            cabi.check(lib.rg_f_ransac_host2(
+                _vp(cabi.context(self.dev.index)), _vp(st), self.P, _vp(self.h_pts.data_ptr()), self.pair_off.ctypes.data_as(pi32),
+                _vp(h_idx.data_ptr()) if h_idx is not None else None, self.hyp_off.ctypes.data_as(pi32), float(thr), int(mode),
+                int(tie_mode), int(solver), int(score_path), int(sample_seed), int(self.lo), _vp(self.h_best_idx.data_ptr()),
+                _vp(self.h_best_count.data_ptr()), _vp(self.h_F.data_ptr()),
+                _vp(self.h_mask.data_ptr()) if self.h_mask is not None else None, None, None, None))
+        if self.world == 1:
+            return self.h_block
+        self.block.copy_(self.h_block, non_blocking=True)
+        _dist().all_gather_into_tensor(self.all_block, self.block, group=self.group)
+        self.h_all_block.copy_(self.all_block, non_blocking=True)
+        import torch
+        torch.cuda.current_stream().synchronize()
+        return self.h_all_block
+
     def gather(self, masks: bool = True) -> dict:
         """All ranks receive the results of all pairs (device tensors; one NCCL all-gather of 80 B per pair, one of N bytes
         per pair for the masks)."""

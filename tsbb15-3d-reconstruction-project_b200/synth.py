@@ -1,5 +1,5 @@
 """Synthetic correspondences of the shapes BASELINE.json names, plus access to the
-Dino fixtures (tests/golden/dino_data.npz, exported from the reference's BAdino2.mat / imgdata/points.txt by
+Dino fixtures (data/dino_data.npz inside the package: INPUT data, not an oracle artefact — exported from the reference's BAdino2.mat / imgdata/points.txt by
 oracle/gen_golden.py).  Pure numpy host code; nothing here is on the hot path.
 """
 from __future__ import annotations
@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DINO_FIXTURE = os.path.join(_ROOT, "tests", "golden", "dino_data.npz")
+DINO_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "dino_data.npz")
 
 # bounding box of the Dino model in world units
 DINO_BBOX = np.array([[-0.045, 0.045], [-0.08, 0.03], [-0.72, -0.54]])
