@@ -486,6 +486,16 @@ def run_split(args, rg, parallel, torch, dist, dev, rank, world) -> dict:
             r = sp.result()
             res[mode] = {"ms": ms, "evals_per_s": float(N3) * H3 / (ms * 1e-3), "winner": r["best_idx"],
                          "count": r["best_count"], "owner_rank": r["owner"], "mask_inliers": int(r["mask"].sum())}
+            if mode in ("p2p", "none"):                 # the same chain replayed as ONE CUDA graph launch
+                try:
+                    sp.capture(thr=1.5, want_mask=True)
+                    msg = ev(sp.replay, 20)
+                    rg_ = sp.result()
+                    res[mode + "_cuda_graph"] = {"ms": msg, "evals_per_s": float(N3) * H3 / (msg * 1e-3),
+                                                 "winner": rg_["best_idx"], "count": rg_["best_count"],
+                                                 "owner_rank": rg_["owner"], "mask_inliers": int(rg_["mask"].sum())}
+                except Exception as e:
+                    res[mode + "_cuda_graph"] = {"error": repr(e)[:200]}
             if sp.p2p is not None:
                 sp.p2p.close()
         best = min((v for v in res.values() if "ms" in v), key=lambda v: v["ms"], default=None)

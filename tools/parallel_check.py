@@ -70,11 +70,58 @@ def main():
     ok4 = (np.array_equal(vsh["best_idx"], vref["best_idx"]) and np.array_equal(vsh["best_count"], vref["best_count"])
            and np.array_equal(vsh["R"], vref["R"], equal_nan=True))
     ok2 = ok2 and ok3 and ok4
+    # ---- device-resident decompositions (round 2): pair-sharded sweep with gather, hypothesis split with the peer-memory
+    # exchange kernel and with NCCL, F and PnP — each against a single-GPU run of the whole problem
+    from tsbb15_b200 import device as dv
+    detail = {}
+    Pn, Nn, Hn = 11, 4000, 1024
+    sh = parallel.PairShardedRansac(Pn, Nn, Hn, device=local, want_mask=True)
+    sh.generate(seed_base=1000)
+    sh.run(thr=1.5, sample_seed=77)
+    got = sh.unpack(sh.gather(masks=True))
+    full, _ = dv.synth_two_view(Pn, Nn, first_pair=0, seed_base=1000, device=local)
+    o = dv.FOutputs(Pn, Pn * Nn, device=local, want_mask=True)
+    dv.f_ransac(full, dv.offsets(np.full(Pn, Nn)), None, dv.offsets(np.full(Pn, Hn)), o, seed=77)
+    ok5 = (np.array_equal(got["best_idx"], o.best_idx.cpu().numpy()) and np.array_equal(got["best_count"], o.best_count.cpu().numpy())
+           and np.array_equal(got["F"].reshape(Pn, 9), o.F.cpu().numpy())
+           and np.array_equal(np.concatenate(got["mask"]), o.mask.cpu().numpy()))
+    sh.alloc_host()
+    sh.h_pts[: sh.P].copy_(sh.d_pts)
+    hb = sh.run_host(thr=1.5, sample_seed=77).numpy().copy()
+    ok5 = ok5 and np.array_equal(hb, sh.gather(masks=False)["block"].cpu().numpy())
+    detail["pair_sharded_device"] = bool(ok5)
+    d1, _ = dv.synth_two_view(1, 30000, first_pair=0, seed_base=3000, device=local)
+    o1 = dv.FOutputs(1, 30000, device=local, want_mask=True)
+    dv.f_ransac(d1, dv.offsets([30000]), None, dv.offsets([4099]), o1, seed=5)
+    ok6 = True
+    for mode in ("p2p", "nccl"):
+        sp = parallel.SplitHypothesesF(d1[0], 4099, exchange=mode, sample_seed=5)
+        for _ in range(3):                              # repeated calls: sequence numbers / double buffering / prepared points
+            sp.run(thr=1.5, want_mask=True)
+        r = sp.result()
+        good = (r["best_idx"] == int(o1.best_idx.item()) and r["best_count"] == int(o1.best_count.item())
+                and np.array_equal(r["F"].reshape(9), o1.F.cpu().numpy().reshape(9)) and np.array_equal(r["mask"], o1.mask.cpu().numpy()))
+        detail["split_f_" + mode] = bool(good)
+        ok6 = ok6 and good
+        if sp.p2p is not None:
+            sp.p2p.close()
+    dXp, dyp = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    for mode in ("p2p", "nccl"):
+        spp = parallel.SplitHypothesesPnp(dXp, dyp, pidx, n=6, exchange=mode)
+        spp.run(thr2); spp.run(thr2)
+        r = spp.result()
+        good = (r["best_idx"] == pone["best_idx"] and r["best_count"] == pone["best_count"] and np.array_equal(r["R"], pone["R"])
+                and np.array_equal(r["t"], pone["t"]))
+        detail["split_pnp_" + mode] = bool(good)
+        ok6 = ok6 and good
+        if spp.p2p is not None:
+            spp.p2p.close()
+    ok2 = ok2 and ok5 and ok6
     res = torch.tensor([int(ok1), int(ok2)], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "pairs_sharded_ok": bool(res[0].item()), "hyp_split_ok": bool(res[1].item()),
-                          "c_abi_allreduce_ok": bool(ok_c), "split_owner": split["owner"], "best": split["best_idx"], "count": split["best_count"]}))
+                          "c_abi_allreduce_ok": bool(ok_c), "device_paths": detail, "split_owner": split["owner"], "best": split["best_idx"], "count": split["best_count"]}))
     dist.destroy_process_group()
     sys.exit(0 if int(res.min().item()) == 1 else 1)
 

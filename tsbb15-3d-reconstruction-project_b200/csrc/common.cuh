@@ -156,6 +156,14 @@ struct PairFrame {
     double thr, B;
 };
 
+struct FPlan {
+    int P = 0;
+    long long Ntot = 0, Htot = 0, N32tot = 0;
+    int n_items = 0;
+    int maxN = 0, maxH = 0;
+    double evals = 0.0;                  // sum_p n_p * H_p
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 0;
@@ -197,6 +205,8 @@ struct Ctx {
     Buffer h_stage[2], h_stats;                    // PairInfo staging, double buffered: the host plans pass k+1 while pass k runs
     cudaEvent_t staging_free[2] = {nullptr, nullptr};   // recorded after the H2D that reads h_stage[i]
     int stage_turn = 0;
+    // the table of the last planned pass is still on the device: a repeated call skips staging and upload (plan.cuh)
+    FPlan plan_cached; unsigned long long plan_hash = 0; const void* plan_table = nullptr; bool plan_valid = false;
     // host-buffer entry points: inputs are uploaded on a second stream in sub-batches so that the copy of sub-batch
     // k+1 overlaps the kernels of sub-batch k
     static constexpr int kMaxSlices = 8;

@@ -1,7 +1,7 @@
 // Host orchestration + C ABI of the F-matrix RANSAC path.  See include/rg_b200.h for the contract of each entry point.
 //
 // One call = one or more PASSES.  A pass is the launch chain
-//   memset(state) -> [sample_indices] -> [f_bbox -> f_normalise] -> f8_solve -> score_packed -> fixup_list -> argmax_counts
+//   memset(state) -> [f_bbox -> f_normalise] -> f8_solve (draws its own samples when idx is NULL) -> score_packed -> fixup_list -> argmax_counts
 //   -> [f_tie_stats -> f_tie_resolve] -> f_mask
 // over a contiguous block of pairs whose workspaces (hypotheses, FP32 points, flag list) stay bounded; BASELINE config 5
 // (4096 pairs x 50 000 x 8 192) runs as 64 passes of 64 pairs.  The per-pass PairInfo table is planned on the host into
@@ -85,7 +85,7 @@ static int f_workspace(Ctx* c, const FPlan& plan, bool seeded) {
     if ((rc = ensure(c->tie_stats, sizeof(double2) * H))) return rc;
     if ((rc = ensure(c->pair_frame, sizeof(PairFrame) * (size_t)std::max(plan.P, 1)))) return rc;
     if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
-    if (seeded && (rc = ensure(c->gen_idx, sizeof(int) * 8 * H))) return rc;
+    (void)seeded;
     return RG_OK;
 }
 
@@ -105,19 +105,20 @@ static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreStat
 }
 
 template <int MODE>
-static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, const int* idx, int solver) {
+static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const double* pts64, const int* idx, int solver,
+                          unsigned long long seed = 0, unsigned first_pair = 0) {
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     const PairFrame* fr = (const PairFrame*)c->pair_frame.ptr;
     if (plan.Htot == 0) return RG_OK;
     if (solver == SOLVER_QR) {
-        f8_solve_qr<MODE><<<ceil_div(plan.Htot, 128), 128, 0, st>>>((const double4*)pts64, idx, pi, fr, plan.P, (int)plan.Htot,
-                                                                  (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
+        f8_solve_qr<MODE><<<ceil_div(plan.Htot, 128), 128, 0, st>>>((const double4*)pts64, idx, seed, first_pair, pi, fr, plan.P,
+                                                                  (int)plan.Htot, (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
                                                                   (unsigned char*)c->flags.ptr);
     } else {
         const int groups_per_block = kJacobiThreads / 16;
         f8_solve_jacobi<MODE><<<ceil_div(plan.Htot, groups_per_block), kJacobiThreads, 0, st>>>(
-            (const double4*)pts64, idx, pi, fr, plan.P, (int)plan.Htot, (double*)c->F64.ptr, (Hyp32*)c->hyp32.ptr,
-            (unsigned char*)c->flags.ptr);
+            (const double4*)pts64, idx, seed, first_pair, pi, fr, plan.P, (int)plan.Htot, (double*)c->F64.ptr,
+            (Hyp32*)c->hyp32.ptr, (unsigned char*)c->flags.ptr);
     }
     c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
@@ -166,6 +167,14 @@ static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Sco
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     int2* best = (int2*)c->best.ptr;
     const bool tie = tie_mode == TIE_REFERENCE && plan.Htot > 0;
+    if (!tie && mask == nullptr) {                    // nothing follows the argmax: it publishes the winners itself
+        argmax_counts<<<plan.P, 256, 0, st>>>(s.counts, pi, best, (const unsigned char*)c->flags.ptr,
+                                              (unsigned long long*)c->stats.ptr, keys, (const double*)c->F64.ptr, 9, best_F,
+                                              best_idx, best_count);
+        c->last_stats[7] += 1;
+        RG_CUDA(cudaGetLastError());
+        return RG_OK;
+    }
     argmax_counts<<<plan.P, 256, 0, st>>>(s.counts, pi, best, (const unsigned char*)c->flags.ptr,
                                           (unsigned long long*)c->stats.ptr, tie ? nullptr : keys);
     c->last_stats[7] += 1;
@@ -212,21 +221,16 @@ static int f_pass(Ctx* c, cudaStream_t st, const FCall& a) {
     // one memset clears the pass's state (the bounding boxes only when the points are prepared in this pass)
     const size_t from = reuse ? s.off_counts : 0;
     RG_CUDA(cudaMemsetAsync((char*)c->state.ptr + from, 0, s.bytes - from, st));
-    const int* idx = a.idx;
-    if (seeded) {
-        sample_indices_kernel<8><<<ceil_div(plan.Htot, 256), 256, 0, st>>>(pi, a.P, (int)plan.Htot, a.sample_seed,
-                                                                            (unsigned)a.first_pair, (int*)c->gen_idx.ptr);
-        c->last_stats[7] += 1;
-        idx = (const int*)c->gen_idx.ptr;
-    }
+    const int* idx = a.idx;                           // NULL: the solver draws its own sample (philox.cuh), no index array exists
     if (!reuse) {
         c->prep_pts = nullptr;
         if ((rc = f_prepare(c, st, plan, s, a.pts64, a.thr))) return rc;
         c->prep_pts = a.pts64; c->prep_P = a.P; c->prep_N = plan.Ntot; c->prep_thr = a.thr; c->prep_hash = hsh;
     }
     prof_mark(c, st, 1);
-    rc = (a.mode == MODE_SAMPSON) ? f_solve_launch<MODE_SAMPSON>(c, st, plan, a.pts64, idx, a.solver)
-                                  : f_solve_launch<MODE_EPI_MAX>(c, st, plan, a.pts64, idx, a.solver);
+    rc = (a.mode == MODE_SAMPSON)
+             ? f_solve_launch<MODE_SAMPSON>(c, st, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair)
+             : f_solve_launch<MODE_EPI_MAX>(c, st, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair);
     if (rc) return rc;
     prof_mark(c, st, 2);
     rc = (a.mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, a.pts64, a.thr, a.score_path)

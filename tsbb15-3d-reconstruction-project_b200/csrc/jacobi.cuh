@@ -114,6 +114,7 @@ struct GroupJacobi {
 // one-sided Jacobi above; the null vector is V[:, argmin sigma]).
 template <int MODE>
 __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4* __restrict__ pts, const int* __restrict__ idx,
+                                                                   unsigned long long seed, unsigned first_pair,
                                                                    const PairInfo* __restrict__ pi,
                                                                    const PairFrame* __restrict__ frames, int P, int Htot,
                                                                    double* __restrict__ F64, Hyp32* __restrict__ hyp32,
@@ -131,9 +132,15 @@ __global__ void __launch_bounds__(kJacobiThreads) f8_solve_jacobi(const double4*
     double X[8], Y[8], x[8], y[8];
     bool bad_index = false;
     {
-        const int4 i0 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2];
-        const int4 i1 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2 + 1];
-        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        int id[8];
+        if (idx != nullptr) {
+            const int4 i0 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2];
+            const int4 i1 = reinterpret_cast<const int4*>(idx)[(size_t)h * 2 + 1];
+            id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w; id[4] = i1.x; id[5] = i1.y; id[6] = i1.z; id[7] = i1.w;
+        } else {      // seeded call: the sample is a pure function of (seed, global pair id, hypothesis index) — philox.cuh
+            sample_distinct<8>(seed, first_pair + (unsigned)lo, (unsigned)(info.hyp_first + (h - info.hyp_off)),
+                               (unsigned)max(info.n, 8), id);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             int q = id[k];

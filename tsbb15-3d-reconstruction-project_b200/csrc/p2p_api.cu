@@ -28,6 +28,8 @@ struct __align__(16) P2PSlot {
 struct P2PBuf {
     P2PSlot slots[2][kP2PMaxWorld][kP2PMaxPairs];
     unsigned flag[kP2PMaxWorld * 32];               // one 128-byte line per source rank
+    unsigned seq;                                   // calls made by THIS rank (only its own kernel touches it): the sequence
+                                                    // number lives on the device so that the exchange can sit in a CUDA graph
 };
 struct P2PPeers { P2PBuf* p[kP2PMaxWorld]; };
 
@@ -40,11 +42,15 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) p2p_argmax_kernel(P2PBuf* local, P2PPeers peers, int rank, int world, unsigned seq, int P,
+__global__ void __launch_bounds__(256) p2p_argmax_kernel(P2PBuf* local, P2PPeers peers, int rank, int world, int P,
                                                           const unsigned long long* __restrict__ key,
                                                           const double* __restrict__ payload, int npay,
                                                           int* __restrict__ best_idx, int* __restrict__ best_count,
                                                           double* __restrict__ payload_out, int* __restrict__ status) {
+    __shared__ unsigned s_seq;
+    if (threadIdx.x == 0) { s_seq = local->seq + 1u; local->seq = s_seq; }
+    __syncthreads();
+    const unsigned seq = s_seq;
     const int par = (int)(seq & 1u);
     for (int t = threadIdx.x; t < world * P; t += blockDim.x) {
         const int r = t / P, p = t - r * P;
@@ -157,8 +163,7 @@ int rg_p2p_argmax_exchange(void* ctx, void* stream, int P, const unsigned long l
     RG_CUDA(cudaSetDevice(c->device));
     P2PPeers peers;
     for (int r = 0; r < kP2PMaxWorld; ++r) peers.p[r] = (P2PBuf*)c->p2p_peer[r];
-    const unsigned seq = ++c->p2p_seq;
-    p2p_argmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((P2PBuf*)c->p2p_local, peers, c->p2p_rank, c->p2p_world, seq, P, key_dev,
+    p2p_argmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((P2PBuf*)c->p2p_local, peers, c->p2p_rank, c->p2p_world, P, key_dev,
                                                            payload_dev, npay, best_idx_dev, best_count_dev, payload_out_dev,
                                                            status_dev);
     RG_CUDA(cudaGetLastError());

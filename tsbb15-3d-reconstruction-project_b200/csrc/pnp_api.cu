@@ -151,11 +151,17 @@ static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const
     prof_mark(c, st, 4);
     int2* best = (int2*)c->best.ptr;
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
-    argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys);
-    const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
-    pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
-                                            best_count);
-    c->last_stats[7] += 2;
+    if (mask == nullptr) {                            // nothing follows the argmax: it publishes the winning poses itself
+        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys,
+                                         (const double*)c->pose64.ptr, 12, Rt, best_idx, best_count);
+        c->last_stats[7] += 1;
+    } else {
+        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys);
+        const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
+        pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
+                                                best_count);
+        c->last_stats[7] += 2;
+    }
     prof_mark(c, st, 5);
     RG_CUDA(cudaGetLastError());
     RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));

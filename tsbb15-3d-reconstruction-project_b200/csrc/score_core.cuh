@@ -364,13 +364,19 @@ __global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, Flag
 
 // best[p] = {index inside the pair of the first hypothesis with the largest count (-1 if that count is 0), count}
 // flags / stats (optional): hypotheses whose flag byte has bit 2 set (sample index out of range) are counted in stats[4]
+// model / best_model / best_idx / best_count (optional): also publish the winner (its F or R|t, model_len doubles per
+// hypothesis) — saves the separate finish kernel when no inlier mask is wanted (hypothesis-split mode)
 // keys (optional): the cross-GPU argmax key of the pair, (count << 32) | (0xFFFFFFFF - (hyp_first + index)), 0 when no
 // hypothesis of this rank has an inlier — what rg_argmax_pack_dev computed with a separate launch in round 1
 __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ counts, const PairInfo* __restrict__ pi,
                                                       int2* __restrict__ best, const unsigned char* __restrict__ flags,
                                                       unsigned long long* __restrict__ stats,
-                                                      unsigned long long* __restrict__ keys) {
+                                                      unsigned long long* __restrict__ keys,
+                                                      const double* __restrict__ model = nullptr, int model_len = 0,
+                                                      double* __restrict__ best_model = nullptr,
+                                                      int* __restrict__ best_idx = nullptr, int* __restrict__ best_count = nullptr) {
     __shared__ unsigned long long sk[8];
+    __shared__ int s_win;
     const int p = blockIdx.x;
     const PairInfo info = pi[p];
     unsigned long long key = 0ull;
@@ -398,6 +404,15 @@ __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ cou
             keys[p] = idx >= 0 ? (((unsigned long long)(unsigned)cnt << 32) |
                                   (unsigned long long)(0xFFFFFFFFu - (unsigned)(info.hyp_first + idx)))
                                : 0ull;
+        if (best_idx != nullptr) { best_idx[p] = idx; best_count[p] = cnt; }
+        s_win = idx;
+    }
+    if (best_model != nullptr) {
+        __syncthreads();
+        const int w = s_win;
+        if ((int)threadIdx.x < model_len)
+            best_model[(size_t)p * model_len + threadIdx.x] =
+                w >= 0 ? model[(size_t)(info.hyp_off + w) * model_len + threadIdx.x] : __longlong_as_double(0x7FF8000000000000ll);
     }
 }
 

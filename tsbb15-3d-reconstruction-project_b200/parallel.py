@@ -533,6 +533,27 @@ class SplitHypothesesF:
             dv.f_inlier_mask(self.d_pts, self.pair_off, self.g_F, thr=thr, mode=mode, out=self.mask)
         return self
 
+    def capture(self, thr=1.5, mode=0, want_mask: bool = True, **kw):
+        """Capture run()'s launch chain in a CUDA graph.  Once the points are prepared and the plan is cached the chain is
+        memset -> solve -> score -> fix-up -> argmax -> exchange kernel -> mask kernel with no host synchronisation, so it
+        can be replayed with one launch (``replay``).  Collective: every rank captures and replays the same number of times.
+        Not available with exchange="nccl" (the NCCL collectives are issued by torch)."""
+        import torch
+        if self.exchange not in ("none", "p2p"):
+            raise ValueError("graph capture needs exchange='p2p' (or a single rank)")
+        for _ in range(2):                                   # prepared points, cached plan, workspaces at their final size
+            self.run(thr=thr, mode=mode, want_mask=want_mask, **kw)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(thr=thr, mode=mode, want_mask=want_mask, **kw)
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
+        return self
+
     def result(self) -> dict:
         if self.p2p is not None:
             self.p2p.check()
