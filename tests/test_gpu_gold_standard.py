@@ -67,7 +67,7 @@ def test_gold_standard_batched_with_masks_and_edge_cases(rt, rg, dino):
         pts = np.hstack([y1[ok], y2[ok]]) + rng.normal(0, 0.3, (ok.sum(), 4))
         pts[::6, 2:] = rng.uniform(0, 600, (len(pts[::6]), 2))
         pairs.append(pts)
-    fr = rg.batched.f_ransac_pairs(pairs, n_hyp=3000, thr=1.5, seed=2)
+    fr = rg.batched.f_ransac_pairs(pairs, n_hyp=3000, thr=1.5, seed=2, host_sampling=True)
     batch = pairs + [np.zeros((0, 4)), pairs[0]]
     F0 = np.concatenate([fr["F"], fr["F"][:1], np.full((1, 3, 3), np.nan)])
     masks = list(fr["mask"]) + [np.zeros(0, np.uint8), fr["mask"][0]]

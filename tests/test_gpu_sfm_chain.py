@@ -208,7 +208,7 @@ def test_ransac_then_two_view_init_with_masks(rg, dino, pnp_golden):
         pts = np.hstack([a, b]) + rng.normal(0, 0.2, (len(a), 4))
         pts[::5, 2:] = rng.uniform(0, 600, (len(pts[::5]), 2))            # 20 % gross outliers
         pairs.append(pts)
-    fr = rg.batched.f_ransac_pairs(pairs, n_hyp=2000, thr=1.5, seed=1)
+    fr = rg.batched.f_ransac_pairs(pairs, n_hyp=2000, thr=1.5, seed=1, host_sampling=True)
     res = rg.batched.two_view_init(pairs, fr["F"], K, masks=fr["mask"])
     Kinv = np.linalg.inv(K)
     for p, pts in enumerate(pairs):

@@ -46,6 +46,14 @@ int score_state_layout(Ctx* c, int P, long long Htot, int bbox_words, ScoreState
     return RG_OK;
 }
 
+// blocks of the fix-up kernel: one full wave for big passes, a few blocks for small ones (a pass of 2048 hypotheses x
+// 100 000 correspondences flags ~90 000 groups: 4736 mostly idle warps cost more to launch and to retire than the work)
+int fixup_grid(const Ctx* c, double evals) {
+    const double expected_records = evals * 6.0e-4;              // measured 4.5e-4 flagged groups per evaluation
+    const long long want = (long long)(expected_records / 256.0) + 1;     // ~one record per thread
+    return (int)std::max<long long>(8, std::min<long long>(want, (long long)c->sm_count * 4));
+}
+
 FlagList flag_list_for(Ctx* c, const ScoreState& s, double evals, int* rc_out) {
     FlagList L{nullptr, s.list_n, 0u, s.ovf};
     double want = evals / 512.0 + 65536.0;            // ~4.3x the measured 4.5e-4 records per evaluation
@@ -147,7 +155,7 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Scor
         prof_mark(c, st, 3);
         typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
                                          (const double*)c->F64.ptr, pi, (const PairFrame*)c->pair_frame.ptr, plan.P};
-        fixup_list<EpiFix<MODE>><<<c->sm_count * 4, 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
+        fixup_list<EpiFix<MODE>><<<fixup_grid(c, plan.evals), 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
         c->last_stats[7] += 2;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));

@@ -251,6 +251,49 @@ __global__ void __launch_bounds__(256) f_make_hyp32(const double* __restrict__ F
 }
 
 // ------------------------------------------------------------------------------------------------
+// fast reciprocal / reciprocal square root / rotation helpers of the one-thread-per-hypothesis solvers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_approx(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+// 1/sqrt(x) to full double precision from the 20-bit hardware seed (MUFU.RSQ64H) + two Newton steps: ~10 dependent
+// instructions instead of the ~60 of sqrt() followed by a division.  x > 0, normal range.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+// 1/x to full double precision: 20-bit seed (MUFU.RCP64H) + two Newton steps.  x finite, normal, non-zero.
+__device__ __forceinline__ double rcp_nr(double x) {
+    double y = rcp_approx(x);
+    y = y * fma(-x, y, 2.0);
+    y = y * fma(-x, y, 2.0);
+    return y;
+}
+// Jacobi rotation for the thread-per-hypothesis solvers.  Any rotation with c^2 + s^2 = 1 (to rounding) keeps the
+// iteration an orthogonal transformation, so only c and s = c t have to be exact functions of t; the ANGLE itself only
+// steers convergence and is computed from 20-bit reciprocal / reciprocal-square-root seeds (a 1e-6 relative error in t
+// leaves an off-diagonal of 1e-6 of the old one instead of zero: at most one extra sweep, measured none).  The exact
+// formula (jacobi_rot: two divisions, two square roots) was ~750 dependent cycles of the ~1100 per rotation.
+__device__ __forceinline__ void jacobi_rot_fast(double a, double b, double g, double& c, double& s) {
+    const double zeta = (b - a) * 0.5 * rcp_approx(g);
+    const double w = fma(zeta, zeta, 1.0);
+    double rs;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(w));
+    const double root = w * rs;                                   // ~ sqrt(1 + zeta^2)
+    double t = copysign(rcp_approx(fabs(zeta) + root), zeta);
+    if (!(fabs(t) <= 1.0)) t = 0.0;       // zeta^2 overflowed (needs a column ratio > 1e278, excluded by the `tiny` test): no rotation
+    c = rsqrt_nr(fma(t, t, 1.0));
+    s = c * t;
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // 3x3: right singular vector of the smallest singular value by one-sided Jacobi, then rank-2 projection
 //      Fs <- Fs - (Fs v3) v3^T      (== U diag(s1,s2,0) V^T, lab3.py:321-324)
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +357,81 @@ __device__ __forceinline__ void rank2_project(double* __restrict__ Fs /* row-maj
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) Fs[3 * i + j] -= fv[i] * v3[j];
+}
+
+// rank-2 projection for the thread-per-hypothesis solver: same iteration with approximate-angle rotations (the rotation
+// stays orthogonal to rounding, see jacobi_rot_fast) and a square-root-free convergence test — the exact version's
+// divisions and square roots were a third of f8_solve_qr's dependent chain
+__device__ __forceinline__ void rank2_project_fast(double* __restrict__ Fs /* row-major 3x3, in/out */) {
+    double w[3][3], v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { w[j][i] = Fs[3 * i + j]; v[j][i] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 14; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            const double a = w[p][0] * w[p][0] + w[p][1] * w[p][1] + w[p][2] * w[p][2];
+            const double b = w[q][0] * w[q][0] + w[q][1] * w[q][1] + w[q][2] * w[q][2];
+            const double g = w[p][0] * w[q][0] + w[p][1] * w[q][1] + w[p][2] * w[q][2];
+            if (g * g > 1e-32 * (a * b)) {
+                double c, s;
+                jacobi_rot_fast(a, b, g, c, s);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double wp = w[p][i], wq = w[q][i];
+                    w[p][i] = c * wp - s * wq;
+                    w[q][i] = s * wp + c * wq;
+                    const double vp = v[p][i], vq = v[q][i];
+                    v[p][i] = c * vp - s * vq;
+                    v[q][i] = s * vp + c * vq;
+                }
+                rotated = true;
+            }
+        }
+        if (!rotated) break;
+    }
+    double n0 = w[0][0] * w[0][0] + w[0][1] * w[0][1] + w[0][2] * w[0][2];
+    double n1 = w[1][0] * w[1][0] + w[1][1] * w[1][1] + w[1][2] * w[1][2];
+    double n2 = w[2][0] * w[2][0] + w[2][1] * w[2][1] + w[2][2] * w[2][2];
+    int jm = 0;
+    if (n1 < n0) { jm = 1; n0 = n1; }
+    if (n2 < n0) { jm = 2; }
+    double v3[3], fv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v3[i] = (jm == 0) ? v[0][i] : (jm == 1 ? v[1][i] : v[2][i]);
+    const double nv = rsqrt_nr(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v3[i] *= nv;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fv[i] = Fs[3 * i] * v3[0] + Fs[3 * i + 1] * v3[1] + Fs[3 * i + 2] * v3[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Fs[3 * i + j] -= fv[i] * v3[j];
+}
+
+// Hartley scaling with one reciprocal square root instead of a square root and three divisions (a = 1/L to full precision)
+__device__ __forceinline__ void hartley8_fast(const double* __restrict__ px, const double* __restrict__ py, double& a, double& b,
+                                              double& c) {
+    double mx = 0.0, my = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mx += px[k]; my += py[k]; }
+    mx *= 0.125; my *= 0.125;
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const double dx = px[k] - mx, dy = py[k] - my; ss += dx * dx + dy * dy; }
+    const double q = ss * 0.0625;
+    if (q > 1e-290 && q < 1e290) {
+        a = rsqrt_nr(q);
+    } else {                                  // coincident / non-finite samples: the exact formula's inf / NaN behaviour
+        a = 1.0 / sqrt(q);
+    }
+    b = -mx * a;
+    c = -my * a;
 }
 
 // Hartley scaling of 8 points (lab3.py:288-295): returns a = 1/L, b = -mx/L, c = -my/L
@@ -389,8 +507,8 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
         }
     }
     double a1, b1, c1, a2, b2, c2;
-    hartley8(X, Y, a1, b1, c1);
-    hartley8(x, y, a2, b2, c2);
+    hartley8_fast(X, Y, a1, b1, c1);
+    hartley8_fast(x, y, a2, b2, c2);
 
     // rows of A (== columns of A^T)
     double A[8][9];
@@ -409,16 +527,20 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
         double ss = 0.0;
 #pragma unroll
         for (int i = k; i < 9; ++i) ss += A[k][i] * A[k][i];
-        const double sigma = sqrt(ss);
         const double x0 = A[k][k];
+        double sigma, bk;
+        if (ss > 1e-290 && ss < 1e290) {                        // reciprocal square root + reciprocal, Newton-refined to full
+            const double r = rsqrt_nr(ss);                      // precision: no sqrt / division chain on the critical path
+            sigma = ss * r;
+            bk = r * rcp_nr(sigma + fabs(x0));                  // 1 / (sigma (sigma + |x0|)) = 2 / |v|^2
+        } else {
+            sigma = sqrt(ss);
+            bk = sigma > 0.0 ? 1.0 / (sigma * (sigma + fabs(x0))) : 0.0;
+        }
         rmin = fmin(rmin, sigma);
         rmax = fmax(rmax, sigma);
-        if (sigma > 0.0) {
-            A[k][k] = x0 + copysign(sigma, x0);                 // v0 = x0 - alpha, alpha = -sign(x0) sigma
-            beta[k] = 1.0 / (sigma * (sigma + fabs(x0)));       // 2 / |v|^2
-        } else {
-            beta[k] = 0.0;
-        }
+        if (sigma > 0.0) A[k][k] = x0 + copysign(sigma, x0);    // v0 = x0 - alpha, alpha = -sign(x0) sigma
+        beta[k] = bk;
 #pragma unroll
         for (int j = k + 1; j < 8; ++j) {
             double d = 0.0;
@@ -450,7 +572,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
 #pragma unroll
         for (int i = 0; i < 9; ++i) nv[i] *= inv;
     }
-    rank2_project(nv);
+    rank2_project_fast(nv);
     double F[9];
     denormalise(nv, a1, b1, c1, a2, b2, c2, F);
     bool finite = true;

@@ -8,6 +8,7 @@ namespace rg {
 struct ScoreState;                                   // f_api.cu (same translation unit)
 int score_state_layout(Ctx* c, int P, long long Htot, int bbox_words, ScoreState& s);
 FlagList flag_list_for(Ctx* c, const ScoreState& s, double evals, int* rc_out);
+int fixup_grid(const Ctx* c, double evals);
 
 static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const double* y, const int* idx, const FPlan& plan,
                             int n, const PnpFrame* fr) {
@@ -107,7 +108,7 @@ static int pnp_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const do
         prof_mark(c, st, 3);
         PnpFix::Params fp{(const float4*)c->X32.ptr, X, y, (const Pose32*)c->pose32.ptr, (const double*)c->pose64.ptr,
                           pi, plan.P, thr2};
-        fixup_list<PnpFix><<<c->sm_count * 4, 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
+        fixup_list<PnpFix><<<fixup_grid(c, plan.evals), 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
         c->last_stats[7] += 2;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));

@@ -381,38 +381,6 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
 constexpr int kRowsThreads = 64;
 constexpr size_t kRowsSmem = (144 + 12) * kRowsThreads * sizeof(double);
 
-// 1/sqrt(x) to full double precision from the 20-bit hardware seed (MUFU.RSQ64H) + two Newton steps: ~10 dependent
-// instructions instead of the ~60 of sqrt() followed by a division.  x > 0, normal range.
-__device__ __forceinline__ double rsqrt_nr(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
-    return y;
-}
-__device__ __forceinline__ double rcp_approx(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return y;
-}
-// Jacobi rotation for the thread-per-hypothesis solver.  Any rotation with c^2 + s^2 = 1 (to rounding) keeps the
-// iteration an orthogonal transformation, so only c and s = c t have to be exact functions of t; the ANGLE itself only
-// steers convergence and is computed from 20-bit reciprocal / reciprocal-square-root seeds (a 1e-6 relative error in t
-// leaves an off-diagonal of 1e-6 of the old one instead of zero: at most one extra sweep, measured none).  The exact
-// formula (jacobi_rot: two divisions, two square roots) was ~750 dependent cycles of the ~1100 per rotation.
-__device__ __forceinline__ void jacobi_rot_fast(double a, double b, double g, double& c, double& s) {
-    const double zeta = (b - a) * 0.5 * rcp_approx(g);
-    const double w = fma(zeta, zeta, 1.0);
-    double rs;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(w));
-    const double root = w * rs;                                   // ~ sqrt(1 + zeta^2)
-    double t = copysign(rcp_approx(fabs(zeta) + root), zeta);
-    if (!(fabs(t) <= 1.0)) t = 0.0;       // zeta^2 overflowed (needs a column ratio > 1e278, excluded by the `tiny` test): no rotation
-    c = rsqrt_nr(fma(t, t, 1.0));
-    s = c * t;
-}
-
 template <int NPTS>
 __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __restrict__ X, const double* __restrict__ y,
                                                                 const int* __restrict__ idx, const PairInfo* __restrict__ pi,

@@ -355,10 +355,14 @@ __global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, Flag
         n_band += __shfl_xor_sync(full, n_band, o);
         n_flip += __shfl_xor_sync(full, n_flip, o);
     }
-    if (lane == 0) {
-        if (n_groups) atomicAdd(&stats[0], n_groups);
-        if (n_band) atomicAdd(&stats[1], n_band);
-        if (n_flip) atomicAdd(&stats[2], n_flip);
+    // one set of atomics per BLOCK (the three statistics words are shared by the whole grid)
+    __shared__ unsigned long long s_stat[3][8];
+    if (lane == 0) { s_stat[0][warp] = n_groups; s_stat[1][warp] = n_band; s_stat[2][warp] = n_flip; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s_stat[threadIdx.x][w];
+        if (t) atomicAdd(&stats[threadIdx.x], t);
     }
 }
 
