@@ -74,6 +74,17 @@ def _worker(rank, world, port, q):
         idxs = [sampling.fast(300, 40, 8, seed=p) for p in range(5)]
         res = parallel.f_ransac_pairs_sharded(pairs, idxs, thr=1.5, compute=_oracle_compute)
         split = parallel.f_ransac_split_hypotheses(pairs[0], idxs[0], thr=1.5, compute=_oracle_compute)
+        # the cross-rank key is the first maximum: the reference's sequential tie rule cannot be merged from per-rank winners
+        try:
+            parallel.f_ransac_split_hypotheses(pairs[0], idxs[0], thr=1.5, compute=_oracle_compute, tie_mode=rg.TIE_REFERENCE)
+            raise AssertionError("tie_mode=TIE_REFERENCE must be refused when the hypotheses are split")
+        except ValueError:
+            pass
+        # fewer hypotheses than ranks: the rank without work contributes a zero key instead of calling compute on nothing
+        tiny = parallel.f_ransac_split_hypotheses(pairs[0], idxs[0][:1], thr=1.5, compute=_oracle_compute)
+        assert tiny["best_idx"] in (0, -1) and tiny["mask"].shape == (300,)
+        masks = parallel.f_ransac_pairs_sharded(pairs, idxs, thr=1.5, compute=_oracle_compute, gather_mask=True)["mask"]
+        assert len(masks) == 5 and all(m.shape == (300,) for m in masks)
         q.put((rank, res["range"], res["best_idx"].tolist(), res["best_count"].tolist(), res["F"].tolist(),
                split["best_idx"], split["best_count"], split["F"].tolist(), split["mask"].tolist(), split["owner"]))
     finally:
