@@ -513,7 +513,31 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     const double r_ev = c->rate_evals_per_s > 0.0 ? c->rate_evals_per_s : 1.5e12;       // until measured: round-1 figures
     const double r_up = c->rate_h2d_bytes_per_s > 0.0 ? c->rate_h2d_bytes_per_s : 5.0e10;
     const double bytes_per_hyp = seeded ? 0.0 : 32.0;
-    if (bounds.size() == 2 && P >= 2 && !c->opt_profile && c->opt_host_slices != 1) {
+    double total_evals = 0.0;
+    for (int p = 0; p < P; ++p) total_evals += (double)(pair_off[p + 1] - pair_off[p]) * (double)(hyp_off[p + 1] - hyp_off[p]);
+    // how many extra passes are affordable: each costs ~0.1 ms of small kernels; spend at most 1 % of the call on them
+    const int levels = (int)std::min(5.0, std::floor(0.01 * (total_evals / r_ev) / 1.0e-4));
+    if (levels >= 2 && c->opt_host_slices == 0 && !c->opt_profile) {
+        // Large batch: nothing hides the upload of the FIRST pass (102 MB for 64 config-5 pairs: 2 ms at 55 GB/s, 17 ms
+        // when eight ranks share the host link), so the first pass is cut into sub-passes of doubling size — 1/2^levels of
+        // it first — each of which covers the upload of the next one.
+        const int p_end = bounds[1];
+        double first_evals = 0.0;
+        for (int p = 0; p < p_end; ++p) first_evals += (double)(pair_off[p + 1] - pair_off[p]) * (double)(hyp_off[p + 1] - hyp_off[p]);
+        std::vector<int> nb;
+        nb.push_back(0);
+        double target = first_evals / (double)(1 << levels), acc = 0.0;
+        for (int p = 0; p < p_end; ++p) {
+            acc += (double)(pair_off[p + 1] - pair_off[p]) * (double)(hyp_off[p + 1] - hyp_off[p]);
+            if (acc >= target && p + 1 < p_end) {
+                nb.push_back(p + 1);
+                acc = 0.0;
+                target *= 2.0;
+            }
+        }
+        for (size_t k = 1; k < bounds.size(); ++k) nb.push_back(bounds[k]);
+        bounds.swap(nb);
+    } else if (bounds.size() == 2 && P >= 2 && !c->opt_profile && c->opt_host_slices != 1) {
         int first = 1;
         double score_s = 0.0;
         auto rest_bytes = [&](int f) {

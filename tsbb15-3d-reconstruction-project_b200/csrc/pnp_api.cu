@@ -20,18 +20,18 @@ static int pnp_solve_launch(Ctx* c, cudaStream_t st, const double* X, const doub
     double* pose64 = (double*)c->pose64.ptr;
     Pose32* pose32 = (Pose32*)c->pose32.ptr;
     unsigned char* flags = (unsigned char*)c->flags.ptr;
-    if (c->opt_pnp_solver == 0) {                    // default: thread per hypothesis, Givens QR + row Jacobi in shared memory
+    if (c->opt_pnp_solver == 0) {                    // default: six lanes per hypothesis, Householder QR + row Jacobi in shared memory
         if (!c->pnp_rows_attr_set) {
-            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
-            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
-            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem<6>()));
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem<7>()));
+            RG_CUDA(cudaFuncSetAttribute(pnp_solve_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem<8>()));
             c->pnp_rows_attr_set = true;             // per context = per device
         }
-        const int g2 = ceil_div(H, kRowsThreads);
+        const int g2 = ceil_div(H, kRowsHypPerBlock);
         switch (n) {
-            case 6: pnp_solve_rows<6><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
-            case 7: pnp_solve_rows<7><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
-            case 8: pnp_solve_rows<8><<<g2, kRowsThreads, kRowsSmem, st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 6: pnp_solve_rows<6><<<g2, kRowsThreads, rows_smem<6>(), st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 7: pnp_solve_rows<7><<<g2, kRowsThreads, rows_smem<7>(), st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
+            case 8: pnp_solve_rows<8><<<g2, kRowsThreads, rows_smem<8>(), st>>>(X, y, idx, pi, plan.P, H, fr, pose64, pose32, flags); break;
             default: set_error("invalid argument: PnP sample size n must be 6, 7 or 8"); return RG_ERR_ARG;
         }
     } else {

@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(256) pnp_make_pose32(const double* __restrict_
 // ------------------------------------------------------------------------------------------------
 // constraint enforcement C0 = (A|b) -> (R|t)    pnp.py:147-151
 // ------------------------------------------------------------------------------------------------
+template <bool FAST = false>
 __device__ __forceinline__ void jacobi3(double (&w)[3][3], double (&v)[3][3]) {
-    for (int sweep = 0; sweep < 12; ++sweep) {
+    for (int sweep = 0; sweep < 14; ++sweep) {
         bool rotated = false;
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
@@ -218,9 +219,9 @@ __device__ __forceinline__ void jacobi3(double (&w)[3][3], double (&v)[3][3]) {
             const double a = w[p][0] * w[p][0] + w[p][1] * w[p][1] + w[p][2] * w[p][2];
             const double b = w[q][0] * w[q][0] + w[q][1] * w[q][1] + w[q][2] * w[q][2];
             const double g = w[p][0] * w[q][0] + w[p][1] * w[q][1] + w[p][2] * w[q][2];
-            if (g != 0.0 && fabs(g) > 1e-16 * sqrt(a * b)) {
+            if (FAST ? (g * g > 1e-32 * (a * b)) : (g != 0.0 && fabs(g) > 1e-16 * sqrt(a * b))) {
                 double c, s;
-                jacobi_rot(a, b, g, c, s);
+                if (FAST) jacobi_rot_fast(a, b, g, c, s); else jacobi_rot(a, b, g, c, s);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double wp = w[p][i], wq = w[q][i];
@@ -244,6 +245,7 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
 }
 
 // c0: 12-vector (row-major 3x4).  Rt: R row-major then t.  Returns false if the result is not finite.
+template <bool FAST = false>
 __device__ __forceinline__ bool enforce_pose(const double* __restrict__ c0, double* __restrict__ Rt) {
     const double A[9] = {c0[0], c0[1], c0[2], c0[4], c0[5], c0[6], c0[8], c0[9], c0[10]};
     const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
@@ -254,7 +256,7 @@ __device__ __forceinline__ bool enforce_pose(const double* __restrict__ c0, doub
     for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int i = 0; i < 3; ++i) { w[j][i] = tau * A[3 * i + j]; v[j][i] = (i == j) ? 1.0 : 0.0; }
-    jacobi3(w, v);
+    jacobi3<FAST>(w, v);
     double sg[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sg[j] = sqrt(w[j][0] * w[j][0] + w[j][1] * w[j][1] + w[j][2] * w[j][2]);
@@ -366,20 +368,35 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// minimal-sample DLT-PnP, default solver (round 2): ONE THREAD per hypothesis, no shuffles.
-//   1. the 3n x 12 design matrix never exists: its rows (r_l (x) Xh_k, 8 non-zeros each) are rotated one by one into the
-//      12 x 12 triangular factor R (Givens row insertion, backward stable), R lives in shared memory [element][thread];
-//   2. the rows of R are orthogonalised by one-sided Jacobi rotations (= Hestenes on R^T): at convergence row i is
-//      sigma_i v_i^T, the right singular vectors of A scaled by the singular values — no V accumulation, 12 instead of
-//      18 + 12 doubles per column, and QR preconditioning roughly halves the sweeps;
+// minimal-sample DLT-PnP, default solver (round 2): SIX LANES per hypothesis, matrices in shared memory, no shuffles in
+// the rotation loop.
+//   1. the 3n x 12 design matrix is written to shared memory (one sample point per lane) and reduced to its triangular
+//      factor R by Householder reflections, every lane owning two columns (backward stable; 12 short steps);
+//   2. the ROWS of R are orthogonalised by one-sided Jacobi rotations (= Hestenes on R^T): at convergence row i is
+//      sigma_i v_i^T — the right singular vectors of A scaled by the singular values — so no V is accumulated and a
+//      rotation touches 2 x 12 doubles instead of 2 x (18 + 12).  A sweep is a round-robin tournament of 11 rounds x 6
+//      DISJOINT pairs: lane l rotates pair l of the round, all six in parallel, one __syncwarp per round;
 //   3. the minimiser c0 = v_12 is the normalised smallest row; when that row is below 1e-4 sigma_1 (exact data: it is pure
-//      rounding noise) c0 is instead the unit vector orthogonal to the other eleven rows (projection of the best
-//      coordinate vector, applied twice), which has the same eps * sigma_1 / gap accuracy as any SVD.
-// Round 1's 16-lane group Jacobi (pnp_solve_jacobi, the solver BASELINE.json names) spent its time in 60 SHFL per rotation
-// round: 0.30 ms for 8192 hypotheses; it stays selectable (rg_set_option(ctx, 7, 1)) and is parity-tested against this one.
+//      rounding noise) c0 is instead the unit vector orthogonal to the other eleven rows (projection of the best coordinate
+//      vector, applied twice), which has the same eps * sigma_1 / gap accuracy as any SVD.
+// Rotations use jacobi_rot_fast: the angle comes from 20-bit reciprocal seeds, c and s are exact functions of it, so the
+// transformation stays orthogonal to rounding and only the convergence path changes (the exact formula's two divisions and
+// two square roots were two thirds of a rotation's dependent chain).
+// History (B200, 8192 hypotheses, config 4): 16-lane group Jacobi on the 18 x 12 matrix with V (round 1, 60 SHFL per
+// rotation round) 0.30 ms; one thread per hypothesis with R in shared memory 0.31 ms (exact rotations) -> 0.22 ms (fast
+// rotations, three interleaved pairs): pure latency, 256 warps on 592 sub-partitions; this kernel: see DESIGN.md.
+// The group Jacobi (pnp_solve_jacobi, the solver BASELINE.json names) stays selectable (rg_set_option(ctx, 7, 1)) and is
+// parity-tested against this one.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRowsThreads = 64;
-constexpr size_t kRowsSmem = (144 + 12) * kRowsThreads * sizeof(double);
+constexpr int kRowsLanes = 6;                          // lanes per hypothesis
+constexpr int kRowsHypPerWarp = 5;                     // 30 of the 32 lanes carry hypotheses
+constexpr int kRowsWarps = 4;
+constexpr int kRowsThreads = 32 * kRowsWarps;
+constexpr int kRowsHypPerBlock = kRowsHypPerWarp * kRowsWarps;
+constexpr int kRS = 14;                                // row stride in doubles: 12 + 2 of padding, so that the 16-byte units of the
+                                                       // six rows a hypothesis touches in one round fall into different bank groups
+template <int NPTS> __host__ __device__ constexpr int rows_stride() { return 3 * NPTS * kRS + 30; }   // even (16-byte rows), = 5 mod 8 units
+template <int NPTS> constexpr size_t rows_smem() { return (size_t)kRowsHypPerBlock * rows_stride<NPTS>() * sizeof(double); }
 
 template <int NPTS>
 __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __restrict__ X, const double* __restrict__ y,
@@ -388,12 +405,19 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
                                                                 double* __restrict__ pose64, Pose32* __restrict__ pose32,
                                                                 unsigned char* __restrict__ flags) {
     extern __shared__ double rows_sm[];
-    constexpr int T = kRowsThreads;
-    double* R = rows_sm + threadIdx.x;                 // R[i][j] at R[(12 * i + j) * T]
-    double* row = rows_sm + 144 * T + threadIdx.x;     // the row being inserted, row[j] at row[j * T]
-    const int hq = blockIdx.x * T + threadIdx.x;
-    const bool live = hq < H;
-    const int h = live ? hq : H - 1;
+    constexpr int ROWS = 3 * NPTS;
+    constexpr int SH = rows_stride<NPTS>();
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / kRowsLanes, l = lane - g * kRowsLanes;
+    const bool act = g < kRowsHypPerWarp;                              // lanes 30, 31 only take part in the warp-wide votes
+    const int hq = (blockIdx.x * kRowsWarps + warp) * kRowsHypPerWarp + g;
+    const bool live = act && hq < H;
+    const int h = (act && hq < H) ? hq : H - 1;
+    double* A = rows_sm + (size_t)(warp * kRowsHypPerWarp + (act ? g : 0)) * SH;      // A[r][c] at A[kRS r + c]
+    double* diag = A + ROWS * kRS;                                     // scratch: diag[12], nrm[12], v0, beta, normF2
+    double* nrm = diag + 12;
+    double* sc = nrm + 12;
     int view = 0;
     {
         int lo = 0, hi = V;
@@ -402,101 +426,157 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
     }
     const int N = pi[view].n_all;
     const size_t pbase = (size_t)pi[view].pt_off;
-    for (int e = 0; e < 144; ++e) R[e * T] = 0.0;
 
-    // ---- 1. Givens row insertion -------------------------------------------------------------------------
-    for (int k = 0; k < NPTS; ++k) {
-        int q = idx[(size_t)h * NPTS + k];
-        q = q < 0 ? 0 : (q >= N ? N - 1 : q);
-        const size_t gq = pbase + q;
-        const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
-        const double y0 = y[2 * gq], y1 = y[2 * gq + 1];
-        for (int l = 0; l < 3; ++l) {
-            // rows of [y]_x for y = (y0, y1, 1):  r0 = (0,-1,y1)  r1 = (1,0,-y0)  r2 = (-y1,y0,0)
-            const double ra = l == 0 ? 0.0 : (l == 1 ? 1.0 : -y1);
-            const double rb = l == 0 ? -1.0 : (l == 1 ? 0.0 : y0);
-            const double rc = l == 0 ? y1 : (l == 1 ? -y0 : 0.0);
+    // ---- 0. design matrix: rows r_l (x) Xh_k, r_l the rows of [y_k]_x -------------------------------------------
+    if (act) {
+        for (int k = l; k < NPTS; k += kRowsLanes) {
+            int q = idx[(size_t)h * NPTS + k];
+            q = q < 0 ? 0 : (q >= N ? N - 1 : q);
+            const size_t gq = pbase + q;
+            const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
+            const double y0 = y[2 * gq], y1 = y[2 * gq + 1];
+            double* r0 = A + 3 * kRS * k;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) { row[b * T] = ra * Xh[b]; row[(4 + b) * T] = rb * Xh[b]; row[(8 + b) * T] = rc * Xh[b]; }
-            for (int i = 0; i < 12; ++i) {
-                const double v = row[i * T];
-                if (v == 0.0) continue;
-                const double d = R[(13 * i) * T];
-                const double x2 = fma(d, d, v * v);
-                if (x2 < 1e-280) continue;                          // |v| below 1e-140: zero for every purpose (NaN still propagates)
-                const double inv = rsqrt_nr(x2);
-                const double cs = d * inv, sn = v * inv;
-                for (int j = i; j < 12; ++j) {
-                    const double a = R[(12 * i + j) * T], b = row[j * T];
-                    R[(12 * i + j) * T] = cs * a + sn * b;
-                    row[j * T] = cs * b - sn * a;
-                }
+            for (int b = 0; b < 4; ++b) {
+                r0[b] = 0.0;                      r0[4 + b] = -Xh[b];               r0[8 + b] = y1 * Xh[b];            // ( 0, -1,  y1)
+                r0[kRS + b] = Xh[b];              r0[kRS + 4 + b] = 0.0;            r0[kRS + 8 + b] = -y0 * Xh[b];     // ( 1,  0, -y0)
+                r0[2 * kRS + b] = -y1 * Xh[b];    r0[2 * kRS + 4 + b] = y0 * Xh[b]; r0[2 * kRS + 8 + b] = 0.0;         // (-y1, y0,  0)
             }
         }
     }
+    __syncwarp();
 
-    // ---- 2. one-sided Jacobi on the rows of R ----------------------------------------------------------------
+    // ---- 1. Householder QR, lane l owns columns l and l + 6 --------------------------------------------------------
+    for (int k = 0; k < 12; ++k) {
+        if (act && l == k % kRowsLanes) {
+            double ss = 0.0;
+            for (int r = k; r < ROWS; ++r) { const double t = A[kRS * r + k]; ss = fma(t, t, ss); }
+            const double x0 = A[kRS * k + k];
+            double sigma, beta;
+            if (ss > 1e-290 && ss < 1e290) {
+                const double ri = rsqrt_nr(ss);
+                sigma = ss * ri;
+                beta = ri * rcp_nr(sigma + fabs(x0));                  // 1 / (sigma (sigma + |x0|)) = 2 / |v|^2
+            } else {
+                sigma = sqrt(ss);
+                beta = sigma > 0.0 ? 1.0 / (sigma * (sigma + fabs(x0))) : 0.0;
+            }
+            diag[k] = -copysign(sigma, x0);                            // R[k][k]
+            sc[0] = x0 + copysign(sigma, x0);                          // v_k (v_r = A[r][k] for r > k)
+            sc[1] = beta;
+        }
+        __syncwarp();
+        if (act) {
+            const double v0 = sc[0], beta = sc[1];
+            for (int c = l; c < 12; c += kRowsLanes) {
+                if (c <= k) continue;
+                double d = v0 * A[kRS * k + c];
+                for (int r = k + 1; r < ROWS; ++r) d = fma(A[kRS * r + k], A[kRS * r + c], d);
+                d *= beta;
+                A[kRS * k + c] -= d * v0;
+                for (int r = k + 1; r < ROWS; ++r) A[kRS * r + c] = fma(-d, A[kRS * r + k], A[kRS * r + c]);
+            }
+        }
+        __syncwarp();
+    }
+    if (act) {                                                         // R in rows 0..11: diagonal in place, zeros below it
+        for (int c = l; c < 12; c += kRowsLanes) {
+            A[kRS * c + c] = diag[c];
+            for (int r = c + 1; r < 12; ++r) A[kRS * r + c] = 0.0;
+        }
+    }
+    __syncwarp();
+
+    // ---- 2. one-sided Jacobi on the rows of R, rows in REGISTERS: lane l holds a "top" and a "bottom" row and rotates that
+    // pair; between rounds the rows travel round the ring top_1 .. top_5, bottom_5 .. bottom_0 (top_0 fixed) — the circle
+    // method: 11 rounds pair every row with every other exactly once.  The exchange is 2 x 12 doubles = 48 SHFL per round
+    // for the FIVE hypotheses of the warp (round 1's group Jacobi: 60 SHFL per round for TWO).  A first version kept the
+    // rows in shared memory: the loop was bound by shared-memory wavefronts (ncu: 69 % of the LSU peak, 41 % of them bank
+    // conflicts, FP64 pipe 27 % busy) at 0.13 ms per 8192 hypotheses.
+    double top[12], bot[12];
+    double part = 0.0;
+    if (act) {
+        const double2* At = reinterpret_cast<const double2*>(A + kRS * l);
+        const double2* Ab = reinterpret_cast<const double2*>(A + kRS * (11 - l));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double2 u = At[k], w = Ab[k];
+            top[2 * k] = u.x; top[2 * k + 1] = u.y; bot[2 * k] = w.x; bot[2 * k + 1] = w.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) part = fma(top[k], top[k], fma(bot[k], bot[k], part));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { top[k] = 0.0; bot[k] = 0.0; }
+    }
+    const int gbase = (act ? g : kRowsHypPerWarp - 1) * kRowsLanes;
     double normF2 = 0.0;
-    for (int e = 0; e < 144; ++e) { const double t = R[e * T]; normF2 += t * t; }
+#pragma unroll
+    for (int t = 0; t < kRowsLanes; ++t) normF2 += __shfl_sync(full, part, gbase + t);
     const double tiny = 7.9e-31 * normF2;
-    // round-robin tournament: 11 rounds x 6 DISJOINT row pairs.  The kernel runs one warp per SM sub-partition at best
-    // (8192 hypotheses = 256 warps), so nothing hides the latency of a rotation's dependent chain (dot products, seeds,
-    // Newton steps): kIlp independent pairs are therefore rotated together by the same thread, interleaved by the compiler.
-    constexpr int kIlp = 3;
+    const int src_left = act ? g * kRowsLanes + (l + kRowsLanes - 1) % kRowsLanes : lane;
+    const int src_right = act ? g * kRowsLanes + (l + 1) % kRowsLanes : lane;
     for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
         bool rotated = false;
         for (int r = 0; r < 11; ++r) {
-            for (int m0 = 0; m0 < 6; m0 += kIlp) {
-                int pi_[kIlp], qi_[kIlp];
-                double rp[kIlp][12], rq[kIlp][12];
+            if (act) {
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, g0 = 0.0, g1 = 0.0;
 #pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    const int m = m0 + u;
-                    int p = (m == 0) ? r : (r + m) % 11;
-                    int q = (m == 0) ? 11 : (r + 11 - m) % 11;
-                    if (p > q) { const int t = p; p = q; q = t; }
-                    pi_[u] = p; qi_[u] = q;
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) { rp[u][k] = R[(12 * p + k) * T]; rq[u][k] = R[(12 * q + k) * T]; }
+                for (int k = 0; k < 12; k += 2) {
+                    a0 = fma(top[k], top[k], a0); a1 = fma(top[k + 1], top[k + 1], a1);
+                    b0 = fma(bot[k], bot[k], b0); b1 = fma(bot[k + 1], bot[k + 1], b1);
+                    g0 = fma(top[k], bot[k], g0); g1 = fma(top[k + 1], bot[k + 1], g1);
                 }
+                const double a = a0 + a1, b = b0 + b1, gg = g0 + g1;
+                const bool conv = !(gg * gg > 1e-30 * (a * b)) || !(fmin(a, b) > tiny);
+                if (!conv) {
+                    double c, s;
+                    jacobi_rot_fast(a, b, gg, c, s);
 #pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, g0 = 0.0, g1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 12; k += 2) {
-                        a0 = fma(rp[u][k], rp[u][k], a0); a1 = fma(rp[u][k + 1], rp[u][k + 1], a1);
-                        b0 = fma(rq[u][k], rq[u][k], b0); b1 = fma(rq[u][k + 1], rq[u][k + 1], b1);
-                        g0 = fma(rp[u][k], rq[u][k], g0); g1 = fma(rp[u][k + 1], rq[u][k + 1], g1);
+                    for (int k = 0; k < 12; ++k) {
+                        const double x = top[k], z = bot[k];
+                        top[k] = c * x - s * z;
+                        bot[k] = s * x + c * z;
                     }
-                    const double a = a0 + a1, b = b0 + b1, g = g0 + g1;
-                    const bool conv = !(g * g > 1e-30 * (a * b)) || !(fmin(a, b) > tiny);
-                    if (!conv) {
-                        double c, s;
-                        jacobi_rot_fast(a, b, g, c, s);
-#pragma unroll
-                        for (int k = 0; k < 12; ++k) {
-                            const double x = rp[u][k], z = rq[u][k];
-                            R[(12 * pi_[u] + k) * T] = c * x - s * z;
-                            R[(12 * qi_[u] + k) * T] = s * x + c * z;
-                        }
-                        rotated = true;
-                    }
+                    // a rotation by less than 1e-8 leaves an off-diagonal below 1e-16 of the norms (quadratic convergence):
+                    // a sweep of only such rotations is the last one, no verification sweep needed
+                    rotated = rotated || fabs(s) > 1e-8;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const double send = (l == 0) ? bot[k] : top[k];           // lane 0's top never moves: it passes its bottom on
+                const double nt = __shfl_sync(full, send, src_left);
+                const double nb = __shfl_sync(full, bot[k], src_right);
+                const double keep = top[k];
+                top[k] = (l == 0) ? keep : nt;
+                bot[k] = (l == kRowsLanes - 1) ? keep : nb;
+            }
         }
-        if (!__any_sync(0xffffffffu, rotated)) break;
+        if (!__any_sync(full, rotated)) break;
     }
 
-    // ---- 3. smallest row -> c0 -----------------------------------------------------------------------------
-    double nrm[12];
+    // ---- 3. smallest row -> c0 -> (R | t) ---------------------------------------------------------------------------
+    if (act) {                                                         // rows (in whatever order they ended up) back to shared memory
+        double2* At = reinterpret_cast<double2*>(A + kRS * (2 * l));
+        double2* Ab = reinterpret_cast<double2*>(A + kRS * (2 * l + 1));
+        double nt = 0.0, nb = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            At[k] = make_double2(top[2 * k], top[2 * k + 1]);
+            Ab[k] = make_double2(bot[2 * k], bot[2 * k + 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { nt = fma(top[k], top[k], nt); nb = fma(bot[k], bot[k], nb); }
+        nrm[2 * l] = nt;
+        nrm[2 * l + 1] = nb;
+    }
+    __syncwarp();
+    if (!(act && l == 0)) return;
     double s0 = INFINITY, s1 = INFINITY, smax = 0.0;
     int jm = 0;
-#pragma unroll
     for (int i = 0; i < 12; ++i) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) { const double r = R[(12 * i + k) * T]; t = fma(r, r, t); }
-        nrm[i] = t;
+        const double t = nrm[i];
         const double key = (t == t) ? t : INFINITY;
         if (key < s0) { s1 = s0; s0 = key; jm = i; }
         else if (key < s1) s1 = key;
@@ -506,7 +586,7 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
     if (s0 > 1e-8 * smax) {
         const double inv = rsqrt(s0);
 #pragma unroll
-        for (int k = 0; k < 12; ++k) c0[k] = R[(12 * jm + k) * T] * inv;
+        for (int k = 0; k < 12; ++k) c0[k] = A[kRS * jm + k] * inv;
     } else {
         // unit vector orthogonal to the eleven other rows; start from the coordinate vector the projector keeps best
         double dg[12];
@@ -516,7 +596,7 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
             if (i == jm || !(nrm[i] > tiny)) continue;
             const double inv = 1.0 / nrm[i];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) { const double r = R[(12 * i + k) * T]; dg[k] -= r * r * inv; }
+            for (int k = 0; k < 12; ++k) { const double r = A[kRS * i + k]; dg[k] -= r * r * inv; }
         }
         int e = 0;
 #pragma unroll
@@ -528,10 +608,10 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
                 if (i == jm || !(nrm[i] > tiny)) continue;
                 double dot = 0.0;
 #pragma unroll
-                for (int k = 0; k < 12; ++k) dot = fma(R[(12 * i + k) * T], c0[k], dot);
+                for (int k = 0; k < 12; ++k) dot = fma(A[kRS * i + k], c0[k], dot);
                 dot /= nrm[i];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) c0[k] -= dot * R[(12 * i + k) * T];
+                for (int k = 0; k < 12; ++k) c0[k] -= dot * A[kRS * i + k];
             }
         }
         double t = 0.0;
@@ -542,7 +622,7 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
         for (int k = 0; k < 12; ++k) c0[k] *= inv;
     }
     double Rt[12];
-    const bool ok = enforce_pose(c0, Rt);
+    const bool ok = enforce_pose<true>(c0, Rt);
     if (live) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) pose64[(size_t)h * 12 + k] = Rt[k];

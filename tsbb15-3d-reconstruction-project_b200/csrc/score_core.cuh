@@ -385,11 +385,27 @@ __global__ void __launch_bounds__(256) argmax_counts(const int* __restrict__ cou
     const PairInfo info = pi[p];
     unsigned long long key = 0ull;
     unsigned bad = 0u;
-    for (int h = threadIdx.x; h < info.H; h += blockDim.x) {
-        const unsigned long long k =
-            ((unsigned long long)(unsigned)counts[info.hyp_off + h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
-        key = k > key ? k : key;
-        if (flags != nullptr) bad += (flags[info.hyp_off + h] >> 2) & 1u;
+    // four independent loads in flight per thread: with one pair per call (hypothesis-split mode) this single block is on
+    // the critical path and was a chain of dependent L2 round trips
+    for (int h0 = threadIdx.x; h0 < info.H; h0 += 4 * blockDim.x) {
+        int cv[4];
+        unsigned fv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * blockDim.x;
+            cv[u] = h < info.H ? counts[info.hyp_off + h] : 0;
+            fv[u] = (flags != nullptr && h < info.H) ? flags[info.hyp_off + h] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * blockDim.x;
+            if (h < info.H) {
+                const unsigned long long k =
+                    ((unsigned long long)(unsigned)cv[u] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+                key = k > key ? k : key;
+                bad += (fv[u] >> 2) & 1u;
+            }
+        }
     }
     if (stats != nullptr && bad) atomicAdd(&stats[4], (unsigned long long)bad);
 #pragma unroll
