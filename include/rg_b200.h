@@ -59,7 +59,9 @@ int rg_host_free(void* p);
  * option 7 = PnP minimal-sample solver: 0 = Givens QR + Jacobi on the rows of R, one thread per hypothesis (default);
  *            1 = register-resident one-sided Jacobi in a 16-lane group (the solver BASELINE.json names)
  * option 8 = test hook: capacity of the guard-band flag list in records (0 = automatic); a small value forces the
- *            FP64 recount of the hypotheses whose flags did not fit; results do not depend on it */
+ *            FP64 recount of the hypotheses whose flags did not fit; results do not depend on it
+ * option 9 = guard-band safety factor x 1000 (default 1000 = the proven FP32 rounding bound): a wider band sends more
+ *            evaluations to the FP64 recheck (results do not depend on it); measures the fix-up cost of a less accurate scorer */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the PASSES since the last read
  * (at most 256 passes are remembered; *out_calls = passes covered); synchronises `stream` */

@@ -155,12 +155,49 @@ __device__ __forceinline__ void eval_ordered(const H2 (&H)[K], const float4* __r
         }
 }
 
+// ---- tensor-core upper bound (round 2): the evaluation body WITHOUT the four packed operations of r = x^T F y, r being
+// read from shared memory instead (one LDS.64 per two evaluations, standing in for the tcgen05.ld that would fetch the
+// tcgen05.mma result from TMEM): the most the FP32 side can gain if the contraction costs nothing at all ----
+template <int K>
+__device__ __forceinline__ void eval_r_given(const H2 (&H)[K], const float4* __restrict__ pr, const float2* __restrict__ rs,
+                                             unsigned (&cnt)[K], float (&minabs)[K]) {
+    const float4 X = pr[0], Y = pr[1];
+    const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
+    const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
+    float2 l1x[K], l1y[K], l2x[K], l2y[K], s1[K], s2[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { l1x[k] = ffma2_sbs(H[k].f[1], y1, H[k].f[2]); l1y[k] = ffma2_sbs(H[k].f[4], y1, H[k].f[5]); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { l1x[k] = ffma2_sbc(H[k].f[0], y0, l1x[k]); l1y[k] = ffma2_sbc(H[k].f[3], y0, l1y[k]); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { l2x[k] = ffma2_sbs(H[k].f[3], x1, H[k].f[6]); l2y[k] = ffma2_sbs(H[k].f[4], x1, H[k].f[7]); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { l2x[k] = ffma2_sbc(H[k].f[0], x0, l2x[k]); l2y[k] = ffma2_sbc(H[k].f[1], x0, l2y[k]); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s1[k] = __ffma2_rn(l1x[k], l1x[k], __fmul2_rn(l1y[k], l1y[k]));
+        s2[k] = __ffma2_rn(l2x[k], l2x[k], __fmul2_rn(l2y[k], l2y[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 r = rs[k * 256];
+        const float2 nm = make_float2(-fminf(s1[k].x, s2[k].x), -fminf(s1[k].y, s2[k].y));
+        const float2 q = __ffma2_rn(r, r, nm);
+        cnt[k] += __float_as_uint(q.x) >> 31;
+        cnt[k] += __float_as_uint(q.y) >> 31;
+        minabs[k] = fminf(minabs[k], fminf(fabsf(q.x), fabsf(q.y)));
+    }
+}
+
 constexpr int kPts = 512;      // points per chunk in shared memory (8 KB)
 
 template <int VARIANT, int K>
 __global__ void __launch_bounds__(256, 3) bench_kernel(const float4* __restrict__ pts, const float* __restrict__ hyp, int iters,
                                                        int* __restrict__ out) {
     __shared__ float4 sp[kPts];     // kPts/2 point pairs x 2 float4
+    __shared__ float2 srs[VARIANT == 200 ? 4 * K * 256 : 1];       // "r from the tensor core": 4 pairs x K hypotheses per thread
+    if (VARIANT == 200)
+        for (int i = threadIdx.x; i < 4 * K * 256; i += blockDim.x) srs[i] = make_float2(0.25f + 1e-3f * (i % 97), -0.3f + 2e-3f * (i % 89));
     for (int i = threadIdx.x; i < kPts; i += blockDim.x) sp[i] = pts[i];
     __syncthreads();
     H2 H[K];
@@ -179,8 +216,11 @@ __global__ void __launch_bounds__(256, 3) bench_kernel(const float4* __restrict_
             float ma[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) ma[k] = INFINITY;
-            if (VARIANT >= 100) {
-                constexpr int NP = VARIANT >= 100 ? VARIANT - 100 : 1;
+            if (VARIANT == 200) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) eval_r_given<K>(H, sp + (g * 4 + j) * 2, srs + j * K * 256 + threadIdx.x, cnt, ma);
+            } else if (VARIANT >= 100) {
+                constexpr int NP = (VARIANT >= 100 && VARIANT < 200) ? VARIANT - 100 : 1;
 #pragma unroll
                 for (int j = 0; j < 4; j += NP) eval_ordered<K, NP>(H, sp + (g * 4 + j) * 2, cnt, ma);
             } else {
@@ -225,6 +265,8 @@ int main() {
     float4* dp; float* dh; int* dout;
     cudaMalloc(&dp, kPts * sizeof(float4)); cudaMalloc(&dh, nh * 4); cudaMalloc(&dout, (size_t)blocks * 256 * 4);
     cudaMemcpy(dp, hp, kPts * sizeof(float4), cudaMemcpyHostToDevice); cudaMemcpy(dh, hh, nh * 4, cudaMemcpyHostToDevice);
+    run<200, 2>(dp, dh, dout, blocks);
+    run<0, 2>(dp, dh, dout, blocks);
     run<101, 2>(dp, dh, dout, blocks);
     run<102, 2>(dp, dh, dout, blocks);
     run<104, 2>(dp, dh, dout, blocks);

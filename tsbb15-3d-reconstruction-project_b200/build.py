@@ -23,6 +23,25 @@ def _stale() -> bool:
     return os.path.getmtime(os.path.abspath(__file__)) > t
 
 
+LIB_DEBUG = os.path.join(HERE, "librg_b200_debug.so")
+
+
+def build_debug(force: bool = False) -> str:
+    """The same library with -DRG_DEBUG: device-side bounds / invariant assertions (RG_ASSERT) compiled in.  Loaded by
+    tests/test_gpu_debug_build.py through RG_LIB; never the default."""
+    if not force and os.path.isfile(LIB_DEBUG) and os.path.getmtime(LIB_DEBUG) >= max(
+            os.path.getmtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS if os.path.isfile(os.path.join(CSRC, f))):
+        return LIB_DEBUG
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    cmd = [nvcc] + flags + ["-DRG_DEBUG"] + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB_DEBUG]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building librg_b200_debug.so")
+    return LIB_DEBUG
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -41,3 +60,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--debug" in sys.argv:
+        print(build_debug(force="--force" in sys.argv))

@@ -7,6 +7,14 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#ifdef RG_DEBUG
+#include <cassert>
+// bounds / invariant checks of the debug build (librg_b200_debug.so, tests/test_gpu_debug_build.py): compute-sanitizer is closed
+// on this pool, so the kernels carry their own assertions; a failed one traps and the next CUDA call reports it
+#define RG_ASSERT(cond) assert(cond)
+#else
+#define RG_ASSERT(cond) ((void)0)
+#endif
 
 namespace rg {
 
@@ -154,6 +162,8 @@ static_assert(sizeof(PairInfo) == 48, "PairInfo layout");
 struct PairFrame {
     double c1x, c1y, c2x, c2y;
     double thr, B;
+    double band_scale;         // multiplies the guard band (1 = the proven bound; option 9 widens it for experiments)
+    double pad;
 };
 
 struct FPlan {
@@ -182,6 +192,7 @@ struct Ctx {
     bool pnp_rows_attr_set = false;                // dynamic shared memory limit of pnp_solve_rows raised on this device
     int opt_pnp_solver = 0;                        // option 7: 0 = Givens-QR + row Jacobi (default), 1 = 16-lane group Jacobi
     long long opt_list_cap = 0;                    // option 8 (test hook): capacity of the guard-band flag list in records (0 = automatic)
+    double opt_band_scale = 1.0;                   // option 9: guard-band safety factor (>= 1)
     long long opt_pass_evals = 0;                  // option 6: evaluations per pass of a large batch (0 = default)
     // peer-to-peer argmax exchange (hypothesis-split mode over NVLink), see p2p_api.cu
     void* p2p_local = nullptr; size_t p2p_bytes = 0; int p2p_rank = 0, p2p_world = 0; unsigned p2p_seq = 0;

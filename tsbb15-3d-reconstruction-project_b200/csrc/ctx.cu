@@ -162,6 +162,9 @@ int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 // option 6: hypothesis x correspondence evaluations per pass of a large RANSAC batch (0 = default 2.7e10)
 // option 7: PnP minimal-sample solver: 0 = Givens QR + row Jacobi, thread per hypothesis (default); 1 = 16-lane group Jacobi
 // option 8: test hook: capacity of the guard-band flag list in records (0 = automatic); a tiny value forces the FP64 recount
+// option 9: guard-band safety factor x 1000 (default 1000 = the proven FP32 rounding bound); larger values keep every result
+//           exact and only send more evaluations to the FP64 recheck — used to MEASURE what a less accurate scorer
+//           (tensor-core split-precision accumulation) would cost in fix-up time
 int rg_set_option(void* ctx, int option, long long value) {
     RG_CHECK_ARG(ctx != nullptr, "ctx is null");
     Ctx* c = (Ctx*)ctx;
@@ -208,6 +211,12 @@ int rg_set_option(void* ctx, int option, long long value) {
     if (option == 7) {
         if (value != 0 && value != 1) { set_error("invalid argument: option 7 (PnP minimal solver) must be 0 or 1"); return RG_ERR_ARG; }
         c->opt_pnp_solver = (int)value;
+        return RG_OK;
+    }
+    if (option == 9) {
+        if (value < 1000 || value > 100000000ll) { set_error("invalid argument: option 9 (guard-band factor x 1000) must be in [1000, 1e8]"); return RG_ERR_ARG; }
+        c->opt_band_scale = (double)value / 1000.0;
+        c->prep_pts = nullptr;
         return RG_OK;
     }
     if (option == 8) {

@@ -105,7 +105,7 @@ static int f_prepare(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreStat
     const int nbx = std::max(1, std::min(64, ceil_div(plan.maxN, 256 * 4)));
     f_bbox<<<dim3(nbx, P), 256, 0, st>>>((const double4*)pts64, pi, s.bbox);
     const int nbn = std::max(1, std::min(128, ceil_div(plan.maxN / 2 + kSub, 256)));
-    f_normalise<<<dim3(nbn, P), 256, 0, st>>>((const double4*)pts64, pi, s.bbox, thr, (PairFrame*)c->pair_frame.ptr,
+    f_normalise<<<dim3(nbn, P), 256, 0, st>>>((const double4*)pts64, pi, s.bbox, thr, c->opt_band_scale, (PairFrame*)c->pair_frame.ptr,
                                               (float4*)c->pts32.ptr);
     c->last_stats[7] += 2;
     RG_CUDA(cudaGetLastError());

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) f_bbox(const double4* __restrict__ pts, c
     }
 }
 
-__device__ __forceinline__ PairFrame frame_from_bbox(const unsigned* __restrict__ bb, double thr) {
+__device__ __forceinline__ PairFrame frame_from_bbox(const unsigned* __restrict__ bb, double thr, double band_scale) {
     double c[4], half = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -137,6 +137,8 @@ __device__ __forceinline__ PairFrame frame_from_bbox(const unsigned* __restrict_
     o.thr = thr;
     // bound on |normalised coordinate| with head-room for the FP64 division and FP32 rounding
     o.B = (half / thr) * (1.0 + 1e-6) + 1e-30;
+    o.band_scale = band_scale;
+    o.pad = 0.0;
     return o;
 }
 
@@ -145,11 +147,11 @@ __device__ __forceinline__ PairFrame frame_from_bbox(const unsigned* __restrict_
 // Points beyond n (padding up to a multiple of kSub) are NaN: they can never count and never flag.
 // Every block derives the pair's frame from the bounding box; block x == 0 also stores it for the later kernels.
 __global__ void __launch_bounds__(256) f_normalise(const double4* __restrict__ pts, const PairInfo* __restrict__ pi,
-                                                    const unsigned* __restrict__ bbox, double thr,
+                                                    const unsigned* __restrict__ bbox, double thr, double band_scale,
                                                     PairFrame* __restrict__ frames, float4* __restrict__ pts32) {
     const int p = blockIdx.y;
     const PairInfo info = pi[p];
-    const PairFrame fr = frame_from_bbox(bbox + p * 8, thr);
+    const PairFrame fr = frame_from_bbox(bbox + p * 8, thr, band_scale);
     if (blockIdx.x == 0 && threadIdx.x == 0) frames[p] = fr;
     const float qnan = __int_as_float(0x7FFFFFFF);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < info.n_pad / 2; j += gridDim.x * blockDim.x) {
@@ -228,7 +230,7 @@ __device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const P
     if (MODE == MODE_SAMPSON) { Mb = S1 + S2; Smax = 1.1 * (S1 + S2); }
     else                      { Mb = fmin(S1, S2); Smax = fmax(S1, S2); }
     const double G = 1.25 * 16.0 * eps * sqrt(Mb) + 2.0 * (100.0 * eps * eps + 10.0 * eps * Smax + 2.0 * eps * Mb);
-    h.G = __double2float_ru(G);
+    h.G = __double2float_ru(G * fr.band_scale);
     // the bound assumes no FP32 underflow: with an extreme threshold / point spread (s1, s2 ~ 1/B^2 near the denormal
     // range) every evaluation of this hypothesis is sent to the FP64 recheck instead
     if (!(Mb > 1e-28) || !(B < 1e12)) h.G = INFINITY;
@@ -502,6 +504,7 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
             int j = id[k];
             bad_index = bad_index || j < 0 || j >= info.n;       // reported through flag bit 2 / the call's status
             j = j < 0 ? 0 : (j >= info.n ? info.n - 1 : j);     // never read out of the pair
+            RG_ASSERT(j >= 0 && j < info.n && h >= info.hyp_off && h < info.hyp_off + info.H);
             const double4 v = pts[info.pt_off + j];
             X[k] = v.x; Y[k] = v.y; x[k] = v.z; y[k] = v.w;
         }

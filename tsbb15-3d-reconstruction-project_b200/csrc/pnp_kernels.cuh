@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
         for (int k = l; k < NPTS; k += kRowsLanes) {
             int q = idx[(size_t)h * NPTS + k];
             q = q < 0 ? 0 : (q >= N ? N - 1 : q);
+            RG_ASSERT(q >= 0 && q < N && view >= 0 && view < V);
             const size_t gq = pbase + q;
             const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
             const double y0 = y[2 * gq], y1 = y[2 * gq + 1];

@@ -55,6 +55,7 @@ __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pi[mid].item_off <= item) lo = mid; else hi = mid; }
     const PairInfo& info = pi[lo];
     const int local = item - info.item_off;
+    RG_ASSERT(lo >= 0 && lo < P && local >= 0 && info.nsplit >= 1 && info.groups_per_split >= 1);
     const int hb = local / info.nsplit;
     const int sp = local - hb * info.nsplit;
     ScoreItem it;
@@ -64,6 +65,7 @@ __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi
     const int ngroups = info.n_pad / kSub;
     it.g0 = min(sp * info.groups_per_split, ngroups);
     it.g1 = min(it.g0 + info.groups_per_split, ngroups);
+    RG_ASSERT(it.g0 < it.g1 && it.h_base < it.H_end && it.h_base >= info.hyp_off);
     return it;
 }
 
@@ -107,6 +109,7 @@ __device__ __forceinline__ void flag_append(const FlagList& L, unsigned fl, int 
     while (fl) {
         const int b = __ffs(fl) - 1;
         fl &= fl - 1;
+        RG_ASSERT(pos < L.cap && h >= 0 && group_base + b >= 0);
         L.rec[pos++] = make_int2(h, group_base + b);
     }
 }
@@ -164,6 +167,7 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
     if (tid == 0) {
         const uint32_t nb = (uint32_t)min((cur.g1 - cur.g0) * kSub, kChunkPts) * kPtBytes;
         const uint32_t hb = (uint32_t)min(kHypPerBlock, cur.H_end - cur.h_base) * (uint32_t)sizeof(typename Pol::Rec);
+        RG_ASSERT(nb > 0 && nb <= sizeof(st[0].pts) && hb > 0 && hb <= sizeof(st[0].hyp) && nb % 16 == 0 && hb % 16 == 0);
         mbar_expect_tx(&full[0], nb + hb);
         tma_load_1d(st[0].pts, cur_src + (size_t)cur.g0 * (kSub / 2) * kV, nb, &full[0]);
         tma_load_1d(st[0].hyp, hyp32 + cur.h_base, hb, &full[0]);
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, Flag
     auto drain2 = [&](int n) {                      // lanes < n: one band evaluation each, FP64
         if (lane < n) {
             const int4 e = q2[lane];
+            RG_ASSERT(e.y >= 0 && e.y < Fix::n_points(prm, e.z) && (e.w == 0 || e.w == 1));
             const int d = Fix::exact(prm, e.x, e.y, e.z) - e.w;
             if (d) { atomicAdd(&counts[e.x], d); n_flip += 1; }
             n_band += 1;
@@ -335,8 +340,10 @@ __global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, Flag
         int aux = 0;
         if (i < n_rec) {
             r = flist.rec[i];
+            RG_ASSERT(r.x >= 0 && r.x < Htot && r.y >= 0);
             if (!flist.ovf[r.x]) {
                 aux = Fix::pair_of(prm, r.x);
+                RG_ASSERT(r.y * kSub < Fix::n_points(prm, aux) + kSub);
                 Fix::scan(prm, r.x, r.y, aux, band, sign);
                 n_groups += 1;
             }
