@@ -304,6 +304,11 @@ def run_ours(args) -> None:
     stats = rt.last_stats(device=local, stream=stream)
     res_dev = sh.unpack(sh.gather(masks=False))                             # the last device-resident step's answer
     ms_e2e, win_e2e = timed(step_host, args.steps)
+    h2d_rate = rt.last_stats(device=local, stream=stream)["h2d_mb_per_s"] * 1e-3          # GB/s this rank's uploads achieved
+    if dist is not None:
+        t = torch.tensor([h2d_rate], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_rate = float(t.item())
     blk = (sh.h_all_block if world > 1 else sh.h_block).numpy()
     # the end-to-end leg must give the same answer as the device-resident one (same inputs, same seed)
     h_cnt = np.concatenate([blk[q * sh.per * 80:(q + 1) * sh.per * 80][sh.per * 76:].view(np.int32)[: b - a]
@@ -370,6 +375,8 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e, "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(sh.P) * N * 32 * world + (world > 1) * sh.per * 80 * world,
                     "d2h_bytes_per_step": (int(sh.P) * (80 + N)) * world + (world > 1) * world * world * sh.per * 80,
+                    "h2d_gbs_per_rank_measured_min": h2d_rate,
+                    "h2d_gbs_needed_per_rank_to_hide_uploads": int(sh.P) * N * 32 / (ms_dev / args.steps * 1e-3) * 1e-9,
                     "note": "rg_f_ransac_host2 on every rank's page-locked shard (uploads pass by pass on a second stream, "
                             "masks and per-pair results downloaded), then the all-gather of the per-pair results; bytes are "
                             "whole-job sums over the ranks"},

@@ -72,8 +72,8 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 int rg_microbench_run(double* out6, void* stream);
 
 /* out8 = {guard-band groups flagged by the FP32 scorer, band evaluations redone in FP64, decisions changed by that,
- *         hypotheses recounted in FP64 because the flag list was full, hypotheses with an out-of-range sample index, 0,
- *         passes of the last call, kernel launches of the last call}.  Synchronises `stream`. */
+ *         hypotheses recounted in FP64 because the flag list was full, hypotheses with an out-of-range sample index,
+ *         upload rate measured by rg_f_ransac_host* (MB/s, running average), passes of the last call, kernel launches of the last call}.  Synchronises `stream`. */
 int rg_get_last_stats(void* ctx, void* stream, long long* out8);
 
 /* ---- F-matrix RANSAC: replaces the loop of fun.getFFromLabCode (fun.py:303-328), which calls

@@ -462,7 +462,7 @@ int rg_f_last_hypotheses_dev(void* ctx, const int** counts_dev, const double** F
 
 // out[0] guard-band groups flagged, [1] band evaluations re-done in FP64, [2] decisions changed by the recheck,
 // [3] hypotheses recounted in FP64 after a flag-list overflow, [4] hypotheses with a sample index out of range,
-// [6] passes of the last call, [7] kernel launches of the last call.  Synchronises the stream.
+// [5] upload rate measured by the host entry point (MB/s, running average), [6] passes of the last call, [7] kernel launches of the last call.  Synchronises the stream.
 int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
     RG_CHECK_ARG(ctx != nullptr && out8 != nullptr, "null argument");
     Ctx* c = (Ctx*)ctx;
@@ -473,6 +473,7 @@ int rg_get_last_stats(void* ctx, void* stream, long long* out8) {
         const unsigned long long* s = (const unsigned long long*)c->h_stats.ptr;
         for (int i = 0; i < 6; ++i) out8[i] = (long long)s[i];
     }
+    out8[5] = (long long)(c->rate_h2d_bytes_per_s * 1e-6);        // measured upload rate of the host entry point, MB/s
     out8[6] = c->last_passes;
     out8[7] = c->last_stats[7];
     return RG_OK;

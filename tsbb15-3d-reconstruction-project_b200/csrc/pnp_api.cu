@@ -153,11 +153,13 @@ static int pnp_ransac_dev(Ctx* c, cudaStream_t st, int V, const double* X, const
     int2* best = (int2*)c->best.ptr;
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     if (mask == nullptr) {                            // nothing follows the argmax: it publishes the winning poses itself
-        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys,
-                                         (const double*)c->pose64.ptr, 12, Rt, best_idx, best_count);
+        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, (const unsigned char*)c->flags.ptr,
+                                         (unsigned long long*)c->stats.ptr, keys, (const double*)c->pose64.ptr, 12, Rt, best_idx,
+                                         best_count);
         c->last_stats[7] += 1;
     } else {
-        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, nullptr, nullptr, keys);
+        argmax_counts<<<V, 256, 0, st>>>((const int*)c->counts_ptr, pi, best, (const unsigned char*)c->flags.ptr,
+                                         (unsigned long long*)c->stats.ptr, keys);
         const int nbx = std::max(1, std::min(c->sm_count * 4, ceil_div(std::max(plan.maxN, 1), 256)));
         pnp_finish<<<dim3(nbx, V), 256, 0, st>>>(X, y, pi, (const double*)c->pose64.ptr, best, thr2, mask, Rt, best_idx,
                                                 best_count);
@@ -273,6 +275,12 @@ int rg_pnp_ransac_batched_host(void* ctx, void* stream, int V, const double* X, 
     if (poses && H) RG_CUDA(cudaMemcpyAsync(poses, c->pose64.ptr, sizeof(double) * 12 * H, cudaMemcpyDeviceToHost, st));
     if (flags && H) RG_CUDA(cudaMemcpyAsync(flags, c->flags.ptr, H, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
+    // sample indices are validated where they are read (the solver clamps them and sets flag bit 2): no host pass over idx
+    if (c->h_stats.ptr && ((const unsigned long long*)c->h_stats.ptr)[4] != 0) {
+        set_error("invalid argument: %llu hypotheses have a sample index outside [0, N) of their view",
+                  ((const unsigned long long*)c->h_stats.ptr)[4]);
+        return RG_ERR_ARG;
+    }
     return RG_OK;
 }
 

@@ -327,9 +327,11 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
     const int cb = j & 3;                      // which component of the homogeneous world point
 
     double w[ROWS], v[12];
+    bool bad_index = false;
 #pragma unroll
     for (int k = 0; k < NPTS; ++k) {
         int q = idx[(size_t)h * NPTS + k];
+        bad_index = bad_index || q < 0 || q >= N;                 // reported through flag bit 2 / the call's status
         q = q < 0 ? 0 : (q >= N ? N - 1 : q);
         const size_t gq = pbase + q;
         const double Xh[4] = {X[3 * gq], X[3 * gq + 1], X[3 * gq + 2], 1.0};
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kJacobiThreads) pnp_solve_jacobi(const double*
         // minimiser not unique: sigma_11 ~ sigma_12 relative to sigma_1
         if (!(sqrt(s1) - sqrt(s0) > 1e-9 * sqrt(smax))) fl |= 1;
         if (!ok) fl |= 2;
+        if (bad_index) fl |= 4;                   // a sample index outside [0, N) of the view: clamped, the host call fails
         flags[h] = fl;
         make_pose32(Rt, fr[view], pose32 + h);
     }
@@ -428,9 +431,12 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
     const size_t pbase = (size_t)pi[view].pt_off;
 
     // ---- 0. design matrix: rows r_l (x) Xh_k, r_l the rows of [y_k]_x -------------------------------------------
+    if (act && l == 0) sc[2] = 0.0;
+    __syncwarp();
     if (act) {
         for (int k = l; k < NPTS; k += kRowsLanes) {
             int q = idx[(size_t)h * NPTS + k];
+            if (q < 0 || q >= N) sc[2] = 1.0;                          // (benign race: every writer stores the same value)
             q = q < 0 ? 0 : (q >= N ? N - 1 : q);
             RG_ASSERT(q >= 0 && q < N && view >= 0 && view < V);
             const size_t gq = pbase + q;
@@ -631,6 +637,7 @@ __global__ void __launch_bounds__(kRowsThreads) pnp_solve_rows(const double* __r
         // minimiser not unique: sigma_11 ~ sigma_12 relative to sigma_1
         if (!(sqrt(s1) - sqrt(s0) > 1e-9 * sqrt(smax))) fl |= 1;
         if (!ok) fl |= 2;
+        if (sc[2] != 0.0) fl |= 4;                // a sample index outside [0, N) of the view: clamped, the host call fails
         flags[h] = fl;
         make_pose32(Rt, fr[view], pose32 + h);
     }

@@ -91,7 +91,7 @@ def last_stats(device=None, stream=0) -> dict:
     out = (C.c_longlong * 8)()
     cabi.check(lib.rg_get_last_stats(_vp(cabi.context(device)), _vp(stream), out))
     return {"recheck_groups": out[0], "band_evals": out[1], "flips": out[2], "overflow": out[3], "bad_index_hyps": out[4],
-            "passes": out[6], "launches": out[7]}
+            "h2d_mb_per_s": out[5], "passes": out[6], "launches": out[7]}
 
 
 def f_ransac_batched(pts_list, idx_list, thr=1.5, mode=MODE_EPI_MAX, tie_mode=TIE_FIRST, solver=SOLVER_QR,
@@ -231,8 +231,7 @@ def pnp_ransac(X, y, idx, thr2, n_sel=None, score_path=SCORE_FP32_GUARDED, want_
         raise ValueError("idx must be (H, n)")
     H, n = idx.shape
     N = X.shape[0]
-    if idx.size and (idx.min() < 0 or idx.max() >= N):
-        raise ValueError("sample index out of range")
+    # (sample indices are range-checked on the device where they are read: the library call fails with ValueError)
     n_sel = N if n_sel is None else int(n_sel)
     best_idx = np.full(1, -1, dtype=np.int32)
     best_count = np.zeros(1, dtype=np.int32)
@@ -277,8 +276,6 @@ def pnp_ransac_batched(X_list, y_list, idx_list, thr2, n_vote=None, score_path=S
             raise ValueError(f"view {v}: X and y must have the same number of rows")
         if ids[v].ndim != 2 or ids[v].shape[1] != n:
             raise ValueError("every idx must be (H, n) with the same n")
-        if ids[v].size and (ids[v].min() < 0 or ids[v].max() >= Xs[v].shape[0]):
-            raise ValueError(f"view {v}: sample index out of range")
         view_off[v + 1] = view_off[v] + Xs[v].shape[0]
         hyp_off[v + 1] = hyp_off[v] + ids[v].shape[0]
     N, H = int(view_off[-1]), int(hyp_off[-1])
