@@ -131,6 +131,10 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         }
         gps_target = best_gps;
     }
+    {   // experiment hook: RG_FORCE_GPS=<groups per item> overrides the planner (tools/r2_eighth_probe.py sweeps it)
+        static const long long forced = [] { const char* e = getenv("RG_FORCE_GPS"); return e ? atoll(e) : 0ll; }();
+        if (forced > 0) gps_target = forced;
+    }
     long long item_off = 0;
     for (int p = 0; p < P; ++p) {
         PairInfo& o = pi[p];
