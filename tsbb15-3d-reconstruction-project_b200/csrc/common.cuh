@@ -223,6 +223,9 @@ struct Ctx {
     static constexpr int kMaxSlices = 8;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> pass_ready;           // one per pass of the host entry point: its inputs have arrived
+    std::vector<cudaEvent_t> pass_done;            // ... its kernels have finished (the mask download of pass k overlaps pass k+1)
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t d2h_done = nullptr;
     cudaEvent_t copy_gate = nullptr;               // recorded on the caller's stream before the first upload
     int opt_host_slices = 0;                       // option 2: 0 = automatic, n >= 1 = force n sub-batches
     bool accumulate_stats = false;                 // sub-batches after the first add to the call's statistics

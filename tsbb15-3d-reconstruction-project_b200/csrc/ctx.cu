@@ -129,6 +129,9 @@ int rg_shutdown(void* ctx) {
         if (c->staging_free[i]) cudaEventDestroy(c->staging_free[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
     for (cudaEvent_t e : c->pass_ready) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->pass_done) cudaEventDestroy(e);
+    if (c->d2h_done) cudaEventDestroy(c->d2h_done);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (int i = 0; i < 4; ++i)
         if (c->rate_ev[i]) cudaEventDestroy(c->rate_ev[i]);
     p2p_release(c);

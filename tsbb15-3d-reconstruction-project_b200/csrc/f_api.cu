@@ -571,6 +571,18 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     }
     for (int k = 0; k < 4; ++k)
         if (!c->rate_ev[k]) RG_CUDA(cudaEventCreate(&c->rate_ev[k]));
+    // the inlier masks of pass k travel back on a third stream while pass k+1 is scored (205 MB for the config-5 sweep:
+    // 3.7 ms at the end of the call otherwise)
+    const bool stream_masks = mask != nullptr && S > 1;
+    if (stream_masks) {
+        if (!c->d2h_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        if (!c->d2h_done) RG_CUDA(cudaEventCreateWithFlags(&c->d2h_done, cudaEventDisableTiming));
+        while ((int)c->pass_done.size() < S) {
+            cudaEvent_t e;
+            RG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->pass_done.push_back(e);
+        }
+    }
 
     double* d_pts = (double*)c->d_in_a.ptr;
     int* d_ix = seeded ? nullptr : (int*)c->d_in_b.ptr;
@@ -622,15 +634,26 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         if (counts && Hk) RG_CUDA(cudaMemcpyAsync(counts + h0, c->counts_ptr, sizeof(int) * Hk, cudaMemcpyDeviceToHost, st));
         if (F_all && Hk) RG_CUDA(cudaMemcpyAsync(F_all + 9 * h0, c->F64.ptr, sizeof(double) * 9 * Hk, cudaMemcpyDeviceToHost, st));
         if (flags && Hk) RG_CUDA(cudaMemcpyAsync(flags + h0, c->flags.ptr, Hk, cudaMemcpyDeviceToHost, st));
+        if (stream_masks) {
+            const size_t n0 = (size_t)pair_off[p0], n1 = (size_t)pair_off[p1];
+            RG_CUDA(cudaEventRecord(c->pass_done[k], st));
+            RG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->pass_done[k], 0));
+            if (n1 > n0)
+                RG_CUDA(cudaMemcpyAsync(mask + n0, (unsigned char*)c->d_out_c.ptr + n0, n1 - n0, cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
     }
     c->last_stats[7] = launches;
     c->last_passes = S;
-    if (rc) { cudaStreamSynchronize(st); if (S > 1) cudaStreamSynchronize(cs); return rc; }
+    if (rc) { cudaStreamSynchronize(st); if (S > 1) cudaStreamSynchronize(cs); if (stream_masks) cudaStreamSynchronize(c->d2h_stream); return rc; }
+    if (stream_masks) {                               // the caller's stream also waits for the mask downloads
+        RG_CUDA(cudaEventRecord(c->d2h_done, c->d2h_stream));
+        RG_CUDA(cudaStreamWaitEvent(st, c->d2h_done, 0));
+    }
     RG_CUDA(cudaEventRecord(c->rate_ev[3], st));
     RG_CUDA(cudaMemcpyAsync(best_idx, d_idx, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_count, d_cnt, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(best_F, c->d_out_b.ptr, sizeof(double) * 9 * (size_t)P, cudaMemcpyDeviceToHost, st));
-    if (mask && Ntot) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_c.ptr, Ntot, cudaMemcpyDeviceToHost, st));
+    if (mask && Ntot && !stream_masks) RG_CUDA(cudaMemcpyAsync(mask, c->d_out_c.ptr, Ntot, cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     {   // measured rates for the next call's sub-batch model (exponential average; uploads of < 1 MB say nothing)
         float ms_up = 0.f, ms_run = 0.f;
