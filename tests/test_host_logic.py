@@ -102,12 +102,20 @@ def _hyp32_model(F, c1, c2, thr, B):
     Ft = Ft / np.sum(np.abs(Ft) * np.outer(w, w))
     a = np.abs(Ft)
     rho = a @ w                      # rho0, rho1 (rows), w-weighted
-    kap = a.T @ w                    # kap0, kap1 (columns)
+    # image-2 normal l2 = (f0 x0 + f3 x1 + f6, f1 x0 + f4 x1 + f7) rotated so that its second component loses the x0 term
+    f = Ft.ravel()
+    hh = np.hypot(f[0], f[1])
+    if hh > 0:
+        g = np.array([hh, (f[0] * f[3] + f[1] * f[4]) / hh, (f[0] * f[6] + f[1] * f[7]) / hh,
+                      (f[0] * f[4] - f[1] * f[3]) / hh, (f[0] * f[7] - f[1] * f[6]) / hh])
+    else:
+        g = np.array([0.0, f[3], f[6], f[4], f[7]])
+    kap = np.array([abs(g[0]) * B + abs(g[1]) * B + abs(g[2]), abs(g[3]) * B + abs(g[4])])
     S1, S2 = rho[0] ** 2 + rho[1] ** 2, kap[0] ** 2 + kap[1] ** 2
     eps = 2.0 ** -24
     Mb, Smax = min(S1, S2), max(S1, S2)
     G = 1.25 * 16 * eps * np.sqrt(Mb) + 2 * (100 * eps * eps + 10 * eps * Smax + 2 * eps * Mb)
-    return Ft, G
+    return Ft, g, G
 
 
 def test_guard_band_dominates_fp32_error(rg):
@@ -125,16 +133,17 @@ def test_guard_band_dominates_fp32_error(rg):
     worst = 0.0
     for sel in idx:
         F = orc.fmatrix_stls(p1[:, sel], p2[:, sel])
-        Ft, G = _hyp32_model(F, c[:2], c[2:], thr, B)
+        Ft, g64, G = _hyp32_model(F, c[:2], c[2:], thr, B)
         f = Ft.astype(np.float32).ravel()
+        g = g64.astype(np.float32)
         x0, x1, y0, y1 = x32[:, 0], x32[:, 1], y32[:, 0], y32[:, 1]
         bc = lambda v: np.full_like(x0, v)
         l1x = _fma32(bc(f[0]), y0, _fma32(bc(f[1]), y1, bc(f[2])))
         l1y = _fma32(bc(f[3]), y0, _fma32(bc(f[4]), y1, bc(f[5])))
         l1z = _fma32(bc(f[6]), y0, _fma32(bc(f[7]), y1, bc(f[8])))
         r = _fma32(l1x, x0, _fma32(l1y, x1, l1z))
-        l2x = _fma32(bc(f[0]), x0, _fma32(bc(f[3]), x1, bc(f[6])))
-        l2y = _fma32(bc(f[1]), x0, _fma32(bc(f[4]), x1, bc(f[7])))
+        l2x = _fma32(bc(g[0]), x0, _fma32(bc(g[1]), x1, bc(g[2])))       # rotated normal: |l2'| = |l2|, one FMA fewer
+        l2y = _fma32(bc(g[3]), x1, bc(g[4]))
         s1 = _fma32(l1x, l1x, (l1y * l1y).astype(np.float32))
         s2 = _fma32(l2x, l2x, (l2y * l2y).astype(np.float32))
         q32 = _fma32(r, r, -np.minimum(s1, s2)).astype(np.float64)

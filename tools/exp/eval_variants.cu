@@ -189,6 +189,109 @@ __device__ __forceinline__ void eval_r_given(const H2 (&H)[K], const float4* __r
     }
 }
 
+// ---- 16 packed operations per evaluation pair (round 2 experiment): s2 = |l2|^2 is invariant under a per-hypothesis rotation
+// of (l2x, l2y), chosen so that l2y' loses its x0 term: l2x' = c x0 + d x1 + e, l2y' = a x1 + b (3 FMA instead of 4); r comes
+// from the l1 side as before.  Coefficients: f[0..8] and g[0..4] = (c, d, e, a, b) ----
+struct H3 { float f[9]; float g[5]; };
+template <int K>
+__device__ __forceinline__ void eval_rot(const H3 (&H)[K], const float4* __restrict__ pr, unsigned (&cnt)[K], float (&minabs)[K]) {
+    const float4 X = pr[0], Y = pr[1];
+    const float2 x0 = make_float2(X.x, X.y), x1 = make_float2(X.z, X.w);
+    const float2 y0 = make_float2(Y.x, Y.y), y1 = make_float2(Y.z, Y.w);
+    float2 l1x[K], l1y[K], l1z[K], l2x[K], l2y[K], r[K], s1[K], s2[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l1x[k] = ffma2_sbs(H[k].f[1], y1, H[k].f[2]);
+        l1y[k] = ffma2_sbs(H[k].f[4], y1, H[k].f[5]);
+        l1z[k] = ffma2_sbs(H[k].f[7], y1, H[k].f[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l1x[k] = ffma2_sbc(H[k].f[0], y0, l1x[k]);
+        l1y[k] = ffma2_sbc(H[k].f[3], y0, l1y[k]);
+        l1z[k] = ffma2_sbc(H[k].f[6], y0, l1z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l2x[k] = ffma2_sbs(H[k].g[1], x1, H[k].g[2]);
+        l2y[k] = ffma2_sbs(H[k].g[3], x1, H[k].g[4]);
+        r[k]   = __ffma2_rn(l1y[k], x1, l1z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        l2x[k] = ffma2_sbc(H[k].g[0], x0, l2x[k]);
+        r[k]   = __ffma2_rn(l1x[k], x0, r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s1[k] = __ffma2_rn(l1x[k], l1x[k], __fmul2_rn(l1y[k], l1y[k]));
+        s2[k] = __ffma2_rn(l2x[k], l2x[k], __fmul2_rn(l2y[k], l2y[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 nm = make_float2(-fminf(s1[k].x, s2[k].x), -fminf(s1[k].y, s2[k].y));
+        const float2 q = __ffma2_rn(r[k], r[k], nm);
+        cnt[k] += __float_as_uint(q.x) >> 31;
+        cnt[k] += __float_as_uint(q.y) >> 31;
+        minabs[k] = fminf(minabs[k], fminf(fabsf(q.x), fabsf(q.y)));
+    }
+}
+
+template <int K, int BLK>
+__global__ void __launch_bounds__(256, BLK) bench_rot(const float4* __restrict__ pts, const float* __restrict__ hyp, int iters,
+                                                      int* __restrict__ out) {
+    __shared__ float4 sp[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sp[i] = pts[i];
+    __syncthreads();
+    H3 H[K];
+    float G[K];
+    unsigned cnt[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float* h = hyp + ((blockIdx.x * 256 + threadIdx.x) * K + k) * 12;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) H[k].f[j] = h[j];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) H[k].g[j] = h[(j + 3) % 9] * 0.75f + h[j] * 0.25f;
+        G[k] = h[9];
+        cnt[k] = 0;
+    }
+    unsigned flags = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int g = 0; g < 64; ++g) {
+            float ma[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) ma[k] = INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) eval_rot<K>(H, sp + (g * 4 + j) * 2, cnt, ma);
+#pragma unroll
+            for (int k = 0; k < K; ++k) flags |= (ma[k] <= G[k] ? 1u : 0u) << (g & 31);
+        }
+    }
+    int s = (int)flags;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += (int)cnt[k];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+template <int K, int BLK>
+static void run_rot(const float4* dp, const float* dh, int* dout, int sms) {
+    const int blocks = sms * 3 * 4;
+    const int iters = 64;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench_rot<K, BLK><<<blocks, 256>>>(dp, dh, iters, dout);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        bench_rot<K, BLK><<<blocks, 256>>>(dp, dh, iters, dout);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    const double evals = (double)blocks * 256 * K * 512 * iters;
+    printf("16-op body (rotated l2) K %d blocks/SM %d: %.3f ms  %.1f Gevals/s  (%s)\n", K, BLK, best, evals / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
+}
+
 constexpr int kPts = 512;      // points per chunk in shared memory (8 KB)
 
 template <int VARIANT, int K>
@@ -265,6 +368,8 @@ int main() {
     float4* dp; float* dh; int* dout;
     cudaMalloc(&dp, kPts * sizeof(float4)); cudaMalloc(&dh, nh * 4); cudaMalloc(&dout, (size_t)blocks * 256 * 4);
     cudaMemcpy(dp, hp, kPts * sizeof(float4), cudaMemcpyHostToDevice); cudaMemcpy(dh, hh, nh * 4, cudaMemcpyHostToDevice);
+    run_rot<2, 3>(dp, dh, dout, prop.multiProcessorCount);
+    run_rot<2, 2>(dp, dh, dout, prop.multiProcessorCount);
     run<200, 2>(dp, dh, dout, blocks);
     run<0, 2>(dp, dh, dout, blocks);
     run<101, 2>(dp, dh, dout, blocks);

@@ -58,14 +58,17 @@ enum : int { SCORE_FP32_GUARDED = 0, SCORE_FP64 = 1 };
 // ---------------------------------------------------------------------------------------------
 // device-side records
 // ---------------------------------------------------------------------------------------------
-// Per hypothesis, FP32 scorer input: F~ = M1^T F M2 scaled to unit weighted abs-sum, plus the
-// rigorous rounding-error band G (see DESIGN.md "guard band").  48 bytes, 16-byte aligned.
+// Per hypothesis, FP32 scorer input: F~ = M1^T F M2 scaled to unit weighted abs-sum (f), the image-2 line normal
+// l2 = (F~^T x~)[:2] ROTATED by the per-hypothesis angle that removes the x0 term of its second component
+// (g = c, d, e, a, b:  l2x' = c x0 + d x1 + e,  l2y' = a x1 + b;  |l2'|^2 = |l2|^2, one FMA fewer per evaluation), and the
+// rigorous rounding-error band G (see DESIGN.md "guard band").  64 bytes, 16-byte aligned.
 struct __align__(16) Hyp32 {
     float f[9];
+    float g[5];
     float G;
-    float pad0, pad1;
+    float pad0;
 };
-static_assert(sizeof(Hyp32) == 48, "Hyp32 layout");
+static_assert(sizeof(Hyp32) == 64, "Hyp32 layout");
 
 // PnP hypothesis for the FP32 scorer: rows P0,P1,P2 (3x4 each, in the normalised frame), band G.
 struct __align__(16) Pose32 {

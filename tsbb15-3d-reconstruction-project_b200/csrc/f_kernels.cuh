@@ -55,13 +55,14 @@ __device__ __forceinline__ int epi_inlier64(const double* __restrict__ F, double
 // Scalar form; op-for-op the same IEEE sequence as the packed form used by the hot kernel.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ float epi_q32(const float* __restrict__ f, float x0, float x1, float y0, float y1) {
+__device__ __forceinline__ float epi_q32(const float* __restrict__ f, const float* __restrict__ g, float x0, float x1, float y0,
+                                         float y1) {
     const float l1x = __fmaf_rn(f[0], y0, __fmaf_rn(f[1], y1, f[2]));
     const float l1y = __fmaf_rn(f[3], y0, __fmaf_rn(f[4], y1, f[5]));
     const float l1z = __fmaf_rn(f[6], y0, __fmaf_rn(f[7], y1, f[8]));
     const float r   = __fmaf_rn(l1x, x0, __fmaf_rn(l1y, x1, l1z));
-    const float l2x = __fmaf_rn(f[0], x0, __fmaf_rn(f[3], x1, f[6]));
-    const float l2y = __fmaf_rn(f[1], x0, __fmaf_rn(f[4], x1, f[7]));
+    const float l2x = __fmaf_rn(g[0], x0, __fmaf_rn(g[1], x1, g[2]));      // rotated image-2 normal: 3 FMA instead of 4
+    const float l2y = __fmaf_rn(g[3], x1, g[4]);
     const float s1  = __fmaf_rn(l1x, l1x, __fmul_rn(l1y, l1y));
     const float s2  = __fmaf_rn(l2x, l2x, __fmul_rn(l2y, l2y));
     const float m   = (MODE == MODE_SAMPSON) ? __fadd_rn(s1, s2) : fminf(s1, s2);
@@ -211,18 +212,38 @@ __device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const P
         const float qnan = __int_as_float(0x7FFFFFFF);
 #pragma unroll
         for (int k = 0; k < 9; ++k) h.f[k] = qnan;
-        h.G = 0.f; h.pad0 = 0.f; h.pad1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) h.g[k] = qnan;
+        h.G = 0.f; h.pad0 = 0.f;
         *out = h;
         return;
     }
     const double inv = 1.0 / phi;
-    double a[9];
+    double a[9], fd[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { a[k] = fabs(ft[k] * inv); h.f[k] = (float)(ft[k] * inv); }
+    for (int k = 0; k < 9; ++k) { fd[k] = ft[k] * inv; a[k] = fabs(fd[k]); h.f[k] = (float)fd[k]; }
+    // l2 = (f0 x0 + f3 x1 + f6, f1 x0 + f4 x1 + f7) rotated by (cos, sin) = (f0, f1) / hypot(f0, f1): the second component
+    // loses its x0 term; |l2'| = |l2| exactly, so s2 and every bound on it carry over with the rotated coefficients
+    double gd[5];
+    {
+        const double hh = sqrt(fd[0] * fd[0] + fd[1] * fd[1]);
+        if (hh > 0.0) {
+            const double ih = 1.0 / hh;
+            gd[0] = hh;
+            gd[1] = (fd[0] * fd[3] + fd[1] * fd[4]) * ih;
+            gd[2] = (fd[0] * fd[6] + fd[1] * fd[7]) * ih;
+            gd[3] = (fd[0] * fd[4] - fd[1] * fd[3]) * ih;
+            gd[4] = (fd[0] * fd[7] - fd[1] * fd[6]) * ih;
+        } else {
+            gd[0] = 0.0; gd[1] = fd[3]; gd[2] = fd[6]; gd[3] = fd[4]; gd[4] = fd[7];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) h.g[k] = (float)gd[k];
     const double rho0 = a[0] * B + a[1] * B + a[2];
     const double rho1 = a[3] * B + a[4] * B + a[5];
-    const double kap0 = a[0] * B + a[3] * B + a[6];
-    const double kap1 = a[1] * B + a[4] * B + a[7];
+    const double kap0 = fabs(gd[0]) * B + fabs(gd[1]) * B + fabs(gd[2]);       // bounds on |l2x'|, |l2y'| over the frame
+    const double kap1 = fabs(gd[3]) * B + fabs(gd[4]);
     const double S1 = rho0 * rho0 + rho1 * rho1;
     const double S2 = kap0 * kap0 + kap1 * kap1;
     const double eps = 5.9604644775390625e-08;   // 2^-24
@@ -234,7 +255,7 @@ __device__ __forceinline__ void make_hyp32(const double* __restrict__ F, const P
     // the bound assumes no FP32 underflow: with an extreme threshold / point spread (s1, s2 ~ 1/B^2 near the denormal
     // range) every evaluation of this hypothesis is sent to the FP64 recheck instead
     if (!(Mb > 1e-28) || !(B < 1e12)) h.G = INFINITY;
-    h.pad0 = 0.f; h.pad1 = 0.f;
+    h.pad0 = 0.f;
     *out = h;
 }
 
@@ -592,8 +613,9 @@ __global__ void __launch_bounds__(128) f8_solve_qr(const double4* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // FP32 packed scorer policy for the epipolar criterion
 // ------------------------------------------------------------------------------------------------
-struct Hyp2 {            // one hypothesis: nine scalar coefficients, broadcast inside FFMA2 (.F32 operand form)
+struct Hyp2 {            // one hypothesis: 9 + 5 scalar coefficients, broadcast inside FFMA2 (.F32 operand form)
     float f[9];
+    float g[5];
 };
 
 template <int MODE>
@@ -607,15 +629,20 @@ struct EpiPolicy {
     __device__ static __forceinline__ void load(const Hyp32* __restrict__ sh, int slot, bool valid, Hyp2& out, float& G) {
         if (valid) {
             const float4* p = reinterpret_cast<const float4*>(sh + slot);
-            const float4 a = p[0], b = p[1], c = p[2];
+            const float4 a = p[0], b = p[1], c = p[2], d = p[3];
             const float f[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
+            const float g[5] = {c.y, c.z, c.w, d.x, d.y};
 #pragma unroll
             for (int k = 0; k < 9; ++k) out.f[k] = f[k];
-            G = c.y;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) out.g[k] = g[k];
+            G = d.z;
         } else {
             const float qnan = __int_as_float(0x7FFFFFFF);
 #pragma unroll
             for (int k = 0; k < 9; ++k) out.f[k] = qnan;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) out.g[k] = qnan;
             G = 0.f;
         }
     }
@@ -644,14 +671,13 @@ struct EpiPolicy {
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            l2x[k] = ffma2_sbs(H[k].f[3], x1, H[k].f[6]);
-            l2y[k] = ffma2_sbs(H[k].f[4], x1, H[k].f[7]);
+            l2x[k] = ffma2_sbs(H[k].g[1], x1, H[k].g[2]);
+            l2y[k] = ffma2_sbs(H[k].g[3], x1, H[k].g[4]);      // rotated normal: no x0 term
             r[k]   = __ffma2_rn(l1y[k], x1, l1z[k]);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            l2x[k] = ffma2_sbc(H[k].f[0], x0, l2x[k]);
-            l2y[k] = ffma2_sbc(H[k].f[1], x0, l2y[k]);
+            l2x[k] = ffma2_sbc(H[k].g[0], x0, l2x[k]);
             r[k]   = __ffma2_rn(l1x[k], x0, r[k]);
         }
 #pragma unroll
@@ -703,7 +729,7 @@ struct EpiFix {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int k = 2 * j + s;
-                const float q = epi_q32<MODE>(hy.f, s ? X.y : X.x, s ? X.w : X.z, s ? Y.y : Y.x, s ? Y.w : Y.z);
+                const float q = epi_q32<MODE>(hy.f, hy.g, s ? X.y : X.x, s ? X.w : X.z, s ? Y.y : Y.x, s ? Y.w : Y.z);
                 const bool valid = flag * kSub + k < info.n;
                 band |= (valid && fabsf(q) <= hy.G ? 1u : 0u) << k;
                 sign |= (__float_as_uint(q) >> 31) << k;

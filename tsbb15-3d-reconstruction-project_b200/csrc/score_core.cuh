@@ -6,7 +6,7 @@
 namespace rg {
 
 #ifndef RG_SCORE_BLOCKS
-#define RG_SCORE_BLOCKS 3
+#define RG_SCORE_BLOCKS 2      // 2 stages x (8 KB points + 32 KB hypothesis records) per block: two blocks per SM, <= 128 registers
 #endif
 #ifndef RG_EPI_CHUNK
 #define RG_EPI_CHUNK 512
@@ -76,7 +76,8 @@ __device__ __forceinline__ ScoreItem decode_item(const PairInfo* __restrict__ pi
 // consecutive correspondences in a register and, once per such word, the warp appends its set flags as dense
 // (hypothesis, group) records to ONE global list (warp-aggregated: REDUX + prefix + one atomicAdd per warp and word, outside
 // the evaluation loop).  If the list is full the hypothesis is marked in `ovf` and recounted entirely in FP64 by the fix-up
-// kernel, so adversarial inputs (everything on the threshold) degrade to the FP64 path instead of failing.
+// kernel, so adversarial inputs (everything on the threshold) degrade to the FP64 path instead of failing (the slots such
+// an append had reserved inside the list are filled with sentinel records).
 struct FlagList {
     int2* rec;                 // {global hypothesis index, group index inside the pair}
     unsigned* n;               // records appended so far (may exceed cap: the excess was not stored)
@@ -104,6 +105,10 @@ __device__ __forceinline__ void flag_append(const FlagList& L, unsigned fl, int 
     unsigned pos = base + (unsigned)(incl - nb);
     if (base + (unsigned)tot > L.cap || base + (unsigned)tot < base) {      // list full: FP64 recount of this hypothesis
         L.ovf[h] = 1;
+        // the part of [base, base + tot) that lies inside the list is counted as present by the fix-up (it reads
+        // min(n, cap) records): fill it with sentinels, or it would re-apply whatever an earlier call left there
+        for (int k = 0; k < nb; ++k)
+            if (pos + (unsigned)k < L.cap && base + (unsigned)tot >= base) L.rec[pos + k] = make_int2(-1, -1);
         return;
     }
     while (fl) {
@@ -340,8 +345,8 @@ __global__ void __launch_bounds__(256) fixup_list(typename Fix::Params prm, Flag
         int aux = 0;
         if (i < n_rec) {
             r = flist.rec[i];
-            RG_ASSERT(r.x >= 0 && r.x < Htot && r.y >= 0);
-            if (!flist.ovf[r.x]) {
+            RG_ASSERT(r.x >= -1 && r.x < Htot && (r.x < 0 || r.y >= 0));
+            if (r.x >= 0 && !flist.ovf[r.x]) {
                 aux = Fix::pair_of(prm, r.x);
                 RG_ASSERT(r.y * kSub < Fix::n_points(prm, aux) + kSub);
                 Fix::scan(prm, r.x, r.y, aux, band, sign);
