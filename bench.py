@@ -324,7 +324,7 @@ def run_ours(args) -> None:
     pairs_per_pass = sh.P / max(dev_stats["passes"], 1)
     evals_per_pass = pairs_per_pass * N * H
     achieved_tflops = FLOP_PER_F_EVAL * evals_per_pass / (score_ms * 1e-3) * 1e-12 if score_ms > 0 else None
-    alg_bytes = pairs_per_pass * (16.0 * N + 48.0 * H + 4.0 * H)
+    alg_bytes = pairs_per_pass * (16.0 * N + 64.0 * H + 4.0 * H)      # FP32 points + 64-byte hypothesis records + counts
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
@@ -392,7 +392,7 @@ def run_ours(args) -> None:
                          "peak_source": "FFMA/FFMA2 chain micro-benchmark run on this GPU at start of bench.py "
                                         "(MEASURED_PEAKS.json has no FP32 figure)",
                          "algorithmic_flop_per_eval": FLOP_PER_F_EVAL,
-                         "executed_fp32_lane_ops_per_eval": 17,
+                         "executed_fp32_lane_ops_per_eval": 16,
                          "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                                  "achieved_gbs": alg_bytes / (score_ms * 1e-3) * 1e-9 if score_ms > 0 else None,
                                  "peak_gbs": hbm_peak}},

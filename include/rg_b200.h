@@ -61,7 +61,10 @@ int rg_host_free(void* p);
  * option 8 = test hook: capacity of the guard-band flag list in records (0 = automatic); a small value forces the
  *            FP64 recount of the hypotheses whose flags did not fit; results do not depend on it
  * option 9 = guard-band safety factor x 1000 (default 1000 = the proven FP32 rounding bound): a wider band sends more
- *            evaluations to the FP64 recheck (results do not depend on it); measures the fix-up cost of a less accurate scorer */
+ *            evaluations to the FP64 recheck (results do not depend on it); measures the fix-up cost of a less accurate scorer
+ * option 10 = pass pipelining of F calls that run in several passes (default 1): the fix-up / selection / mask kernels of
+ *            pass k run on a second stream while pass k+1 is solved and scored; 0 = one stream, strictly in order
+ *            (results do not depend on it; the caller's stream sees the whole call complete either way) */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the PASSES since the last read
  * (at most 256 passes are remembered; *out_calls = passes covered); synchronises `stream` */

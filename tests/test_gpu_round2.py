@@ -364,6 +364,56 @@ def test_sharded_and_split_classes_world_size_1(rg, torch):
     assert r2["best_idx"] == r["best_idx"] and np.array_equal(r2["mask"], r["mask"]) and np.array_equal(r2["F"], r["F"])
 
 
+def test_pipelined_passes_equal_serial_passes(rt, rg, torch):
+    """Calls of several passes run the fix-up / selection / mask kernels of pass k on a second stream while pass k+1 is solved
+    and scored (option 10, two sets of per-pass workspaces).  Every output must be identical to the strictly serial order and
+    to the single-pass call, through the host entry point and the device entry point, for both tie rules, with ragged
+    pairs, an odd number of passes and calls repeated back to back (the sets are reused across calls)."""
+    from tsbb15_b200 import device as dv
+    sizes = [5000, 3000, 4100, 2048, 900, 7000, 1234]
+    hyps = [700, 300, 513, 1100, 64, 900, 257]
+    pairs = [rg.synth.two_view(n, seed=80 + k)[0] for k, n in enumerate(sizes)]
+    for tie in (rg.TIE_FIRST, rg.TIE_REFERENCE):
+        ref = rt.f_ransac_batched(pairs, None, n_hyp=hyps, sample_seed=5, want_mask=True, tie_mode=tie)
+        assert rt.last_stats()["passes"] == 1
+        outs = []
+        try:
+            rt.set_option(6, 1)                              # every pair its own pass
+            for piped in (1, 0, 1, 1):
+                rt.set_option(10, piped)
+                outs.append(rt.f_ransac_batched(pairs, None, n_hyp=hyps, sample_seed=5, want_mask=True, tie_mode=tie))
+                assert rt.last_stats()["passes"] == len(pairs)
+        finally:
+            rt.set_option(6, 0)
+            rt.set_option(10, 1)
+        for o in outs:
+            assert np.array_equal(o["best_idx"], ref["best_idx"]) and np.array_equal(o["best_count"], ref["best_count"])
+            assert np.array_equal(o["F"], ref["F"])
+            assert all(np.array_equal(a, b) for a, b in zip(o["mask"], ref["mask"]))
+    # device-resident entry point: one call, its passes pipelined internally; guard-band statistics must also agree
+    dev = torch.device("cuda", 0)
+    d_pts = torch.from_numpy(np.concatenate(pairs)).to(dev)
+    po, ho = dv.offsets(sizes), dv.offsets(hyps)
+    res = {}
+    try:
+        for label, opt6, opt10 in (("single", 0, 1), ("piped", 1, 1), ("serial", 1, 0), ("piped2", 1, 1)):
+            rt.set_option(6, opt6)
+            rt.set_option(10, opt10)
+            o = dv.FOutputs(len(sizes), int(po[-1]), want_mask=True)
+            dv.f_ransac(d_pts, po, None, ho, o, seed=9, tie_mode=rg.TIE_REFERENCE)
+            st = rt.last_stats()
+            res[label] = (o.best_idx.cpu().numpy(), o.best_count.cpu().numpy(), o.F.cpu().numpy(), o.mask.cpu().numpy(),
+                          st["recheck_groups"], st["band_evals"], st["flips"])
+            assert st["passes"] == (len(sizes) if opt6 else 1)
+    finally:
+        rt.set_option(6, 0)
+        rt.set_option(10, 1)
+    for label in ("piped", "serial", "piped2"):
+        for a, b in zip(res[label][:4], res["single"][:4]):
+            assert np.array_equal(a, b), label
+        assert res[label][4:] == res["single"][4:], (label, res[label][4:], res["single"][4:])
+
+
 def test_two_devices_in_one_process(rg, torch):
     """One process driving two GPUs (the scorer's dynamic-shared-memory attribute and occupancy are per
     device): the same batch on both devices gives identical results."""

@@ -7,8 +7,9 @@ import torch
 from tsbb15_b200 import device as dv, parallel
 d3, _ = dv.synth_two_view(1, 100000, first_pair=0, seed_base=3000)
 sp = parallel.SplitHypothesesF(d3[0], 16384, sample_seed=20261018)
-sp.lo, sp.hi = 3 * 2048, 4 * 2048                 # pretend to be rank 3 of 8
-sp.hyp_off = np.array([0, 2048], dtype=np.int32)
+W = int(os.environ.get("R2_WORLD", "8"))          # pretend to be rank W//2 of W
+sp.lo, sp.hi = (W // 2) * (16384 // W), (W // 2 + 1) * (16384 // W)
+sp.hyp_off = np.array([0, 16384 // W], dtype=np.int32)
 for _ in range(3):
     sp.run(thr=1.5, want_mask=True)
 torch.cuda.synchronize()
@@ -17,7 +18,7 @@ e0.record()
 for _ in range(50):
     sp.run(thr=1.5, want_mask=True)
 e1.record(); e1.synchronize()
-print("plain ms", e0.elapsed_time(e1) / 50)
+print("world", W, "gps", os.environ.get("RG_FORCE_GPS", "planner"), "plain ms", e0.elapsed_time(e1) / 50)
 sp.capture(thr=1.5, want_mask=True)
 e0.record()
 for _ in range(50):

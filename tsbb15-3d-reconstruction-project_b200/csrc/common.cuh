@@ -186,6 +186,18 @@ struct Ctx {
     int* counts_ptr = nullptr;                     // inside `state` (valid after f_state_layout of the current pass)
     unsigned char* ovf_ptr = nullptr;
     Buffer gen_idx;                                // device-drawn sample indices of the current pass (seeded calls)
+    // Pass pipelining (F calls of several passes): the fix-up / selection / mask kernels ("tail") of pass k run on a second
+    // stream while pass k+1 is solved and scored — the tail is latency bound (23 % issue active) and one of its blocks fits
+    // next to the scorer's four on every SM.  The per-pass workspaces exist twice; ws_swap() exchanges the named buffers
+    // with this second set at the start of every pipelined pass, so all the code below keeps using c->F64, c->state, ...
+    struct PassSet { Buffer pair_info, pair_frame, state, pts32, F64, hyp32, flags, flag_list, best, tie_stats; } alt;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t score_done[2] = {nullptr, nullptr};     // recorded on the caller's stream after the scorer of the pass in set i
+    cudaEvent_t tail_done[2] = {nullptr, nullptr};      // recorded on the tail stream after the last tail kernel of that pass
+    bool tail_pending[2] = {false, false};              // tail_done[i] was recorded and nobody has waited for it yet
+    int tail_carve_max = -1;                            // shared-memory carve-out preference of the tail kernels: -1 never set, 0 default, 1 max
+    int ws_slot = 0;                                    // which set is the current one
+    int opt_pipeline = 1;                               // option 10: 0 = passes strictly one after the other on one stream
     // points prepared by the last F pass (RG_FLAG_REUSE_POINTS: score another hypothesis set against the same points)
     const void* prep_pts = nullptr; int prep_P = 0; long long prep_N = 0; double prep_thr = 0.0; unsigned long long prep_hash = 0;
     int last_passes = 0;                           // passes of the last RANSAC call (per-hypothesis results cover the last pass)

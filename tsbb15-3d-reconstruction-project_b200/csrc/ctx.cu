@@ -100,6 +100,7 @@ int rg_init(int device, void** out_ctx) {
     Ctx* c = new Ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (getenv("RG_NOPIPE")) c->opt_pipeline = 0;              // experiment hook (tools/r2_pipe_sweep.sh); rg_set_option(ctx, 10, v) is the API
     for (int i = 0; i < 2; ++i) RG_CUDA(cudaEventCreateWithFlags(&c->staging_free[i], cudaEventDisableTiming));
     *out_ctx = c;
     return RG_OK;
@@ -114,6 +115,14 @@ int rg_shutdown(void* ctx) {
                       &c->flag_list, &c->gen_idx, &c->stats, &c->best, &c->tie_stats, &c->d_in_a, &c->d_in_b, &c->d_in_c, &c->geom, &c->geom_ws, &c->gs_ws, &c->ba_ws, &c->d_out_a, &c->d_out_b,
                       &c->d_out_c, &c->d_out_d, &c->pose64, &c->pose32, &c->X32})
         release(*b);
+    for (Buffer* b : {&c->alt.pair_info, &c->alt.pair_frame, &c->alt.state, &c->alt.pts32, &c->alt.F64, &c->alt.hyp32,
+                      &c->alt.flags, &c->alt.flag_list, &c->alt.best, &c->alt.tie_stats})
+        release(*b);
+    for (int i = 0; i < 2; ++i) {
+        if (c->score_done[i]) cudaEventDestroy(c->score_done[i]);
+        if (c->tail_done[i]) cudaEventDestroy(c->tail_done[i]);
+    }
+    if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
     release_pinned(c->h_stage[0]);
     release_pinned(c->h_stage[1]);
     release_pinned(c->h_stats);
@@ -165,6 +174,8 @@ int rg_device_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
 // option 6: hypothesis x correspondence evaluations per pass of a large RANSAC batch (0 = default 2.7e10)
 // option 7: PnP minimal-sample solver: 0 = Givens QR + row Jacobi, thread per hypothesis (default); 1 = 16-lane group Jacobi
 // option 8: test hook: capacity of the guard-band flag list in records (0 = automatic); a tiny value forces the FP64 recount
+// option 10: 1 (default) = in F calls of several passes the fix-up / selection / mask kernels of pass k run on a second
+//           stream while pass k+1 is solved and scored (two sets of per-pass workspaces); 0 = strictly one after the other
 // option 9: guard-band safety factor x 1000 (default 1000 = the proven FP32 rounding bound); larger values keep every result
 //           exact and only send more evaluations to the FP64 recheck — used to MEASURE what a less accurate scorer
 //           (tensor-core split-precision accumulation) would cost in fix-up time
@@ -220,6 +231,11 @@ int rg_set_option(void* ctx, int option, long long value) {
         if (value < 1000 || value > 100000000ll) { set_error("invalid argument: option 9 (guard-band factor x 1000) must be in [1000, 1e8]"); return RG_ERR_ARG; }
         c->opt_band_scale = (double)value / 1000.0;
         c->prep_pts = nullptr;
+        return RG_OK;
+    }
+    if (option == 10) {
+        if (value != 0 && value != 1) { set_error("invalid argument: option 10 (pass pipelining) must be 0 or 1"); return RG_ERR_ARG; }
+        c->opt_pipeline = (int)value;
         return RG_OK;
     }
     if (option == 8) {

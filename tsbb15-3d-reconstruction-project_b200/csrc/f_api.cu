@@ -76,6 +76,68 @@ struct FCall {
     unsigned long long* keys = nullptr;
 };
 
+// ---- pass pipelining (Ctx::alt, common.cuh) ----
+// pipe = 0: the pass runs entirely on the caller's stream in the current workspace set (single-pass calls: unchanged, the
+//           launch chain stays capturable in a CUDA graph and RG_FLAG_REUSE_POINTS finds its prepared points);
+// pipe = 1: the pass takes the OTHER set, its tail goes to the tail stream behind an event, the caller's stream moves on;
+// pipe = 2: the same for the LAST pass of a call (nothing follows that could hide the tail: it gets its full grid).
+static void ws_swap(Ctx* c) {
+    std::swap(c->pair_info, c->alt.pair_info);   std::swap(c->pair_frame, c->alt.pair_frame);
+    std::swap(c->state, c->alt.state);           std::swap(c->pts32, c->alt.pts32);
+    std::swap(c->F64, c->alt.F64);               std::swap(c->hyp32, c->alt.hyp32);
+    std::swap(c->flags, c->alt.flags);           std::swap(c->flag_list, c->alt.flag_list);
+    std::swap(c->best, c->alt.best);             std::swap(c->tie_stats, c->alt.tie_stats);
+    c->ws_slot ^= 1;
+    c->plan_valid = false;                       // the cached PairInfo table lives in the set that just left
+    c->prep_pts = nullptr;                       // ... and so do the prepared points
+}
+
+// An SM cannot change its L1 / shared-memory split while blocks are resident.  The tail kernels of pass k are still resident
+// when the scorer of pass k+1 arrives; left to the default carve-out they had switched the SM to a smaller shared-memory
+// partition and only three of the scorer's four 49 KB blocks fitted until they drained (measured: scorer 15.41 -> 16.10 ms
+// with the tail beside it, 15.55 ms once the tail kernels ask for the maximum carve-out too; profiles/r02_pipe_sweep.txt).
+// The preference is a per-function attribute: it is switched on for pipelined passes only, so that single-pass calls (and
+// the last pass of a call, whose tail runs alone) keep the large L1 the fix-up's gathers like.
+static int tail_carveout(Ctx* c, bool want_max) {
+    static const int off = [] { const char* e = getenv("RG_TAIL_NO_CARVEOUT"); return e ? atoi(e) : 0; }();     // experiment hook
+    if (off || c->tail_carve_max == (int)want_max) return RG_OK;
+    const int v = want_max ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+    RG_CUDA(cudaFuncSetAttribute(fixup_list<EpiFix<MODE_EPI_MAX>>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(fixup_list<EpiFix<MODE_SAMPSON>>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(f_mask, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(argmax_counts, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(f_tie_stats, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(f_tie_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(f8_solve_qr<MODE_EPI_MAX>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    RG_CUDA(cudaFuncSetAttribute(f8_solve_qr<MODE_SAMPSON>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    c->tail_carve_max = (int)want_max;
+    return RG_OK;
+}
+
+static int pipe_setup(Ctx* c) {
+    if (!c->tail_stream) {
+        static const int low = [] { const char* e = getenv("RG_TAIL_PRIO"); return e ? atoi(e) : 0; }();     // experiment hook
+        int lo_p = 0, hi_p = 0;
+        RG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        RG_CUDA(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, low ? lo_p : 0));
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!c->score_done[i]) RG_CUDA(cudaEventCreateWithFlags(&c->score_done[i], cudaEventDisableTiming));
+        if (!c->tail_done[i]) RG_CUDA(cudaEventCreateWithFlags(&c->tail_done[i], cudaEventDisableTiming));
+    }
+    return RG_OK;
+}
+
+// the caller's stream waits for every tail still in flight (end of a call, or before anything reads a pass's results)
+static int pipe_join(Ctx* c, cudaStream_t st) {
+    for (int i = 0; i < 2; ++i)
+        if (c->tail_pending[i]) {
+            RG_CUDA(cudaStreamWaitEvent(st, c->tail_done[i], 0));
+            c->tail_pending[i] = false;
+        }
+    return RG_OK;
+}
+
 static unsigned long long hash_offsets(const int* off, int n) {
     unsigned long long h = 1469598103934665603ull;
     for (int i = 0; i <= n; ++i) { h ^= (unsigned)off[i]; h *= 1099511628211ull; }
@@ -136,12 +198,21 @@ static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
 // counts / work counter / flag list are already cleared by the pass's memset
 template <int MODE>
 static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
-                          int score_path) {
+                          int score_path, int pipe = 0) {
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
     unsigned long long* stats = (unsigned long long*)c->stats.ptr;
+    cudaStream_t ts = pipe ? c->tail_stream : st;
+    // everything after the scorer (fix-up here, selection and masks in f_select_launch) is the pass's tail
+    auto hand_over = [&]() -> int {
+        if (pipe) {
+            RG_CUDA(cudaEventRecord(c->score_done[c->ws_slot], st));
+            RG_CUDA(cudaStreamWaitEvent(ts, c->score_done[c->ws_slot], 0));
+        }
+        return RG_OK;
+    };
     if (plan.Htot == 0 || plan.Ntot == 0 || (score_path == SCORE_FP32_GUARDED && plan.n_items == 0)) {
         prof_mark(c, st, 3);
-        return RG_OK;
+        return hand_over();
     }
     if (score_path == SCORE_FP32_GUARDED) {
         int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE>>(&bps);
@@ -153,9 +224,17 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Scor
         score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>((const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr,
                                                                         pi, plan.P, plan.n_items, s.counts, fl, s.work);
         prof_mark(c, st, 3);
+        if ((rc = hand_over())) return rc;
         typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
                                          (const double*)c->F64.ptr, pi, (const PairFrame*)c->pair_frame.ptr, plan.P};
-        fixup_list<EpiFix<MODE>><<<fixup_grid(c, plan.evals), 256, 0, st>>>(fp, fl, (int)plan.Htot, s.counts, stats);
+        // next to the following pass's scorer (4 blocks x 128 threads x 96 registers per SM) exactly one 256-thread block
+        // of the fix-up (64 registers) fits: a grid of one block per SM runs beside it instead of ahead of it
+        int fgrid = fixup_grid(c, plan.evals);
+        if (pipe == 1) {
+            static const int forced = [] { const char* e = getenv("RG_TAIL_GRID"); return e ? atoi(e) : 0; }();   // experiment hook
+            fgrid = std::min(fgrid, forced > 0 ? forced : c->sm_count);
+        }
+        fixup_list<EpiFix<MODE>><<<fgrid, 256, 0, ts>>>(fp, fl, (int)plan.Htot, s.counts, stats);
         c->last_stats[7] += 2;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
@@ -163,6 +242,8 @@ static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Scor
                                                                                  pi, thr, MODE, s.counts);
         prof_mark(c, st, 3);
         c->last_stats[7] += 1;
+        int rc = hand_over();
+        if (rc) return rc;
     }
     RG_CUDA(cudaGetLastError());
     return RG_OK;
@@ -202,10 +283,22 @@ static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Sco
 }
 
 // one pass on device pointers; offsets are relative to the pass
-static int f_pass(Ctx* c, cudaStream_t st, const FCall& a) {
+static int f_pass(Ctx* c, cudaStream_t st, const FCall& a, int pipe = 0) {
     FPlan plan;
     int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>(&bps);
     if (rc) return rc;
+    cudaStream_t ts = st;
+    if (c->tail_carve_max >= 0 || pipe == 1)
+        if ((rc = tail_carveout(c, pipe == 1))) return rc;
+    if (pipe) {
+        if ((rc = pipe_setup(c))) return rc;
+        ws_swap(c);
+        if (c->tail_pending[c->ws_slot]) {           // the tail of the pass before last still reads this set
+            RG_CUDA(cudaStreamWaitEvent(st, c->tail_done[c->ws_slot], 0));
+            c->tail_pending[c->ws_slot] = false;
+        }
+        ts = c->tail_stream;
+    }
     if ((rc = f_plan(c, st, a.P, a.pair_off, a.hyp_off, plan, bps, nullptr, a.hyp_first))) return rc;
     for (int p = 0; p < a.P; ++p) {
         const int n = a.pair_off[p + 1] - a.pair_off[p], H = a.hyp_off[p + 1] - a.hyp_off[p];
@@ -241,14 +334,18 @@ static int f_pass(Ctx* c, cudaStream_t st, const FCall& a) {
              : f_solve_launch<MODE_EPI_MAX>(c, st, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair);
     if (rc) return rc;
     prof_mark(c, st, 2);
-    rc = (a.mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, a.pts64, a.thr, a.score_path)
-                                  : f_score_launch<MODE_EPI_MAX>(c, st, plan, s, a.pts64, a.thr, a.score_path);
+    rc = (a.mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, a.pts64, a.thr, a.score_path, pipe)
+                                  : f_score_launch<MODE_EPI_MAX>(c, st, plan, s, a.pts64, a.thr, a.score_path, pipe);
     if (rc) return rc;
-    prof_mark(c, st, 4);
-    if ((rc = f_select_launch(c, st, plan, s, a.pts64, a.thr, a.mode, a.tie_mode, a.mask, a.best_F, a.best_idx, a.best_count,
+    prof_mark(c, ts, 4);
+    if ((rc = f_select_launch(c, ts, plan, s, a.pts64, a.thr, a.mode, a.tie_mode, a.mask, a.best_F, a.best_idx, a.best_count,
                               a.keys)))
         return rc;
-    prof_mark(c, st, 5);
+    prof_mark(c, ts, 5);
+    if (pipe) {
+        RG_CUDA(cudaEventRecord(c->tail_done[c->ws_slot], ts));
+        c->tail_pending[c->ws_slot] = true;
+    }
     return RG_OK;
 }
 
@@ -307,8 +404,12 @@ static FCall f_sub_call(const FCall& a, int p0, int p1, std::vector<int>& po, st
     return s;
 }
 
-// full pipeline on device pointers; asynchronous with respect to the host except for the PairInfo staging
-static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
+// full pipeline on device pointers; asynchronous with respect to the host except for the PairInfo staging.
+// outer = 0: a call of its own — passes are pipelined among themselves when there are several, and the caller's stream has
+//            joined every tail when this returns (stream semantics of a plain sequence of launches);
+// outer = 1 / 2: one sub-batch of the host entry point's loop (not the last / the last): every pass is pipelined with its
+//            neighbours across the sub-batches, nothing is joined and the statistics are not copied — the caller does both.
+static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a, int outer = 0) {
     int rc = f_check_call(a);
     if (rc) return rc;
     RG_CUDA(cudaSetDevice(c->device));
@@ -322,16 +423,26 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
     f_pass_bounds(c, a, bounds);
     const int n_pass = (int)bounds.size() - 1;
     RG_CHECK_ARG(n_pass == 1 || !(a.flags & FLAG_REUSE_POINTS), "RG_FLAG_REUSE_POINTS needs a call that fits one pass");
+    const bool piped = c->opt_pipeline && !(a.flags & FLAG_REUSE_POINTS) && (outer != 0 || n_pass > 1);
     for (int k = 0; k < n_pass; ++k) {
+        const int pipe = !piped ? 0 : ((k == n_pass - 1 && outer != 1) ? 2 : 1);
         if (n_pass == 1) {
-            if ((rc = f_pass(c, st, a))) return rc;
+            rc = f_pass(c, st, a, pipe);
         } else {
             FCall s = f_sub_call(a, bounds[k], bounds[k + 1], po, ho);
-            if ((rc = f_pass(c, st, s))) return rc;
+            rc = f_pass(c, st, s, pipe);
+        }
+        if (rc) {                                     // leave no tail behind an error return
+            if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+            c->tail_pending[0] = c->tail_pending[1] = false;
+            return rc;
         }
     }
     c->last_passes = n_pass;
-    RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    if (outer == 0) {
+        if ((rc = pipe_join(c, st))) return rc;
+        RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    }
     return RG_OK;
 }
 
@@ -574,6 +685,9 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     // the inlier masks of pass k travel back on a third stream while pass k+1 is scored (205 MB for the config-5 sweep:
     // 3.7 ms at the end of the call otherwise)
     const bool stream_masks = mask != nullptr && S > 1;
+    // sub-batches pipelined with each other (their tails on the tail stream) unless per-hypothesis results are copied out
+    // after every sub-batch, which needs the tail finished anyway
+    const bool piped = S > 1 && c->opt_pipeline && !(counts || F_all || flags);
     if (stream_masks) {
         if (!c->d2h_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
         if (!c->d2h_done) RG_CUDA(cudaEventCreateWithFlags(&c->d2h_done, cudaEventDisableTiming));
@@ -619,7 +733,7 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
             rc = f_ransac_dev(c, st, a);
         } else {
             FCall s = f_sub_call(a, p0, p1, po, ho);
-            rc = f_ransac_dev(c, st, s);
+            rc = f_ransac_dev(c, st, s, piped ? (k == S - 1 ? 2 : 1) : 0);
         }
         c->accumulate_stats = false;
         launches += c->last_stats[7];
@@ -636,7 +750,8 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         if (flags && Hk) RG_CUDA(cudaMemcpyAsync(flags + h0, c->flags.ptr, Hk, cudaMemcpyDeviceToHost, st));
         if (stream_masks) {
             const size_t n0 = (size_t)pair_off[p0], n1 = (size_t)pair_off[p1];
-            RG_CUDA(cudaEventRecord(c->pass_done[k], st));
+            // (pipelined: the masks of this sub-batch are complete when the tail stream gets here — f_mask is the last tail kernel)
+            RG_CUDA(cudaEventRecord(c->pass_done[k], piped ? c->tail_stream : st));
             RG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->pass_done[k], 0));
             if (n1 > n0)
                 RG_CUDA(cudaMemcpyAsync(mask + n0, (unsigned char*)c->d_out_c.ptr + n0, n1 - n0, cudaMemcpyDeviceToHost, c->d2h_stream));
@@ -644,7 +759,18 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     }
     c->last_stats[7] = launches;
     c->last_passes = S;
-    if (rc) { cudaStreamSynchronize(st); if (S > 1) cudaStreamSynchronize(cs); if (stream_masks) cudaStreamSynchronize(c->d2h_stream); return rc; }
+    if (rc) {
+        cudaStreamSynchronize(st);
+        if (S > 1) cudaStreamSynchronize(cs);
+        if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+        c->tail_pending[0] = c->tail_pending[1] = false;
+        if (stream_masks) cudaStreamSynchronize(c->d2h_stream);
+        return rc;
+    }
+    if (piped) {                                      // the sub-batches joined nothing and copied no statistics
+        if ((rc = pipe_join(c, st))) return rc;
+        RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    }
     if (stream_masks) {                               // the caller's stream also waits for the mask downloads
         RG_CUDA(cudaEventRecord(c->d2h_done, c->d2h_stream));
         RG_CUDA(cudaStreamWaitEvent(st, c->d2h_done, 0));

@@ -119,7 +119,10 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
         // large batches keep >= kItemsPerBlock items per block (the dynamic tail is half an item); a batch so small that the
         // target sits on its floor may also use fewer, larger items when that fills the grid's rounds better
         const bool small = gps_target == 64;
-        const long long lo = std::max<long long>(16, gps_target / 2), hi = std::min<long long>(ng, small ? gps_target * 2 : gps_target);
+        // (upper end 4 x the floor: with 256-hypothesis items one rank's share of a split pair fills ONE round of the
+        //  592-block grid at 169 groups per item — 0.614 -> 0.572 / 0.326 -> 0.323 / 0.186 -> 0.182 ms for the 1/2, 1/4, 1/8
+        //  shares of config 3, profiles/r02_split_gps_sweep.txt)
+        const long long lo = std::max<long long>(16, gps_target / 2), hi = std::min<long long>(ng, small ? gps_target * 4 : gps_target);
         double best_cost = 1e300;
         long long best_gps = std::min<long long>(ng, gps_target);
         for (long long gps = lo; gps <= hi; ++gps) {

@@ -6,13 +6,13 @@
 namespace rg {
 
 #ifndef RG_SCORE_BLOCKS
-#define RG_SCORE_BLOCKS 2      // 2 stages x (8 KB points + 32 KB hypothesis records) per block: two blocks per SM, <= 128 registers
+#define RG_SCORE_BLOCKS 4      // 128 threads x 4 blocks: 2 stages x (8 KB points + 16 KB hypothesis records) per block, <= 128 registers
 #endif
 #ifndef RG_EPI_CHUNK
 #define RG_EPI_CHUNK 512
 #endif
 #ifndef RG_SCORE_THREADS
-#define RG_SCORE_THREADS 256
+#define RG_SCORE_THREADS 128      // 4 warps per barrier domain: 128 x 4 blocks beats 256 x 2 by 1.7 % (profiles/r02_variant_sweep_rot.txt)
 #endif
 #ifndef RG_HPT
 #define RG_HPT 2
