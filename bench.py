@@ -304,6 +304,16 @@ def run_ours(args) -> None:
     stats = rt.last_stats(device=local, stream=stream)
     res_dev = sh.unpack(sh.gather(masks=False))                             # the last device-resident step's answer
     ms_e2e, win_e2e = timed(step_host, args.steps)
+    # the same step with the passes strictly one after the other on one stream (option 10 = 0): the scorer ALONE on the GPU.
+    # In the timed region above the solver of the next pass and the fix-up / selection / masks of the previous one run beside
+    # it on a second stream, which hides them but slows each scorer launch by ~2 %.
+    rt.set_option(10, 0, device=local)
+    step_dev(0)
+    rt.set_option(1, 1, device=local)
+    ms_serial, _ = timed(step_dev, 1)
+    prof_serial = rt.profile(device=local, stream=stream)
+    rt.set_option(1, 0, device=local)
+    rt.set_option(10, 1, device=local)
     h2d_rate = rt.last_stats(device=local, stream=stream)["h2d_mb_per_s"] * 1e-3          # GB/s this rank's uploads achieved
     if dist is not None:
         t = torch.tensor([h2d_rate], dtype=torch.float64, device=dev)
@@ -388,6 +398,15 @@ def run_ours(args) -> None:
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "traffic_note": (traffic or {}).get("note"),
                          "kernel_ms_per_launch": score_ms, "launches_timed": passes,
+                         "timed_with": "pass pipelining (option 10): head of pass k+1 and tail of pass k-1 run beside the scorer "
+                                       "of pass k on a second stream",
+                         "kernel_alone": {
+                             "kernel_ms_per_launch": prof_serial["score_ms"] / max(prof_serial["calls"], 1),
+                             "frac": (FLOP_PER_F_EVAL * evals_per_pass / (prof_serial["score_ms"] / max(prof_serial["calls"], 1) * 1e-3)
+                                      * 1e-12 / fp32_peak_tflops) if prof_serial["score_ms"] > 0 else None,
+                             "ms_per_step_serial_passes": ms_serial,
+                             "note": "one more step with option 10 = 0 (passes strictly in order on one stream), outside the "
+                                     "timed region: the scorer with the GPU to itself"},
                          "units_per_launch": evals_per_pass,
                          "peak_source": "FFMA/FFMA2 chain micro-benchmark run on this GPU at start of bench.py "
                                         "(MEASURED_PEAKS.json has no FP32 figure)",

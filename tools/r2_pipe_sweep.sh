@@ -10,6 +10,5 @@ PY
 }
 run RG_NOPIPE=1
 run RG_TAIL_GRID=148
-run RG_TAIL_GRID=148 RG_TAIL_NO_CARVEOUT=1
 run RG_TAIL_GRID=111
 run RG_TAIL_GRID=222

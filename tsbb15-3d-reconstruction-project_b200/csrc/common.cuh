@@ -186,14 +186,17 @@ struct Ctx {
     int* counts_ptr = nullptr;                     // inside `state` (valid after f_state_layout of the current pass)
     unsigned char* ovf_ptr = nullptr;
     Buffer gen_idx;                                // device-drawn sample indices of the current pass (seeded calls)
-    // Pass pipelining (F calls of several passes): the fix-up / selection / mask kernels ("tail") of pass k run on a second
-    // stream while pass k+1 is solved and scored — the tail is latency bound (23 % issue active) and one of its blocks fits
-    // next to the scorer's four on every SM.  The per-pass workspaces exist twice; ws_swap() exchanges the named buffers
-    // with this second set at the start of every pipelined pass, so all the code below keeps using c->F64, c->state, ...
+    // Pass pipelining (F calls of several passes): the caller's stream runs the scorers back to back; the solver ("head") of
+    // pass k+1 and the fix-up / selection / mask kernels ("tail") of pass k-1 run on a second stream BESIDE the scorer of pass k
+    // — they are latency bound (23 % issue active) and one of their blocks fits next to the scorer's four on every SM.  The
+    // per-pass workspaces exist twice; ws_swap() exchanges the named buffers with this second set, so all the code keeps
+    // using c->F64, c->state, ... for "the set of the pass being queued".
     struct PassSet { Buffer pair_info, pair_frame, state, pts32, F64, hyp32, flags, flag_list, best, tie_stats; } alt;
     cudaStream_t tail_stream = nullptr;
+    cudaEvent_t head_done[2] = {nullptr, nullptr};      // recorded on the side stream after the solver of the pass in set i
     cudaEvent_t score_done[2] = {nullptr, nullptr};     // recorded on the caller's stream after the scorer of the pass in set i
-    cudaEvent_t tail_done[2] = {nullptr, nullptr};      // recorded on the tail stream after the last tail kernel of that pass
+    cudaEvent_t tail_done[2] = {nullptr, nullptr};      // [0]: recorded on the side stream behind the last tail kernel of a run
+    cudaEvent_t pipe_gate = nullptr;                    // recorded on the caller's stream before the side stream starts a run
     bool tail_pending[2] = {false, false};              // tail_done[i] was recorded and nobody has waited for it yet
     int tail_carve_max = -1;                            // shared-memory carve-out preference of the tail kernels: -1 never set, 0 default, 1 max
     int ws_slot = 0;                                    // which set is the current one
@@ -248,8 +251,11 @@ struct Ctx {
     // optional phase profiling (option 1): CUDA events on the launching stream around the phases of every call
     int opt_profile = 0;
     static constexpr int kProfPhases = 5;          // prepare, solve, score kernel, fixup+repair, select
+    static constexpr int kProfScoreStart = 6;      // extra boundary: the scorer's own start (pipelined passes: the solver ended long before)
+    static constexpr int kProfEvents = 7;          // boundaries 0..5 + the scorer start
     static constexpr int kProfRing = 256;          // calls remembered between two reads
-    cudaEvent_t* prof_ev = nullptr;                // kProfRing * (kProfPhases + 1) events
+    cudaEvent_t* prof_ev = nullptr;                // kProfRing * kProfEvents events
+    int prof_cur = -1;                             // pass opened by the last prof_mark(.., 0) (sequential callers)
     int prof_calls = 0;                            // calls recorded in the ring since profiling was switched on / last read
     bool prof_open = false;                        // boundary 0 of the current call was recorded (ring not full)
     unsigned prof_masks[kProfRing] = {0};          // boundaries recorded per pass
@@ -257,6 +263,8 @@ struct Ctx {
 
 int ensure_pinned(Buffer& b, size_t bytes);
 void prof_mark(Ctx* c, cudaStream_t st, int boundary);   // boundary 0 opens a call, 1..kProfPhases close the phases
+int prof_begin(Ctx* c);                                  // opens a pass explicitly: its ring index, or -1 (off / ring full)
+void prof_mark_at(Ctx* c, cudaStream_t st, int call, int boundary);   // boundary of THAT pass (phases of passes may interleave)
 void release_pinned(Buffer& b);
 int ensure(Buffer& b, size_t bytes);      // grow-only cudaMalloc
 void release(Buffer& b);

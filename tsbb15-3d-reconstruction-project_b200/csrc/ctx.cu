@@ -49,19 +49,24 @@ void release(Buffer& b) {
 // boundary 0 opens a pass (dropped, together with the pass's other boundaries, once the ring is full); boundaries
 // 1..kProfPhases close the phases.  prof_masks[] remembers which boundaries of a pass were recorded, so a pass that
 // failed half-way is skipped by rg_get_profile instead of pairing events of different passes.
-void prof_mark(Ctx* c, cudaStream_t st, int boundary) {
+int prof_begin(Ctx* c) {
+    if (!c->opt_profile || !c->prof_ev) return -1;
+    c->prof_open = c->prof_calls < Ctx::kProfRing;
+    if (!c->prof_open) return -1;
+    c->prof_masks[c->prof_calls] = 0u;
+    return c->prof_calls++;
+}
+
+void prof_mark_at(Ctx* c, cudaStream_t st, int call, int boundary) {
     if (!c->opt_profile || !c->prof_ev) return;
-    if (boundary == 0) {
-        c->prof_open = c->prof_calls < Ctx::kProfRing;
-        if (!c->prof_open) return;
-        c->prof_masks[c->prof_calls] = 0u;
-        c->prof_calls++;
-    }
-    if (!c->prof_open) return;
-    const int call = c->prof_calls - 1;
-    if (call < 0 || call >= Ctx::kProfRing || boundary < 0 || boundary > Ctx::kProfPhases) return;
-    if (cudaEventRecord(c->prof_ev[call * (Ctx::kProfPhases + 1) + boundary], st) == cudaSuccess)
+    if (call < 0 || call >= Ctx::kProfRing || boundary < 0 || boundary >= Ctx::kProfEvents) return;
+    if (cudaEventRecord(c->prof_ev[call * Ctx::kProfEvents + boundary], st) == cudaSuccess)
         c->prof_masks[call] |= 1u << boundary;
+}
+
+void prof_mark(Ctx* c, cudaStream_t st, int boundary) {
+    if (boundary == 0) c->prof_cur = prof_begin(c);
+    prof_mark_at(c, st, c->prof_cur, boundary);
 }
 
 void release_pinned(Buffer& b) {
@@ -119,9 +124,11 @@ int rg_shutdown(void* ctx) {
                       &c->alt.flags, &c->alt.flag_list, &c->alt.best, &c->alt.tie_stats})
         release(*b);
     for (int i = 0; i < 2; ++i) {
+        if (c->head_done[i]) cudaEventDestroy(c->head_done[i]);
         if (c->score_done[i]) cudaEventDestroy(c->score_done[i]);
         if (c->tail_done[i]) cudaEventDestroy(c->tail_done[i]);
     }
+    if (c->pipe_gate) cudaEventDestroy(c->pipe_gate);
     if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
     release_pinned(c->h_stage[0]);
     release_pinned(c->h_stage[1]);
@@ -131,7 +138,7 @@ int rg_shutdown(void* ctx) {
     for (int i = 0; i < 2; ++i)
         if (c->ba_iter_ev[i]) cudaEventDestroy(c->ba_iter_ev[i]);
     if (c->prof_ev) {
-        for (int i = 0; i < Ctx::kProfRing * (Ctx::kProfPhases + 1); ++i) cudaEventDestroy(c->prof_ev[i]);
+        for (int i = 0; i < Ctx::kProfRing * Ctx::kProfEvents; ++i) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
     }
     for (int i = 0; i < 2; ++i)
@@ -186,8 +193,9 @@ int rg_set_option(void* ctx, int option, long long value) {
         c->opt_profile = value != 0;
         c->prof_calls = 0;
         c->prof_open = false;
+        c->prof_cur = -1;
         if (c->opt_profile && !c->prof_ev) {
-            const int n = Ctx::kProfRing * (Ctx::kProfPhases + 1);
+            const int n = Ctx::kProfRing * Ctx::kProfEvents;
             c->prof_ev = new cudaEvent_t[n];
             for (int i = 0; i < n; ++i) RG_CUDA(cudaEventCreate(&c->prof_ev[i]));
         }
@@ -259,11 +267,13 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls) {
     *out_calls = c->prof_calls;
     int complete = 0;
     for (int call = 0; call < c->prof_calls; ++call) {
-        if (c->prof_masks[call] != (1u << (Ctx::kProfPhases + 1)) - 1u) continue;      // pass aborted between two boundaries
-        cudaEvent_t* e = c->prof_ev + call * (Ctx::kProfPhases + 1);
+        const unsigned need = (1u << (Ctx::kProfPhases + 1)) - 1u;
+        if ((c->prof_masks[call] & need) != need) continue;                             // pass aborted between two boundaries
+        cudaEvent_t* e = c->prof_ev + call * Ctx::kProfEvents;
+        const bool own_start = (c->prof_masks[call] >> Ctx::kProfScoreStart) & 1u;     // the scorer's own start was recorded
         for (int k = 0; k < Ctx::kProfPhases; ++k) {
             float ms = 0.f;
-            RG_CUDA(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+            RG_CUDA(cudaEventElapsedTime(&ms, (k == 2 && own_start) ? e[Ctx::kProfScoreStart] : e[k], e[k + 1]));
             out_ms5[k] += ms;
         }
         ++complete;
@@ -271,6 +281,7 @@ int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls) {
     *out_calls = complete;
     c->prof_calls = 0;
     c->prof_open = false;
+    c->prof_cur = -1;
     return RG_OK;
 }
 

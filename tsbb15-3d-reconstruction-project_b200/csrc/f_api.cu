@@ -76,11 +76,9 @@ struct FCall {
     unsigned long long* keys = nullptr;
 };
 
-// ---- pass pipelining (Ctx::alt, common.cuh) ----
-// pipe = 0: the pass runs entirely on the caller's stream in the current workspace set (single-pass calls: unchanged, the
-//           launch chain stays capturable in a CUDA graph and RG_FLAG_REUSE_POINTS finds its prepared points);
-// pipe = 1: the pass takes the OTHER set, its tail goes to the tail stream behind an event, the caller's stream moves on;
-// pipe = 2: the same for the LAST pass of a call (nothing follows that could hide the tail: it gets its full grid).
+// ---- pass pipelining (Ctx::alt, common.cuh; the driver is f_run_piped below) ----
+// Single-pass calls never swap: their launch chain stays on the caller's stream in the current set (capturable in a CUDA graph,
+// RG_FLAG_REUSE_POINTS finds its prepared points).
 static void ws_swap(Ctx* c) {
     std::swap(c->pair_info, c->alt.pair_info);   std::swap(c->pair_frame, c->alt.pair_frame);
     std::swap(c->state, c->alt.state);           std::swap(c->pts32, c->alt.pts32);
@@ -122,9 +120,11 @@ static int pipe_setup(Ctx* c) {
         RG_CUDA(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, low ? lo_p : 0));
     }
     for (int i = 0; i < 2; ++i) {
+        if (!c->head_done[i]) RG_CUDA(cudaEventCreateWithFlags(&c->head_done[i], cudaEventDisableTiming));
         if (!c->score_done[i]) RG_CUDA(cudaEventCreateWithFlags(&c->score_done[i], cudaEventDisableTiming));
         if (!c->tail_done[i]) RG_CUDA(cudaEventCreateWithFlags(&c->tail_done[i], cudaEventDisableTiming));
     }
+    if (!c->pipe_gate) RG_CUDA(cudaEventCreateWithFlags(&c->pipe_gate, cudaEventDisableTiming));
     return RG_OK;
 }
 
@@ -195,58 +195,81 @@ static int f_solve_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const doub
     return RG_OK;
 }
 
+// ---- one pass = three phases that may run on different streams (pass pipelining, see f_run_piped) ----
+//   head : PairInfo plan + memset(state) + [f_bbox, f_normalise] + f8_solve      (needs only the pass's inputs)
+//   score: score_packed                                                          (the FP32-bound 94 % of a pass)
+//   tail : fixup_list + argmax_counts [+ f_tie_stats + f_tie_resolve] + f_mask   (latency bound, needs the scorer's counts)
+struct PassCtl {
+    FCall a;
+    std::vector<int> po, ho;              // storage behind a.pair_off / a.hyp_off when the pass is a sub-range of a call
+    FPlan plan;
+    ScoreState s;
+    FlagList fl{nullptr, nullptr, 0u, nullptr};
+    bool scored = false;                  // the packed scorer ran: its flag list wants the fix-up
+    int slot = 0;                         // workspace set of the pass (Ctx::alt)
+    int prof_call = -1;                   // ring index of the pass's phase events (option 1)
+    cudaEvent_t ready = nullptr;          // optional: the pass's inputs have arrived (host entry point)
+    cudaEvent_t done = nullptr;           // optional: recorded behind the pass's last tail kernel
+};
+
 // counts / work counter / flag list are already cleared by the pass's memset
 template <int MODE>
-static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
-                          int score_path, int pipe = 0) {
+static int f_score_only(Ctx* c, cudaStream_t st, PassCtl& k) {
+    const FPlan& plan = k.plan;
     const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
-    unsigned long long* stats = (unsigned long long*)c->stats.ptr;
-    cudaStream_t ts = pipe ? c->tail_stream : st;
-    // everything after the scorer (fix-up here, selection and masks in f_select_launch) is the pass's tail
-    auto hand_over = [&]() -> int {
-        if (pipe) {
-            RG_CUDA(cudaEventRecord(c->score_done[c->ws_slot], st));
-            RG_CUDA(cudaStreamWaitEvent(ts, c->score_done[c->ws_slot], 0));
-        }
-        return RG_OK;
-    };
-    if (plan.Htot == 0 || plan.Ntot == 0 || (score_path == SCORE_FP32_GUARDED && plan.n_items == 0)) {
-        prof_mark(c, st, 3);
-        return hand_over();
-    }
-    if (score_path == SCORE_FP32_GUARDED) {
+    k.scored = false;
+    if (plan.Htot == 0 || plan.Ntot == 0 || (k.a.score_path == SCORE_FP32_GUARDED && plan.n_items == 0)) return RG_OK;
+    if (k.a.score_path == SCORE_FP32_GUARDED) {
         int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE>>(&bps);
         if (rc) return rc;
-        FlagList fl = flag_list_for(c, s, plan.evals, &rc);
+        k.fl = flag_list_for(c, k.s, plan.evals, &rc);
         if (rc) return rc;
         constexpr size_t smem = score_smem_bytes<EpiPolicy<MODE>>();
         const int grid = std::min(plan.n_items, c->sm_count * bps);
         score_packed<EpiPolicy<MODE>><<<grid, kScoreThreads, smem, st>>>((const float4*)c->pts32.ptr, (const Hyp32*)c->hyp32.ptr,
-                                                                        pi, plan.P, plan.n_items, s.counts, fl, s.work);
-        prof_mark(c, st, 3);
-        if ((rc = hand_over())) return rc;
-        typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)pts64, (const Hyp32*)c->hyp32.ptr,
-                                         (const double*)c->F64.ptr, pi, (const PairFrame*)c->pair_frame.ptr, plan.P};
-        // next to the following pass's scorer (4 blocks x 128 threads x 96 registers per SM) exactly one 256-thread block
-        // of the fix-up (64 registers) fits: a grid of one block per SM runs beside it instead of ahead of it
-        int fgrid = fixup_grid(c, plan.evals);
-        if (pipe == 1) {
-            static const int forced = [] { const char* e = getenv("RG_TAIL_GRID"); return e ? atoi(e) : 0; }();   // experiment hook
-            fgrid = std::min(fgrid, forced > 0 ? forced : c->sm_count);
-        }
-        fixup_list<EpiFix<MODE>><<<fgrid, 256, 0, ts>>>(fp, fl, (int)plan.Htot, s.counts, stats);
-        c->last_stats[7] += 2;
+                                                                        pi, plan.P, plan.n_items, k.s.counts, k.fl, k.s.work);
+        k.scored = true;
     } else {
         const int zs = std::max(1, std::min(64, ceil_div(plan.maxN, 2048)));
-        f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, zs), 128, 0, st>>>((const double4*)pts64, (const double*)c->F64.ptr,
-                                                                                 pi, thr, MODE, s.counts);
-        prof_mark(c, st, 3);
-        c->last_stats[7] += 1;
-        int rc = hand_over();
-        if (rc) return rc;
+        f_score_fp64<<<dim3(ceil_div(plan.maxH, 128), plan.P, zs), 128, 0, st>>>((const double4*)k.a.pts64, (const double*)c->F64.ptr,
+                                                                                 pi, k.a.thr, MODE, k.s.counts);
     }
+    c->last_stats[7] += 1;
     RG_CUDA(cudaGetLastError());
     return RG_OK;
+}
+
+// beside_scorer: the kernel will run NEXT TO the following pass's scorer (4 blocks x 128 threads x 96 registers per SM leave
+// room for exactly one 256-thread, 64-register block): a grid of one block per SM runs beside the scorer instead of ahead of it
+template <int MODE>
+static int f_fixup_launch(Ctx* c, cudaStream_t ts, PassCtl& k, bool beside_scorer) {
+    if (!k.scored) return RG_OK;
+    const FPlan& plan = k.plan;
+    typename EpiFix<MODE>::Params fp{(const float4*)c->pts32.ptr, (const double4*)k.a.pts64, (const Hyp32*)c->hyp32.ptr,
+                                     (const double*)c->F64.ptr, (const PairInfo*)c->pair_info.ptr,
+                                     (const PairFrame*)c->pair_frame.ptr, plan.P};
+    int fgrid = fixup_grid(c, plan.evals);
+    if (beside_scorer) {
+        static const int forced = [] { const char* e = getenv("RG_TAIL_GRID"); return e ? atoi(e) : 0; }();   // experiment hook
+        fgrid = std::min(fgrid, forced > 0 ? forced : c->sm_count);
+    }
+    fixup_list<EpiFix<MODE>><<<fgrid, 256, 0, ts>>>(fp, k.fl, (int)plan.Htot, k.s.counts, (unsigned long long*)c->stats.ptr);
+    c->last_stats[7] += 1;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// scorer + fix-up on one stream (stage entry point rg_epi_score_count_host)
+template <int MODE>
+static int f_score_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
+                          int score_path) {
+    PassCtl k;
+    k.a.pts64 = pts64; k.a.thr = thr; k.a.score_path = score_path;
+    k.plan = plan; k.s = s;
+    int rc = f_score_only<MODE>(c, st, k);
+    if (rc) return rc;
+    prof_mark(c, st, 3);
+    return f_fixup_launch<MODE>(c, st, k, false);
 }
 
 static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const ScoreState& s, const double* pts64, double thr,
@@ -282,34 +305,22 @@ static int f_select_launch(Ctx* c, cudaStream_t st, const FPlan& plan, const Sco
     return RG_OK;
 }
 
-// one pass on device pointers; offsets are relative to the pass
-static int f_pass(Ctx* c, cudaStream_t st, const FCall& a, int pipe = 0) {
-    FPlan plan;
+// head of a pass on stream hs, in the CURRENT workspace set
+static int f_pass_head(Ctx* c, cudaStream_t hs, PassCtl& k) {
+    const FCall& a = k.a;
+    FPlan& plan = k.plan;
     int bps = 1, rc = score_blocks_per_sm<EpiPolicy<MODE_EPI_MAX>>(&bps);
     if (rc) return rc;
-    cudaStream_t ts = st;
-    if (c->tail_carve_max >= 0 || pipe == 1)
-        if ((rc = tail_carveout(c, pipe == 1))) return rc;
-    if (pipe) {
-        if ((rc = pipe_setup(c))) return rc;
-        ws_swap(c);
-        if (c->tail_pending[c->ws_slot]) {           // the tail of the pass before last still reads this set
-            RG_CUDA(cudaStreamWaitEvent(st, c->tail_done[c->ws_slot], 0));
-            c->tail_pending[c->ws_slot] = false;
-        }
-        ts = c->tail_stream;
-    }
-    if ((rc = f_plan(c, st, a.P, a.pair_off, a.hyp_off, plan, bps, nullptr, a.hyp_first))) return rc;
+    if ((rc = f_plan(c, hs, a.P, a.pair_off, a.hyp_off, plan, bps, nullptr, a.hyp_first))) return rc;
     for (int p = 0; p < a.P; ++p) {
         const int n = a.pair_off[p + 1] - a.pair_off[p], H = a.hyp_off[p + 1] - a.hyp_off[p];
         RG_CHECK_ARG(H == 0 || n >= 8, "a pair with hypotheses needs at least 8 correspondences");
     }
     const bool seeded = a.idx == nullptr && plan.Htot > 0;
     if ((rc = f_workspace(c, plan, seeded))) return rc;
-    ScoreState s;
-    if ((rc = score_state_layout(c, a.P, plan.Htot, 8, s))) return rc;
+    if ((rc = score_state_layout(c, a.P, plan.Htot, 8, k.s))) return rc;
     if (a.P == 0) return RG_OK;
-    const PairInfo* pi = (const PairInfo*)c->pair_info.ptr;
+    const ScoreState& s = k.s;
 
     bool reuse = (a.flags & FLAG_REUSE_POINTS) != 0;
     const unsigned long long hsh = hash_offsets(a.pair_off, a.P);
@@ -318,34 +329,116 @@ static int f_pass(Ctx* c, cudaStream_t st, const FCall& a, int pipe = 0) {
                          c->prep_thr == a.thr && c->prep_hash == hsh,
                      "RG_FLAG_REUSE_POINTS: the previous pass on this context prepared different points / threshold");
     }
-    prof_mark(c, st, 0);
+    k.prof_call = prof_begin(c);
+    prof_mark_at(c, hs, k.prof_call, 0);
     // one memset clears the pass's state (the bounding boxes only when the points are prepared in this pass)
     const size_t from = reuse ? s.off_counts : 0;
-    RG_CUDA(cudaMemsetAsync((char*)c->state.ptr + from, 0, s.bytes - from, st));
+    RG_CUDA(cudaMemsetAsync((char*)c->state.ptr + from, 0, s.bytes - from, hs));
     const int* idx = a.idx;                           // NULL: the solver draws its own sample (philox.cuh), no index array exists
     if (!reuse) {
         c->prep_pts = nullptr;
-        if ((rc = f_prepare(c, st, plan, s, a.pts64, a.thr))) return rc;
+        if ((rc = f_prepare(c, hs, plan, s, a.pts64, a.thr))) return rc;
         c->prep_pts = a.pts64; c->prep_P = a.P; c->prep_N = plan.Ntot; c->prep_thr = a.thr; c->prep_hash = hsh;
     }
-    prof_mark(c, st, 1);
+    prof_mark_at(c, hs, k.prof_call, 1);
     rc = (a.mode == MODE_SAMPSON)
-             ? f_solve_launch<MODE_SAMPSON>(c, st, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair)
-             : f_solve_launch<MODE_EPI_MAX>(c, st, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair);
+             ? f_solve_launch<MODE_SAMPSON>(c, hs, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair)
+             : f_solve_launch<MODE_EPI_MAX>(c, hs, plan, a.pts64, idx, a.solver, a.sample_seed, (unsigned)a.first_pair);
     if (rc) return rc;
-    prof_mark(c, st, 2);
-    rc = (a.mode == MODE_SAMPSON) ? f_score_launch<MODE_SAMPSON>(c, st, plan, s, a.pts64, a.thr, a.score_path, pipe)
-                                  : f_score_launch<MODE_EPI_MAX>(c, st, plan, s, a.pts64, a.thr, a.score_path, pipe);
+    prof_mark_at(c, hs, k.prof_call, 2);
+    return RG_OK;
+}
+
+static int f_pass_score(Ctx* c, cudaStream_t st, PassCtl& k) {
+    if (k.a.P == 0) return RG_OK;
+    prof_mark_at(c, st, k.prof_call, Ctx::kProfScoreStart);
+    const int rc = (k.a.mode == MODE_SAMPSON) ? f_score_only<MODE_SAMPSON>(c, st, k) : f_score_only<MODE_EPI_MAX>(c, st, k);
+    prof_mark_at(c, st, k.prof_call, 3);
+    return rc;
+}
+
+static int f_pass_tail(Ctx* c, cudaStream_t ts, PassCtl& k, bool beside_scorer) {
+    if (k.a.P == 0) return RG_OK;
+    const FCall& a = k.a;
+    int rc = (a.mode == MODE_SAMPSON) ? f_fixup_launch<MODE_SAMPSON>(c, ts, k, beside_scorer)
+                                      : f_fixup_launch<MODE_EPI_MAX>(c, ts, k, beside_scorer);
     if (rc) return rc;
-    prof_mark(c, ts, 4);
-    if ((rc = f_select_launch(c, ts, plan, s, a.pts64, a.thr, a.mode, a.tie_mode, a.mask, a.best_F, a.best_idx, a.best_count,
+    prof_mark_at(c, ts, k.prof_call, 4);
+    if ((rc = f_select_launch(c, ts, k.plan, k.s, a.pts64, a.thr, a.mode, a.tie_mode, a.mask, a.best_F, a.best_idx, a.best_count,
                               a.keys)))
         return rc;
-    prof_mark(c, ts, 5);
-    if (pipe) {
-        RG_CUDA(cudaEventRecord(c->tail_done[c->ws_slot], ts));
-        c->tail_pending[c->ws_slot] = true;
+    prof_mark_at(c, ts, k.prof_call, 5);
+    return RG_OK;
+}
+
+// one pass on device pointers, everything on the caller's stream in the current workspace set; offsets are relative to the pass
+static int f_pass(Ctx* c, cudaStream_t st, const FCall& a) {
+    PassCtl k;
+    k.a = a;
+    k.slot = c->ws_slot;
+    int rc;
+    if (c->tail_carve_max > 0 && (rc = tail_carveout(c, false))) return rc;
+    if ((rc = f_pass_head(c, st, k))) return rc;
+    if ((rc = f_pass_score(c, st, k))) return rc;
+    return f_pass_tail(c, st, k, false);
+}
+
+static void ws_use(Ctx* c, int slot) {
+    if (c->ws_slot != slot) ws_swap(c);
+}
+
+// Several passes, software-pipelined over two streams and two workspace sets:
+//
+//   caller's stream :            score(0)            score(1)            score(2)         ...      join
+//   side stream     :  head(0)   head(1)   tail(0)   head(2)   tail(1)   head(3)   tail(2) ...
+//
+// The caller's stream runs the scorers back to back; the side stream's kernels run BESIDE them: the tail of pass k and the head
+// of pass k+2 need the same workspace set, which the side stream's own order serialises.  head(k+1) is queued before tail(k)
+// (tail(k) has to wait for score(k), head(k+1) has not).  jobs[k].ready / .done tie in the host entry point's uploads and mask
+// downloads.  join: the caller's stream waits for the last tail before this returns (otherwise pipe_join() does it later).
+static int f_run_piped(Ctx* c, cudaStream_t st, std::vector<PassCtl>& jobs, bool join) {
+    const int n = (int)jobs.size();
+    if (n == 0) return RG_OK;
+    int rc;
+    if ((rc = pipe_setup(c))) return rc;
+    if ((rc = tail_carveout(c, true))) return rc;
+    cudaStream_t side = c->tail_stream;
+    auto fail = [&](int code) {                       // leave nothing in flight behind an error return
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(side);
+        c->tail_pending[0] = c->tail_pending[1] = false;
+        return code;
+    };
+    if ((rc = pipe_join(c, st))) return rc;           // (a previous unjoined run on this context)
+    RG_CUDA(cudaEventRecord(c->pipe_gate, st));       // the side stream may not overtake what the caller queued before the call
+    RG_CUDA(cudaStreamWaitEvent(side, c->pipe_gate, 0));
+    const int base = c->ws_slot ^ 1;
+    for (int k = 0; k < n; ++k) jobs[k].slot = (base + k) & 1;
+    auto head = [&](int k) -> int {
+        ws_use(c, jobs[k].slot);
+        if (jobs[k].ready) RG_CUDA(cudaStreamWaitEvent(side, jobs[k].ready, 0));
+        int r = f_pass_head(c, side, jobs[k]);
+        if (r) return r;
+        RG_CUDA(cudaEventRecord(c->head_done[jobs[k].slot], side));
+        return RG_OK;
+    };
+    if ((rc = head(0))) return fail(rc);
+    for (int k = 0; k < n; ++k) {
+        PassCtl& j = jobs[k];
+        RG_CUDA(cudaStreamWaitEvent(st, c->head_done[j.slot], 0));
+        ws_use(c, j.slot);
+        if ((rc = f_pass_score(c, st, j))) return fail(rc);
+        RG_CUDA(cudaEventRecord(c->score_done[j.slot], st));
+        if (k + 1 < n && (rc = head(k + 1))) return fail(rc);
+        RG_CUDA(cudaStreamWaitEvent(side, c->score_done[j.slot], 0));
+        ws_use(c, j.slot);
+        if ((rc = f_pass_tail(c, side, j, k + 1 < n))) return fail(rc);
+        if (j.done) RG_CUDA(cudaEventRecord(j.done, side));
     }
+    RG_CUDA(cudaEventRecord(c->tail_done[0], side));
+    c->tail_pending[0] = true;
+    // (the current set is the last pass's: counts_ptr / F64 / flags of rg_f_last_hypotheses_dev and the prepared points)
+    if (join) return pipe_join(c, st);
     return RG_OK;
 }
 
@@ -404,12 +497,10 @@ static FCall f_sub_call(const FCall& a, int p0, int p1, std::vector<int>& po, st
     return s;
 }
 
-// full pipeline on device pointers; asynchronous with respect to the host except for the PairInfo staging.
-// outer = 0: a call of its own — passes are pipelined among themselves when there are several, and the caller's stream has
-//            joined every tail when this returns (stream semantics of a plain sequence of launches);
-// outer = 1 / 2: one sub-batch of the host entry point's loop (not the last / the last): every pass is pipelined with its
-//            neighbours across the sub-batches, nothing is joined and the statistics are not copied — the caller does both.
-static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a, int outer = 0) {
+// full pipeline on device pointers; asynchronous with respect to the host except for the PairInfo staging.  A call of several
+// passes is pipelined (f_run_piped, option 10); the caller's stream has joined every tail when this returns, i.e. it keeps
+// the stream semantics of a plain sequence of launches.
+static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
     int rc = f_check_call(a);
     if (rc) return rc;
     RG_CUDA(cudaSetDevice(c->device));
@@ -423,26 +514,22 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a, int outer = 0) 
     f_pass_bounds(c, a, bounds);
     const int n_pass = (int)bounds.size() - 1;
     RG_CHECK_ARG(n_pass == 1 || !(a.flags & FLAG_REUSE_POINTS), "RG_FLAG_REUSE_POINTS needs a call that fits one pass");
-    const bool piped = c->opt_pipeline && !(a.flags & FLAG_REUSE_POINTS) && (outer != 0 || n_pass > 1);
-    for (int k = 0; k < n_pass; ++k) {
-        const int pipe = !piped ? 0 : ((k == n_pass - 1 && outer != 1) ? 2 : 1);
-        if (n_pass == 1) {
-            rc = f_pass(c, st, a, pipe);
-        } else {
-            FCall s = f_sub_call(a, bounds[k], bounds[k + 1], po, ho);
-            rc = f_pass(c, st, s, pipe);
-        }
-        if (rc) {                                     // leave no tail behind an error return
-            if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
-            c->tail_pending[0] = c->tail_pending[1] = false;
-            return rc;
+    if (n_pass > 1 && c->opt_pipeline) {
+        std::vector<PassCtl> jobs(n_pass);
+        for (int k = 0; k < n_pass; ++k) jobs[k].a = f_sub_call(a, bounds[k], bounds[k + 1], jobs[k].po, jobs[k].ho);
+        if ((rc = f_run_piped(c, st, jobs, true))) return rc;
+    } else {
+        for (int k = 0; k < n_pass; ++k) {
+            if (n_pass == 1) {
+                if ((rc = f_pass(c, st, a))) return rc;
+            } else {
+                FCall s = f_sub_call(a, bounds[k], bounds[k + 1], po, ho);
+                if ((rc = f_pass(c, st, s))) return rc;
+            }
         }
     }
     c->last_passes = n_pass;
-    if (outer == 0) {
-        if ((rc = pipe_join(c, st))) return rc;
-        RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
-    }
+    RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     return RG_OK;
 }
 
@@ -685,8 +772,8 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     // the inlier masks of pass k travel back on a third stream while pass k+1 is scored (205 MB for the config-5 sweep:
     // 3.7 ms at the end of the call otherwise)
     const bool stream_masks = mask != nullptr && S > 1;
-    // sub-batches pipelined with each other (their tails on the tail stream) unless per-hypothesis results are copied out
-    // after every sub-batch, which needs the tail finished anyway
+    // sub-batches pipelined with each other over two streams unless per-hypothesis results are copied out after every
+    // sub-batch (which needs that sub-batch finished anyway)
     const bool piped = S > 1 && c->opt_pipeline && !(counts || F_all || flags);
     if (stream_masks) {
         if (!c->d2h_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -723,7 +810,37 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
     std::vector<int> po, ho;
     rc = RG_OK;
     long long launches = 0;
-    for (int k = 0; k < S && rc == RG_OK; ++k) {
+    if (piped) {
+        // every sub-batch is one pass (the bounds come from f_pass_bounds and were only refined); the passes are pipelined
+        // over two streams (f_run_piped): heads wait for their own upload, mask downloads hang on the tails
+        std::vector<PassCtl> jobs;
+        std::vector<int> job_batch;
+        jobs.reserve(S);
+        for (int k = 0; k < S; ++k) {
+            if (bounds[k + 1] == bounds[k]) continue;
+            jobs.emplace_back();
+            PassCtl& j = jobs.back();
+            j.a = f_sub_call(a, bounds[k], bounds[k + 1], j.po, j.ho);
+            j.ready = c->pass_ready[k];
+            j.done = stream_masks ? c->pass_done[k] : nullptr;
+            job_batch.push_back(k);
+        }
+        c->last_stats[7] = 0;
+        if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
+        if ((rc = ensure_pinned(c->h_stats, sizeof(unsigned long long) * 8))) return rc;
+        RG_CUDA(cudaMemsetAsync(c->stats.ptr, 0, sizeof(unsigned long long) * 8, st));
+        rc = f_run_piped(c, st, jobs, false);
+        launches = c->last_stats[7];
+        if (rc == RG_OK && stream_masks) {
+            for (int k : job_batch) {
+                const size_t n0 = (size_t)pair_off[bounds[k]], n1 = (size_t)pair_off[bounds[k + 1]];
+                RG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->pass_done[k], 0));
+                if (n1 > n0)
+                    RG_CUDA(cudaMemcpyAsync(mask + n0, (unsigned char*)c->d_out_c.ptr + n0, n1 - n0, cudaMemcpyDeviceToHost, c->d2h_stream));
+            }
+        }
+    }
+    for (int k = 0; k < S && rc == RG_OK && !piped; ++k) {
         const int p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 == p0) continue;
         const size_t h0 = (size_t)hyp_off[p0];
@@ -733,7 +850,7 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
             rc = f_ransac_dev(c, st, a);
         } else {
             FCall s = f_sub_call(a, p0, p1, po, ho);
-            rc = f_ransac_dev(c, st, s, piped ? (k == S - 1 ? 2 : 1) : 0);
+            rc = f_ransac_dev(c, st, s);
         }
         c->accumulate_stats = false;
         launches += c->last_stats[7];
@@ -750,8 +867,7 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         if (flags && Hk) RG_CUDA(cudaMemcpyAsync(flags + h0, c->flags.ptr, Hk, cudaMemcpyDeviceToHost, st));
         if (stream_masks) {
             const size_t n0 = (size_t)pair_off[p0], n1 = (size_t)pair_off[p1];
-            // (pipelined: the masks of this sub-batch are complete when the tail stream gets here — f_mask is the last tail kernel)
-            RG_CUDA(cudaEventRecord(c->pass_done[k], piped ? c->tail_stream : st));
+            RG_CUDA(cudaEventRecord(c->pass_done[k], st));
             RG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->pass_done[k], 0));
             if (n1 > n0)
                 RG_CUDA(cudaMemcpyAsync(mask + n0, (unsigned char*)c->d_out_c.ptr + n0, n1 - n0, cudaMemcpyDeviceToHost, c->d2h_stream));
@@ -767,7 +883,7 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         if (stream_masks) cudaStreamSynchronize(c->d2h_stream);
         return rc;
     }
-    if (piped) {                                      // the sub-batches joined nothing and copied no statistics
+    if (piped) {                                      // join the last tail, then the statistics are final
         if ((rc = pipe_join(c, st))) return rc;
         RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     }
