@@ -331,8 +331,12 @@ def run_ours(args) -> None:
     e2e = evals_per_step * args.steps / (ms_e2e * 1e-3)
     passes = max(prof["calls"], 1)
     score_ms = prof["score_ms"] / passes                                    # one scorer launch = one pass
+    # passes differ in size (the first and the last pass of a call are cut into 1/8 .. 1/2 pieces: pipeline fill / drain), so the
+    # scorer's rate is total evaluations over total scorer time of the profiled passes = whole steps of this rank
+    steps_covered = passes / max(dev_stats["passes"], 1)
+    whole_steps = abs(steps_covered - round(steps_covered)) < 1e-9 and steps_covered >= 1    # false only beyond 2048 passes
     pairs_per_pass = sh.P / max(dev_stats["passes"], 1)
-    evals_per_pass = pairs_per_pass * N * H
+    evals_per_pass = pairs_per_pass * N * H                                 # average over the passes of a step
     achieved_tflops = FLOP_PER_F_EVAL * evals_per_pass / (score_ms * 1e-3) * 1e-12 if score_ms > 0 else None
     alg_bytes = pairs_per_pass * (16.0 * N + 64.0 * H + 4.0 * H)      # FP32 points + 64-byte hypothesis records + counts
     try:
@@ -398,11 +402,12 @@ def run_ours(args) -> None:
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "traffic_note": (traffic or {}).get("note"),
                          "kernel_ms_per_launch": score_ms, "launches_timed": passes,
+                         "launches_cover_whole_steps": bool(whole_steps),
                          "timed_with": "pass pipelining (option 10): head of pass k+1 and tail of pass k-1 run beside the scorer "
                                        "of pass k on a second stream",
                          "kernel_alone": {
                              "kernel_ms_per_launch": prof_serial["score_ms"] / max(prof_serial["calls"], 1),
-                             "frac": (FLOP_PER_F_EVAL * evals_per_pass / (prof_serial["score_ms"] / max(prof_serial["calls"], 1) * 1e-3)
+                             "frac": (FLOP_PER_F_EVAL * float(sh.P) * N * H / (prof_serial["score_ms"] * 1e-3)
                                       * 1e-12 / fp32_peak_tflops) if prof_serial["score_ms"] > 0 else None,
                              "ms_per_step_serial_passes": ms_serial,
                              "note": "one more step with option 10 = 0 (passes strictly in order on one stream), outside the "

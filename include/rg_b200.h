@@ -67,7 +67,7 @@ int rg_host_free(void* p);
  *            (results do not depend on it; the caller's stream sees the whole call complete either way) */
 int rg_set_option(void* ctx, int option, long long value);
 /* summed milliseconds of {prepare, solve, score kernel, fixup + repair, select} over the PASSES since the last read
- * (at most 256 passes are remembered; *out_calls = passes covered); synchronises `stream` */
+ * (at most 2048 passes are remembered; *out_calls = passes covered); synchronises `stream` */
 int rg_get_profile(void* ctx, void* stream, double* out_ms5, int* out_calls);
 
 /* Pipe micro-benchmarks on the context's device (roofline denominators for bench.py):

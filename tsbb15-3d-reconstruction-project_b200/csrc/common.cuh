@@ -253,7 +253,7 @@ struct Ctx {
     static constexpr int kProfPhases = 5;          // prepare, solve, score kernel, fixup+repair, select
     static constexpr int kProfScoreStart = 6;      // extra boundary: the scorer's own start (pipelined passes: the solver ended long before)
     static constexpr int kProfEvents = 7;          // boundaries 0..5 + the scorer start
-    static constexpr int kProfRing = 256;          // calls remembered between two reads
+    static constexpr int kProfRing = 2048;         // passes remembered between two reads (20 steps of a tapered 64-pass sweep)
     cudaEvent_t* prof_ev = nullptr;                // kProfRing * kProfEvents events
     int prof_cur = -1;                             // pass opened by the last prof_mark(.., 0) (sequential callers)
     int prof_calls = 0;                            // calls recorded in the ring since profiling was switched on / last read

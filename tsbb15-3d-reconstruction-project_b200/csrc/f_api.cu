@@ -479,6 +479,33 @@ static void f_pass_bounds(const Ctx* c, const FCall& a, std::vector<int>& bounds
     bounds.push_back(a.P);
 }
 
+// Pipeline fill and drain (f_run_piped): the head of the FIRST pass and the tail of the LAST one have no scorer to hide
+// behind (0.3 + 0.8 ms for a 64-pair config-5 pass, plus the last pass's mask download in the host entry point: 1 % of a
+// rank's step when eight GPUs share the sweep).  Cutting the last pass into 1/2, 1/4, 1/8, 1/8 of its pairs (the first one
+// into 1/8, 1/8, 1/4, 1/2) leaves an eighth exposed.  Used by the host entry point for the last pass (512-pair sweep end to
+// end 127.30 -> 126.68 ms; its first pass is already cut for the uploads).
+static void taper_pass(std::vector<int>& bounds, size_t i, bool toward_end) {
+    static const int off = [] { const char* e = getenv("RG_NO_TAPER"); return e ? atoi(e) : 0; }();       // experiment hook
+    const int p0 = bounds[i], n = bounds[i + 1] - bounds[i];
+    if (n < 2 || off) return;
+    std::vector<int> cuts;                            // interior boundaries, ascending
+    if (toward_end) {                                 // 1/2, 1/4, 1/8, 1/8
+        int done = 0;
+        for (int part = n / 2; part >= 1 && n - (done + part) >= 1 && cuts.size() < 3; part /= 2) {
+            done += part;
+            cuts.push_back(p0 + done);
+        }
+    } else {                                          // 1/8, 1/8, 1/4, 1/2
+        int part = std::max(1, n / 8), done = 0;
+        while (cuts.size() < 3 && done + part < n) {
+            done += part;
+            cuts.push_back(p0 + done);
+            if (cuts.size() >= 2) part *= 2;
+        }
+    }
+    bounds.insert(bounds.begin() + (long)i + 1, cuts.begin(), cuts.end());
+}
+
 // sub-call of pairs [p0, p1) with offsets rebased to the pass
 static FCall f_sub_call(const FCall& a, int p0, int p1, std::vector<int>& po, std::vector<int>& ho) {
     FCall s = a;
@@ -515,6 +542,8 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
     const int n_pass = (int)bounds.size() - 1;
     RG_CHECK_ARG(n_pass == 1 || !(a.flags & FLAG_REUSE_POINTS), "RG_FLAG_REUSE_POINTS needs a call that fits one pass");
     if (n_pass > 1 && c->opt_pipeline) {
+        // (no taper_pass here: on device-resident inputs the smaller passes cost the scorer more than the exposed head and
+        //  tail they save — 512-pair sweep 126.96 -> 127.32 ms, profiles/r02_taper.txt)
         std::vector<PassCtl> jobs(n_pass);
         for (int k = 0; k < n_pass; ++k) jobs[k].a = f_sub_call(a, bounds[k], bounds[k + 1], jobs[k].po, jobs[k].ho);
         if ((rc = f_run_piped(c, st, jobs, true))) return rc;
@@ -528,7 +557,7 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
             }
         }
     }
-    c->last_passes = n_pass;
+    c->last_passes = (int)bounds.size() - 1;
     RG_CUDA(cudaMemcpyAsync(c->h_stats.ptr, c->stats.ptr, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     return RG_OK;
 }
@@ -759,6 +788,8 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
             for (int k = 1; k <= S; ++k) bounds.push_back(first + (int)((long long)(P - first) * (k - 1) / (S - 1)));
         }
     }
+    if (bounds.size() >= 4 && c->opt_pipeline && !(counts || F_all || flags) && !c->opt_profile && c->opt_host_slices == 0)
+        taper_pass(bounds, bounds.size() - 2, true);  // drain of the pass pipeline (the fill is the upload split above)
     const int S = (int)bounds.size() - 1;
     if (!c->copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->copy_gate) RG_CUDA(cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming));
