@@ -244,8 +244,11 @@ score_packed(const float4* __restrict__ pts32, const typename Pol::Rec* __restri
                     const float4* gp = wp + g * (kSub / 2) * kV;
 #pragma unroll kPairUnroll
                     for (int j = 0; j < kSub / 2; ++j) Pol::template evalN<kHypPerThread>(Hy, gp + j * kV, cnt, ma);
+                    const unsigned bit = 1u << g;             // uniform: the shift stays in the uniform datapath
 #pragma unroll
-                    for (int k = 0; k < kHypPerThread; ++k) flag[k] |= (ma[k] <= G[k] ? 1u : 0u) << g;
+                    for (int k = 0; k < kHypPerThread; ++k)   // (NaN: no flag) FSETP + predicated LOP3; plain C++ compiles to FSETP + SEL + SHF + LOP3
+                        asm("{\n.reg .pred p;\nsetp.le.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}"
+                            : "+r"(flag[k]) : "f"(ma[k]), "f"(G[k]), "r"(bit));
                 }
 #pragma unroll
                 for (int k = 0; k < kHypPerThread; ++k)
