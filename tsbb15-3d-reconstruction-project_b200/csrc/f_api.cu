@@ -210,6 +210,10 @@ struct PassCtl {
     int prof_call = -1;                   // ring index of the pass's phase events (option 1)
     cudaEvent_t ready = nullptr;          // optional: the pass's inputs have arrived (host entry point)
     cudaEvent_t done = nullptr;           // optional: recorded behind the pass's last tail kernel
+    // optional: a copy queued on out_stream behind `done` as soon as the pass's tail is queued (host entry point: the pass's
+    // inlier masks travel back while later passes are scored; queued after all passes instead, a 64-pass call had its host
+    // thread stuck in the driver's launch queue and every mask download ended up behind the last scorer)
+    cudaStream_t out_stream = nullptr; void* out_dst = nullptr; const void* out_src = nullptr; size_t out_bytes = 0;
 };
 
 // counts / work counter / flag list are already cleared by the pass's memset
@@ -434,6 +438,10 @@ static int f_run_piped(Ctx* c, cudaStream_t st, std::vector<PassCtl>& jobs, bool
         ws_use(c, j.slot);
         if ((rc = f_pass_tail(c, side, j, k + 1 < n))) return fail(rc);
         if (j.done) RG_CUDA(cudaEventRecord(j.done, side));
+        if (j.done && j.out_stream && j.out_bytes) {
+            RG_CUDA(cudaStreamWaitEvent(j.out_stream, j.done, 0));
+            RG_CUDA(cudaMemcpyAsync(j.out_dst, j.out_src, j.out_bytes, cudaMemcpyDeviceToHost, j.out_stream));
+        }
     }
     RG_CUDA(cudaEventRecord(c->tail_done[0], side));
     c->tail_pending[0] = true;
@@ -479,33 +487,6 @@ static void f_pass_bounds(const Ctx* c, const FCall& a, std::vector<int>& bounds
     bounds.push_back(a.P);
 }
 
-// Pipeline fill and drain (f_run_piped): the head of the FIRST pass and the tail of the LAST one have no scorer to hide
-// behind (0.3 + 0.8 ms for a 64-pair config-5 pass, plus the last pass's mask download in the host entry point: 1 % of a
-// rank's step when eight GPUs share the sweep).  Cutting the last pass into 1/2, 1/4, 1/8, 1/8 of its pairs (the first one
-// into 1/8, 1/8, 1/4, 1/2) leaves an eighth exposed.  Used by the host entry point for the last pass (512-pair sweep end to
-// end 127.30 -> 126.68 ms; its first pass is already cut for the uploads).
-static void taper_pass(std::vector<int>& bounds, size_t i, bool toward_end) {
-    static const int off = [] { const char* e = getenv("RG_NO_TAPER"); return e ? atoi(e) : 0; }();       // experiment hook
-    const int p0 = bounds[i], n = bounds[i + 1] - bounds[i];
-    if (n < 2 || off) return;
-    std::vector<int> cuts;                            // interior boundaries, ascending
-    if (toward_end) {                                 // 1/2, 1/4, 1/8, 1/8
-        int done = 0;
-        for (int part = n / 2; part >= 1 && n - (done + part) >= 1 && cuts.size() < 3; part /= 2) {
-            done += part;
-            cuts.push_back(p0 + done);
-        }
-    } else {                                          // 1/8, 1/8, 1/4, 1/2
-        int part = std::max(1, n / 8), done = 0;
-        while (cuts.size() < 3 && done + part < n) {
-            done += part;
-            cuts.push_back(p0 + done);
-            if (cuts.size() >= 2) part *= 2;
-        }
-    }
-    bounds.insert(bounds.begin() + (long)i + 1, cuts.begin(), cuts.end());
-}
-
 // sub-call of pairs [p0, p1) with offsets rebased to the pass
 static FCall f_sub_call(const FCall& a, int p0, int p1, std::vector<int>& po, std::vector<int>& ho) {
     FCall s = a;
@@ -542,8 +523,9 @@ static int f_ransac_dev(Ctx* c, cudaStream_t st, const FCall& a) {
     const int n_pass = (int)bounds.size() - 1;
     RG_CHECK_ARG(n_pass == 1 || !(a.flags & FLAG_REUSE_POINTS), "RG_FLAG_REUSE_POINTS needs a call that fits one pass");
     if (n_pass > 1 && c->opt_pipeline) {
-        // (no taper_pass here: on device-resident inputs the smaller passes cost the scorer more than the exposed head and
-        //  tail they save — 512-pair sweep 126.96 -> 127.32 ms, profiles/r02_taper.txt)
+        // (cutting the first / last pass into 1/8 .. 1/2 pieces to shorten the exposed head and tail was tried: the smaller
+        //  passes cost the scorer as much as they save — 512-pair sweep 126.96 -> 127.32 ms resident, full sweep end to end
+        //  987.1 -> 988.6 ms; profiles/r02_taper.txt)
         std::vector<PassCtl> jobs(n_pass);
         for (int k = 0; k < n_pass; ++k) jobs[k].a = f_sub_call(a, bounds[k], bounds[k + 1], jobs[k].po, jobs[k].ho);
         if ((rc = f_run_piped(c, st, jobs, true))) return rc;
@@ -788,8 +770,6 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
             for (int k = 1; k <= S; ++k) bounds.push_back(first + (int)((long long)(P - first) * (k - 1) / (S - 1)));
         }
     }
-    if (bounds.size() >= 4 && c->opt_pipeline && !(counts || F_all || flags) && !c->opt_profile && c->opt_host_slices == 0)
-        taper_pass(bounds, bounds.size() - 2, true);  // drain of the pass pipeline (the fill is the upload split above)
     const int S = (int)bounds.size() - 1;
     if (!c->copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->copy_gate) RG_CUDA(cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming));
@@ -845,7 +825,6 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         // every sub-batch is one pass (the bounds come from f_pass_bounds and were only refined); the passes are pipelined
         // over two streams (f_run_piped): heads wait for their own upload, mask downloads hang on the tails
         std::vector<PassCtl> jobs;
-        std::vector<int> job_batch;
         jobs.reserve(S);
         for (int k = 0; k < S; ++k) {
             if (bounds[k + 1] == bounds[k]) continue;
@@ -853,8 +832,12 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
             PassCtl& j = jobs.back();
             j.a = f_sub_call(a, bounds[k], bounds[k + 1], j.po, j.ho);
             j.ready = c->pass_ready[k];
-            j.done = stream_masks ? c->pass_done[k] : nullptr;
-            job_batch.push_back(k);
+            if (stream_masks) {
+                const size_t n0 = (size_t)pair_off[bounds[k]], n1 = (size_t)pair_off[bounds[k + 1]];
+                j.done = c->pass_done[k];
+                j.out_stream = c->d2h_stream;
+                j.out_dst = mask + n0; j.out_src = (const unsigned char*)c->d_out_c.ptr + n0; j.out_bytes = n1 - n0;
+            }
         }
         c->last_stats[7] = 0;
         if ((rc = ensure(c->stats, sizeof(unsigned long long) * 8))) return rc;
@@ -862,14 +845,6 @@ int rg_f_ransac_host2(void* ctx, void* stream, int P, const double* pts64, const
         RG_CUDA(cudaMemsetAsync(c->stats.ptr, 0, sizeof(unsigned long long) * 8, st));
         rc = f_run_piped(c, st, jobs, false);
         launches = c->last_stats[7];
-        if (rc == RG_OK && stream_masks) {
-            for (int k : job_batch) {
-                const size_t n0 = (size_t)pair_off[bounds[k]], n1 = (size_t)pair_off[bounds[k + 1]];
-                RG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->pass_done[k], 0));
-                if (n1 > n0)
-                    RG_CUDA(cudaMemcpyAsync(mask + n0, (unsigned char*)c->d_out_c.ptr + n0, n1 - n0, cudaMemcpyDeviceToHost, c->d2h_stream));
-            }
-        }
     }
     for (int k = 0; k < S && rc == RG_OK && !piped; ++k) {
         const int p0 = bounds[k], p1 = bounds[k + 1];
