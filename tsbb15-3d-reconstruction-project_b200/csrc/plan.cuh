@@ -10,7 +10,7 @@ namespace rg {
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Fill the PairInfo table (integer part) on the host and upload it.  Work items of the packed scorer:
-// item = (pair, 512-hypothesis block, contiguous range of kSub-point groups), claimed dynamically by the persistent grid.
+// item = (pair, kHypPerBlock-hypothesis block, contiguous range of kSub-point groups), claimed dynamically by the persistent grid.
 // resident blocks per SM of a persistent scorer instantiation (queried once; also sets the dynamic smem attribute)
 // (cached per DEVICE: cudaFuncSetAttribute is a per-device function attribute, and one process may drive several GPUs)
 template <class Pol>
@@ -101,7 +101,7 @@ inline int f_plan(Ctx* c, cudaStream_t st, int P, const int* pair_off, const int
     const long long grid = (long long)c->sm_count * blocks_per_sm;
     // Items are claimed dynamically, so what matters is (a) enough items per resident block that the tail is short and
     // (b), for SMALL batches (one pair split over GPUs: a few hundred items), an item count that fills whole rounds of the
-    // grid: 784 equal items on 444 resident blocks take two rounds (88 % busy), 444 take one.  Aim for ~kItemsPerBlock
+    // grid: 784 equal items on 592 resident blocks take two rounds (66 % busy), 592 take one.  Aim for ~kItemsPerBlock
     // items per block, never below 16 groups (128 points) per item, then search the neighbourhood of that size for the
     // split whose rounded-up rounds waste the least (uniform batches; ragged ones take the target as is).  Since the
     // guard-band flags went from a bitmap to a list, item boundaries may fall on any group.

@@ -23,7 +23,7 @@ namespace rg {
 constexpr int kScoreThreads = RG_SCORE_THREADS;
 constexpr int kScoreBlocksPerSM = RG_SCORE_BLOCKS;
 constexpr int kHypPerThread = RG_HPT;
-constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 512 hypotheses per work item
+constexpr int kHypPerBlock  = kScoreThreads * kHypPerThread;   // 256 hypotheses per work item
 constexpr int kStages       = 2;
 constexpr int kPairUnroll   = RG_PAIR_UNROLL;
 
@@ -135,7 +135,7 @@ template <class Pol>
 constexpr size_t score_smem_bytes() { return kStages * sizeof(ScoreStage<Pol>) + 64; }
 
 // persistent block: first item blockIdx.x, then items claimed from a global counter (dynamic: with static round-robin a
-// batch whose item count is not a multiple of the grid leaves most SMs idle during the last round); every item = 512
+// batch whose item count is not a multiple of the grid leaves most SMs idle during the last round); every item = kHypPerBlock
 // hypotheses x a contiguous range of kSub-point groups of one pair.  Host guarantees every item has >= 1 group and >= 1
 // hypothesis; *work_counter is 0 at launch.
 // Points and (at the first chunk of an item) hypothesis records arrive by 1-D bulk TMA on one mbarrier per stage;
